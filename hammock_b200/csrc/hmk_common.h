@@ -1,0 +1,105 @@
+// hmk_common.h -- shared host/device primitives of the B200 greedy-clustering engine.
+//
+// Compiles under nvcc (device + host) and under plain g++ (tests/emu builds the resolver
+// logic for the CPU so that the speculate+repair control flow can be checked against the
+// oracle at full scale without a GPU; that harness is test-only and is not part of
+// libhammock_b200.so).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HMK_HD __host__ __device__ __forceinline__
+#else
+#define HMK_HD inline
+#endif
+
+#define HMK_NRES 24
+#define HMK_JMIN ((int32_t)0x80000000)
+#define HMK_JMAX ((int32_t)0x7fffffff)
+
+// Java int arithmetic wraps
+HMK_HD int32_t hmk_wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+HMK_HD int32_t hmk_wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+
+// Scalar gapless all-offset score S(seq1, seq2) == ShiftedScorer.sequenceScore(seq1, seq2)
+// (reference ShiftedScorer.java:48-100).  seq1 = member of the database cluster, seq2 = the
+// compared (query) sequence at every call site of the greedy path
+// (ClinkageClusterScorer.java:38).  Formulated per diagonal k = (position in longer) -
+// (position in shorter); equal lengths make the SECOND argument the "shorter" one.
+// Requires max_shift < shorter length (checked by the caller -> status 1).
+HMK_HD int32_t hmk_pair_score(const uint8_t* seq1, int len1, const uint8_t* seq2, int len2,
+                              const int32_t* M, int X, int P) {
+    const uint8_t* s;
+    const uint8_t* l;
+    int ls, ll;
+    if (len1 >= len2) { s = seq2; ls = len2; l = seq1; ll = len1; }
+    else              { s = seq1; ls = len1; l = seq2; ll = len2; }
+    const int d = ll - ls;
+    int32_t best = HMK_JMIN;
+    for (int k = -X; k <= X + d; k++) {
+        // longer index j pairs with shorter index j-k
+        int j0 = k > 0 ? k : 0;
+        int j1 = ls + k < ll ? ls + k : ll;
+        int32_t sc = 0;
+        for (int j = j0; j < j1; j++) sc = hmk_wadd(sc, M[s[j - k] * HMK_NRES + l[j]]);
+        sc = hmk_wadd(sc, hmk_wmul(d, P));
+        if (k < 0) sc = hmk_wadd(sc, hmk_wmul(-2 * k, P));
+        if (k > d) sc = hmk_wadd(sc, hmk_wmul(2 * (k - d), P));
+        if (sc > best) best = sc;
+    }
+    return best;
+}
+
+// cells / shifts summed by one pair score -- work accounting only
+HMK_HD int64_t hmk_pair_cells(int len1, int len2, int X) {
+    int ls = len1 < len2 ? len1 : len2, ll = len1 < len2 ? len2 : len1;
+    int d = ll - ls;
+    int64_t cells = 0;
+    for (int k = -X; k <= X + d; k++) {
+        int j0 = k > 0 ? k : 0;
+        int j1 = ls + k < ll ? ls + k : ll;
+        if (j1 > j0) cells += j1 - j0;
+    }
+    return cells;
+}
+
+// Best-hit key for the singleton (partner) search: bigger key == preferred candidate under
+// NearestClusterRunner's order (score desc, size desc, id asc;
+// ClinkageSequenceClusterer.java:258-293).  `tierank` is the candidate's rank under
+// (abundance desc, id asc); it equals the id when the input is abundance-sorted.
+HMK_HD uint64_t hmk_key_make(int32_t score, uint32_t tierank) {
+    return ((uint64_t)((uint32_t)score ^ 0x80000000u) << 32) | (uint64_t)(uint32_t)(~tierank);
+}
+HMK_HD int32_t hmk_key_score(uint64_t key) { return (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u); }
+HMK_HD uint32_t hmk_key_rank(uint64_t key) { return ~(uint32_t)key; }
+
+// status codes of the engine / C ABI (include/hammock_b200.h)
+enum {
+    HMK_OK = 0,
+    HMK_ERR_SHIFT_TOO_BIG = 1,  // DataException "Shift too big" (ShiftedScorer.java:59-62)
+    HMK_ERR_NULL_CLUSTER = 2,   // NullPointerException (LimitedGreedySequenceClusterer.java:104,108)
+    HMK_ERR_BAD_RESIDUE = 3,    // residue code >= 24 (UniqueSequence.java:51-54)
+    HMK_ERR_CUDA = 4,           // CUDA / NCCL failure; there is no CPU fallback
+    HMK_ERR_BAD_ARG = 5
+};
+
+// phase-1 resolver exit reasons (device -> host, per batch)
+enum {
+    HMK_P1_CONTINUE = 0,  // batch fully consumed, more work
+    HMK_P1_DONE = 1,      // K clusters reached or list exhausted
+    HMK_P1_NPE = 2,       // reference would throw NullPointerException at this step
+    HMK_P1_RESTART = 3    // partner list exhausted but truncated: rescore from ctl.cur
+};
+
+struct HmkCtl {
+    int32_t cur;           // first id not yet visited by phase 1
+    int32_t ncl;           // multi-member clusters so far (actualClusters.size())
+    int32_t unproc_alive;  // initialList.size() - index
+    int32_t status;        // HMK_P1_*
+    int32_t npe_step;
+    int32_t steps, joins, creates, orphans;
+    int32_t restarts;
+    int32_t pad0, pad1;
+    int64_t scalar_pairs;  // pair scores computed one at a time (resolvers, member checks)
+    int64_t scalar_cells;
+};

@@ -1,0 +1,843 @@
+// hmk_engine.cu -- host driver of the B200 greedy-clustering engine + the C ABI
+// (include/hammock_b200.h).  Replaces LimitedGreedySequenceClusterer.cluster()
+// (reference LimitedGreedySequenceClusterer.java:39-69) and everything below it.
+//
+// Structure of one run (all state device-resident, one CUDA stream):
+//   phase 1  batches of B abundance-ordered queries:
+//              select -> profiles -> bulk partner search (top-k per query over all later
+//              singletons) -> founder filter + member check (cluster search) -> intra-batch
+//              scores -> in-order resolver (one warp, reference order)
+//   phase 2  founder profiles -> bulk founder filter over all remaining singletons ->
+//              member check -> candidate lists sorted by query and by cluster ->
+//              wavefront rounds that resolve queries in reference order
+// There is no CPU fallback: every scoring and every decision happens in CUDA kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hammock_b200.h"
+#include "hmk_kernels.cuh"
+
+namespace {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                            ":" + std::to_string(__LINE__) + ")");                                \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void reserve(size_t n) {   // contents are NOT preserved
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        cap = n;
+    }
+    void grow_keep(size_t n, size_t used, cudaStream_t st) {
+        if (n <= cap) return;
+        T* q = nullptr;
+        CK(cudaMalloc(&q, n * sizeof(T)));
+        if (p && used) CK(cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        if (p) CK(cudaFree(p));
+        p = q;
+        cap = n;
+    }
+};
+
+struct Options {
+    int64_t batch = 192;        // phase-1 queries per batch
+    int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
+    int64_t kb = 8;             // partner candidates kept per query
+    int64_t waves = 2;          // CTAs per SM targeted by the stripe split
+    int64_t p2_chunk = 1 << 18; // phase-2 queries per founder-filter launch
+    int64_t hit_cap = 1 << 22;  // initial founder-hit capacity
+    int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
+    int64_t profile = 0;        // 1: time every bulk launch with CUDA events
+    int64_t round_check = 4;    // phase-2 rounds between host checks
+};
+
+class Engine {
+public:
+    explicit Engine(int device) : device_(device) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0)
+            throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                            "); libhammock_b200 has no CPU fallback");
+        if (device < 0 || device >= count) throw CudaError("invalid CUDA device index");
+        CK(cudaSetDevice(device_));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device_));
+        sm_count_ = prop.multiProcessorCount;
+        smem_optin_ = prop.sharedMemPerBlockOptin;
+        CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        CK(cudaMallocHost(&h_ctl_, sizeof(HmkCtl)));
+        CK(cudaMallocHost(&h_scalars_, 16 * sizeof(int32_t)));
+        CK(cudaEventCreate(&ev_a_));
+        CK(cudaEventCreate(&ev_b_));
+        CK(cudaEventCreate(&ev_c_));
+    }
+    ~Engine() {
+        cudaSetDevice(device_);
+        for (auto& e : ev_pool_) cudaEventDestroy(e);
+        if (ev_a_) cudaEventDestroy(ev_a_);
+        if (ev_b_) cudaEventDestroy(ev_b_);
+        if (ev_c_) cudaEventDestroy(ev_c_);
+        if (h_ctl_) cudaFreeHost(h_ctl_);
+        if (h_scalars_) cudaFreeHost(h_scalars_);
+        if (st_) cudaStreamDestroy(st_);
+    }
+
+    Options opt;
+
+    void upload(const hmk_greedy_in* in);
+    int run();
+    void download(hmk_greedy_out* out);
+    void score_block(const int32_t* first, int32_t nf, const int32_t* second, int32_t ns, int32_t* scores);
+    hmk_stats stats{};
+    int error_step = -1;
+
+private:
+    // ---- problem
+    int device_;
+    int sm_count_ = 148;
+    size_t smem_optin_ = 0;
+    cudaStream_t st_ = nullptr;
+    int32_t n_ = 0, T_ = 0, X_ = 0, P_ = 0, K_ = 0;
+    int32_t min_len_ = 0, max_len_ = 0;
+    bool uploaded_ = false, ran_ = false, bad_residue_ = false;
+    bool fast_ = false;
+    HmkScheme sc_{};
+    std::vector<int32_t> h_off_;
+    DevBuf<uint8_t> d_res_;
+    DevBuf<int32_t> d_off_, d_ab_, d_M_, d_tierank_, d_id_of_rank_;
+    DevBuf<uint64_t> d_packed_;
+    bool identity_rank_ = true;
+    // ---- clustering state
+    DevBuf<int32_t> d_slot_, d_rank_, d_next_, d_cf_, d_cs_, d_cc_, d_ct_;
+    DevBuf<HmkCtl> d_ctl_;
+    HmkCtl* h_ctl_ = nullptr;
+    int32_t* h_scalars_ = nullptr;
+    // ---- phase-1 scratch
+    DevBuf<int32_t> d_qid_, d_nq_, d_tk_cnt_, d_tk_ovf_, d_bk_cnt_, d_bk_ovf_, d_ib_, d_bm_slot_, d_bm_ref_,
+        d_nf_b_, d_nf_slot_, d_ac_head_, d_ac_next_, d_ac_slot_, d_ac_score_;
+    DevBuf<uint64_t> d_tk_key_, d_bk_key_;
+    DevBuf<uint32_t> d_prof_;
+    DevBuf<int4> d_hits_;
+    DevBuf<unsigned int> d_counts_;   // [0] hit_count, [1] cand_count
+    DevBuf<unsigned long long> d_pairctr_;
+    // ---- phase-2 scratch
+    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cc_q_, d_qstart_, d_cstart_,
+        d_head_a_, d_head_b_, d_dyn_, d_dyn_n_, d_flags_;
+    DevBuf<unsigned long long> d_key_q_, d_key_c_, d_key_tmp_;
+    DevBuf<unsigned char> d_cub_;
+    DevBuf<uint32_t> d_fprof_;
+    // ---- outputs
+    DevBuf<int32_t> d_cluster_id_, d_member_rank_;
+    int32_t n_unassigned_ = 0;
+    // ---- timing
+    cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
+    std::vector<cudaEvent_t> ev_pool_;
+    size_t ev_used_ = 0;
+    int launches_ = 0, bulk_launches_ = 0;
+    int64_t bulk_pairs_host_ = 0;
+
+    HmkState state() {
+        HmkState S;
+        S.n = n_; S.res = d_res_.p; S.off = d_off_.p; S.ab = d_ab_.p; S.M = d_M_.p;
+        S.T = T_; S.X = X_; S.P = P_; S.K = K_;
+        S.id_of_rank = identity_rank_ ? nullptr : d_id_of_rank_.p;
+        S.slot = d_slot_.p; S.rank = d_rank_.p; S.next = d_next_.p;
+        S.c_founder = d_cf_.p; S.c_size = d_cs_.p; S.c_count = d_cc_.p; S.c_tail = d_ct_.p;
+        S.ctl = d_ctl_.p;
+        return S;
+    }
+    void choose_scheme(const int32_t* M);
+    int qt_max() const;
+    void launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof);
+    void launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query);
+    cudaEvent_t next_event();
+    void fetch_ctl() {
+        CK(cudaMemcpyAsync(h_ctl_, d_ctl_.p, sizeof(HmkCtl), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+    }
+    int phase1();
+    void phase2();
+    int compact_unassigned(int32_t* out);
+    void sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_bits);
+};
+
+// ---------------------------------------------------------------- upload
+void Engine::choose_scheme(const int32_t* M) {
+    fast_ = false;
+    sc_ = HmkScheme{};
+    sc_.L = max_len_; sc_.X = X_; sc_.P = P_; sc_.T = T_;
+    if (opt.force_generic) return;
+    if (n_ <= 0 || min_len_ != max_len_ || max_len_ < 1 || max_len_ > HMK_MAXL1) return;
+    if (X_ < 0 || X_ >= max_len_) return;
+    int64_t mmin = M[0], mmax = M[0];
+    for (int i = 0; i < HMK_NRES * HMK_NRES; i++) { mmin = std::min<int64_t>(mmin, M[i]); mmax = std::max<int64_t>(mmax, M[i]); }
+    const int64_t bias = mmin < 0 ? -mmin : 0;
+    const int lanes = 2 * X_ + 1;
+    for (int lane16 = 0; lane16 <= 1; lane16++) {
+        const int64_t half = lane16 ? 32768 : 128, top = lane16 ? 65535 : 255;
+        const int nw = lane16 ? (lanes + 1) / 2 : (lanes + 3) / 4;
+        if (nw > 4) continue;
+        bool ok = true;
+        for (int k = -X_; k <= X_ && ok; k++) {
+            const int64_t ak = k < 0 ? -k : k, nk = max_len_ - ak;
+            const int64_t init = 2 * (int64_t)P_ * ak + half - (int64_t)T_ - nk * bias;
+            const int64_t hi = init + nk * (mmax + bias);
+            if (init < 0 || hi > top || init > top) ok = false;
+        }
+        if (!ok) continue;
+        fast_ = true;
+        sc_.nw = nw; sc_.lane16 = lane16; sc_.bias = (int32_t)bias; sc_.half = (int32_t)half;
+        sc_.prof_words = nw * HMK_MAXL1 * HMK_NRES;
+        return;
+    }
+}
+
+void Engine::upload(const hmk_greedy_in* in) {
+    CK(cudaSetDevice(device_));
+    if (!in || in->n < 0 || (in->n > 0 && (!in->residues || !in->offsets || !in->abundance)) || !in->matrix)
+        throw std::invalid_argument("hmk_upload: null input");
+    n_ = in->n; T_ = in->threshold; X_ = in->max_shift; P_ = in->shift_penalty; K_ = in->max_clusters;
+    h_off_.assign(in->offsets, in->offsets + n_ + 1);
+    const size_t total = n_ ? (size_t)h_off_[n_] : 0;
+    min_len_ = n_ ? INT32_MAX : 0; max_len_ = 0;
+    for (int i = 0; i < n_; i++) {
+        int l = h_off_[i + 1] - h_off_[i];
+        if (l < 0) throw std::invalid_argument("hmk_upload: offsets not monotone");
+        min_len_ = std::min(min_len_, l); max_len_ = std::max(max_len_, l);
+    }
+    d_res_.reserve(total + 16); d_off_.reserve(n_ + 1); d_ab_.reserve(n_); d_M_.reserve(HMK_NRES * HMK_NRES);
+    if (total) CK(cudaMemcpyAsync(d_res_.p, in->residues, total, cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_off_.p, h_off_.data(), sizeof(int32_t) * (n_ + 1), cudaMemcpyHostToDevice, st_));
+    if (n_) CK(cudaMemcpyAsync(d_ab_.p, in->abundance, sizeof(int32_t) * n_, cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_M_.p, in->matrix, sizeof(int32_t) * HMK_NRES * HMK_NRES, cudaMemcpyHostToDevice, st_));
+    // tie-break rank of the partner search: (abundance desc, id asc); identity when the
+    // input is abundance-sorted (order "size", UniqueSequence.java:180)
+    identity_rank_ = true;
+    for (int i = 1; i < n_; i++)
+        if (in->abundance[i] > in->abundance[i - 1]) { identity_rank_ = false; break; }
+    if (!identity_rank_) {
+        std::vector<int32_t> ids(n_), rk(n_);
+        std::iota(ids.begin(), ids.end(), 0);
+        const int32_t* ab = in->abundance;
+        std::stable_sort(ids.begin(), ids.end(), [ab](int32_t a, int32_t b) { return ab[a] > ab[b]; });
+        for (int i = 0; i < n_; i++) rk[ids[i]] = i;
+        d_tierank_.reserve(n_); d_id_of_rank_.reserve(n_);
+        CK(cudaMemcpyAsync(d_tierank_.p, rk.data(), sizeof(int32_t) * n_, cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(d_id_of_rank_.p, ids.data(), sizeof(int32_t) * n_, cudaMemcpyHostToDevice, st_));
+        CK(cudaStreamSynchronize(st_));
+    }
+    choose_scheme(in->matrix);
+    // validate residues + pack 5 bits/residue on the device
+    d_packed_.reserve(std::max(n_, 1));
+    d_flags_.reserve(8);
+    CK(cudaMemsetAsync(d_flags_.p, 0, 8 * sizeof(int32_t), st_));
+    if (n_) {
+        hmk_pack_sequences<<<(n_ + 255) / 256, 256, 0, st_>>>(n_, d_res_.p, d_off_.p, d_packed_.p, d_flags_.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(h_scalars_, d_flags_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    bad_residue_ = h_scalars_[0] != 0;
+    const int kc = std::max(K_, 1);
+    d_slot_.reserve(std::max(n_, 1)); d_rank_.reserve(std::max(n_, 1)); d_next_.reserve(std::max(n_, 1));
+    d_cf_.reserve(kc); d_cs_.reserve(kc); d_cc_.reserve(kc); d_ct_.reserve(kc);
+    d_ctl_.reserve(1); d_counts_.reserve(4); d_pairctr_.reserve(2);
+    d_cluster_id_.reserve(std::max(n_, 1)); d_member_rank_.reserve(std::max(n_, 1));
+    d_singles_.reserve(std::max(n_, 1)); d_blockcnt_.reserve((n_ + 1023) / 1024 + 1);
+    uploaded_ = true;
+    ran_ = false;
+}
+
+// ---------------------------------------------------------------- launch helpers
+cudaEvent_t Engine::next_event() {
+    if (ev_used_ == ev_pool_.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ev_pool_.push_back(e);
+    }
+    return ev_pool_[ev_used_++];
+}
+
+int Engine::qt_max() const {
+    if (opt.qt > 0) return (int)opt.qt;
+    const size_t pwb = (size_t)sc_.prof_words * 4;
+    const size_t per = pwb + (size_t)opt.kb * 8 + 8 + 12;
+    return (int)std::max<size_t>(1, (smem_optin_ - 64) / per);
+}
+
+void Engine::launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof) {
+    if (nq <= 0) return;
+    hmk_build_profiles<<<nq, 128, 0, st_>>>(sc_, mode, ids, nq, d_res_.p, d_off_.p, d_M_.p, prof);
+    CK(cudaGetLastError());
+    launches_++;
+}
+
+template <int NW, int MODE>
+static void launch_fast_inst(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    static size_t configured_smem = 0;
+    if (!configured || smem > configured_smem) {
+        CK(cudaFuncSetAttribute(hmk_bulk_fast<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+        configured_smem = smem;
+    }
+    hmk_bulk_fast<NW, MODE><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
+}
+
+template <int MODE>
+static void launch_fast_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    switch (a.sc.nw) {
+        case 1: launch_fast_inst<1, MODE>(a, grid, smem, st); break;
+        case 2: launch_fast_inst<2, MODE>(a, grid, smem, st); break;
+        case 3: launch_fast_inst<3, MODE>(a, grid, smem, st); break;
+        default: launch_fast_inst<4, MODE>(a, grid, smem, st); break;
+    }
+}
+
+template <int MODE>
+static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, cudaStream_t st) {
+    static size_t configured_smem = 0;
+    if (smem > configured_smem) {
+        CK(cudaFuncSetAttribute(hmk_bulk_generic<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_smem = smem;
+    }
+    hmk_bulk_generic<MODE><<<grid, 256, smem, st>>>(g);
+}
+
+// fills in the tiling fields of `a` (nqt, qt, nstripes, chunk) and launches
+void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query) {
+    if (a.nq <= 0 || a.ndb <= 0) return;
+    a.sc = sc_;
+    a.pair_counter = d_pairctr_.p;
+    a.kb = (int)opt.kb;
+    const int threads = fast_ ? HMK_BULK_THREADS : 256;
+    const int qmax = fast_ ? qt_max() : 128;
+    a.nqt = (a.nq + qmax - 1) / qmax;
+    a.qt = (a.nq + a.nqt - 1) / a.nqt;
+    int want = (int)((sm_count_ * opt.waves + a.nqt - 1) / a.nqt);
+    int max_stripes = (a.ndb + threads - 1) / threads;
+    a.nstripes = std::max(1, std::min(want, max_stripes));
+    a.chunk = (a.ndb + a.nstripes - 1) / a.nstripes;
+    a.chunk = (a.chunk + threads - 1) / threads * threads;
+    a.nstripes = (a.ndb + a.chunk - 1) / a.chunk;
+    if (mode == HMK_MODE_TOPK) {
+        const size_t slots = (size_t)a.nstripes * a.nq;
+        d_tk_key_.reserve(slots * a.kb); d_tk_cnt_.reserve(slots); d_tk_ovf_.reserve(slots);
+        a.tk_key = d_tk_key_.p; a.tk_cnt = d_tk_cnt_.p; a.tk_ovf = d_tk_ovf_.p;
+    }
+    const int grid = a.nqt * a.nstripes;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, st_)); }
+    if (fast_) {
+        size_t smem = (((size_t)a.qt * sc_.prof_words * 4 + 15) & ~(size_t)15) + 16 + (size_t)a.qt * a.kb * 8 +
+                      (size_t)a.qt * 8 + (size_t)a.qt * 12;
+        if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, st_);
+        else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, st_);
+        else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, st_);
+    } else {
+        HmkGenericArgs g;
+        g.b = a; g.prof_ids = prof_ids; g.prof_is_query = prof_is_query;
+        g.res = d_res_.p; g.off = d_off_.p; g.M = d_M_.p; g.maxlen = std::max(max_len_, 1);
+        size_t smem = HMK_NRES * HMK_NRES * 4 + (size_t)a.qt * 4 + 8 + (size_t)a.qt * a.kb * 8 + (size_t)a.qt * 8 +
+                      (size_t)a.qt * 12 + (size_t)a.qt * g.maxlen + 16;
+        if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(g, grid, smem, st_);
+        else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(g, grid, smem, st_);
+        else launch_generic_mode<HMK_MODE_DENSE>(g, grid, smem, st_);
+    }
+    CK(cudaGetLastError());
+    if (opt.profile) CK(cudaEventRecord(e1, st_));
+    launches_++;
+    bulk_launches_++;
+    if (mode == HMK_MODE_TOPK) {
+        d_bk_key_.reserve((size_t)a.nq * a.kb); d_bk_cnt_.reserve(a.nq); d_bk_ovf_.reserve(a.nq);
+        hmk_topk_merge<<<(a.nq * 32 + 255) / 256, 256, 0, st_>>>(a.nq, a.nstripes, a.kb, d_tk_key_.p, d_tk_cnt_.p,
+                                                                 d_tk_ovf_.p, d_bk_key_.p, d_bk_cnt_.p, d_bk_ovf_.p);
+        CK(cudaGetLastError());
+        launches_++;
+    }
+}
+
+int Engine::compact_unassigned(int32_t* out) {
+    if (n_ == 0) return 0;
+    const int nb = (n_ + 1023) / 1024;
+    hmk_count_unassigned<<<nb, 1024, 0, st_>>>(d_slot_.p, n_, d_blockcnt_.p);
+    hmk_scan_blocks<<<1, 32, 0, st_>>>(d_blockcnt_.p, nb, d_flags_.p + 4);
+    hmk_scatter_unassigned<<<nb, 1024, 0, st_>>>(d_slot_.p, n_, d_blockcnt_.p, out);
+    CK(cudaGetLastError());
+    launches_ += 3;
+    CK(cudaMemcpyAsync(h_scalars_ + 4, d_flags_.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    return h_scalars_[4];
+}
+
+void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_bits) {
+    // ancillary plumbing (grouping the sparse candidate list); CUB radix sort, in place via temporaries
+    d_key_tmp_.reserve(n);
+    d_cand_score2_.reserve(n);
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, d_key_tmp_.p, vals, d_cand_score2_.p, n, 0, key_bits, st_));
+    d_cub_.reserve(bytes);
+    CK(cub::DeviceRadixSort::SortPairs(d_cub_.p, bytes, keys, d_key_tmp_.p, vals, d_cand_score2_.p, n, 0, key_bits, st_));
+    CK(cudaMemcpyAsync(keys, d_key_tmp_.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToDevice, st_));
+    CK(cudaMemcpyAsync(vals, d_cand_score2_.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st_));
+    launches_ += 8;
+}
+
+// ---------------------------------------------------------------- phase 1
+int Engine::phase1() {
+    const int B = (int)std::max<int64_t>(1, opt.batch);
+    d_qid_.reserve(B); d_nq_.reserve(1);
+    d_ib_.reserve((size_t)B * B);
+    d_bm_slot_.reserve(2 * B); d_bm_ref_.reserve(2 * B); d_nf_b_.reserve(B); d_nf_slot_.reserve(B);
+    d_ac_head_.reserve(B);
+    if (fast_) d_prof_.reserve((size_t)B * sc_.prof_words);
+    size_t hit_cap = (size_t)opt.hit_cap;
+    d_hits_.reserve(hit_cap);
+    d_ac_next_.reserve(hit_cap); d_ac_slot_.reserve(hit_cap); d_ac_score_.reserve(hit_cap);
+    fetch_ctl();
+    while (h_ctl_->ncl < K_ && h_ctl_->unproc_alive > 0) {
+        const int nq = std::min(B, h_ctl_->unproc_alive);
+        const int cur = h_ctl_->cur, ncl = h_ctl_->ncl;
+        hmk_select_queries<<<1, 1024, 0, st_>>>(d_slot_.p, n_, d_ctl_.p, nq, d_qid_.p, d_nq_.p);
+        CK(cudaGetLastError());
+        launches_++;
+        if (fast_) launch_profiles(HMK_PROF_QUERY, d_qid_.p, nq, d_prof_.p);
+        // B: partner search over all later singletons
+        {
+            HmkBulkArgs a{};
+            a.prof = d_prof_.p; a.nq = nq;
+            a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = cur; a.ndb = n_ - cur;
+            a.slot = d_slot_.p; a.q_minid = d_qid_.p;
+            a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
+            if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, d_qid_.p, 1);
+            else {
+                d_bk_key_.reserve((size_t)nq * opt.kb); d_bk_cnt_.reserve(nq); d_bk_ovf_.reserve(nq);
+                CK(cudaMemsetAsync(d_bk_cnt_.p, 0, sizeof(int32_t) * nq, st_));
+                CK(cudaMemsetAsync(d_bk_ovf_.p, 0, sizeof(int32_t) * nq, st_));
+            }
+        }
+        // A: clusters whose founder scores >= T, then complete linkage over their members
+        CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
+        CK(cudaMemsetAsync(d_ac_head_.p, 0xff, sizeof(int32_t) * nq, st_));
+        if (ncl > 0) {
+            HmkBulkArgs a{};
+            a.prof = d_prof_.p; a.nq = nq;
+            a.packed = d_packed_.p; a.db_ids = d_cf_.p; a.db_begin = 0; a.ndb = ncl;
+            a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
+            launch_bulk(HMK_MODE_EMIT, a, d_qid_.p, 1);
+            HmkCheckArgs c{};
+            c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
+            c.hit_t_is_query = 1; c.qids = d_qid_.p;
+            c.ac_head = d_ac_head_.p; c.ac_next = d_ac_next_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p;
+            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)hit_cap; c.linked = 1;
+            hmk_member_check<<<sm_count_ * 2, 256, 0, st_>>>(c);
+            CK(cudaGetLastError());
+            launches_++;
+        }
+        // intra-batch scores S(member = q_b2, query = q_b)
+        {
+            HmkBulkArgs a{};
+            a.prof = d_prof_.p; a.nq = nq;
+            a.packed = d_packed_.p; a.db_ids = d_qid_.p; a.db_begin = 0; a.ndb = nq;
+            a.dense = d_ib_.p; a.dense_stride = nq;
+            launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
+        }
+        HmkP1Batch pb{};
+        pb.nq = nq; pb.qid = d_qid_.p; pb.kb = (int)opt.kb;
+        pb.bk_key = d_bk_key_.p; pb.bk_cnt = d_bk_cnt_.p; pb.bk_ovf = d_bk_ovf_.p;
+        pb.ac_head = d_ac_head_.p; pb.ac_next = d_ac_next_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
+        pb.ib = d_ib_.p; pb.ib_stride = nq;
+        pb.bm_slot = d_bm_slot_.p; pb.bm_ref = d_bm_ref_.p; pb.nf_b = d_nf_b_.p; pb.nf_slot = d_nf_slot_.p;
+        // the resolver must not run on truncated hit lists: checked on the host first
+        CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        if ((size_t)(uint32_t)h_scalars_[0] > hit_cap) {   // grow and redo this batch (state untouched)
+            hit_cap = (size_t)(uint32_t)h_scalars_[0] * 5 / 4 + 1024;
+            d_hits_.reserve(hit_cap); d_ac_next_.reserve(hit_cap); d_ac_slot_.reserve(hit_cap); d_ac_score_.reserve(hit_cap);
+            continue;
+        }
+        hmk_p1_resolve_kernel<<<1, 32, 0, st_>>>(state(), pb);
+        CK(cudaGetLastError());
+        launches_++;
+        stats.p1_batches++;
+        fetch_ctl();
+        if (h_ctl_->status == HMK_P1_NPE) { error_step = h_ctl_->npe_step; stats.error_step = error_step; return HMK_ERR_NULL_CLUSTER; }
+        if (h_ctl_->status == HMK_P1_DONE) break;
+    }
+    return HMK_OK;
+}
+
+// ---------------------------------------------------------------- phase 2
+void Engine::phase2() {
+    const int ncl = h_ctl_->ncl;
+    const int ns = compact_unassigned(d_singles_.p);
+    stats.p2_queries = ns;
+    if (ncl == 0 || ns == 0) return;
+    // founder profiles (member side), built once: founders are fixed during phase 2
+    if (fast_) {
+        d_fprof_.reserve((size_t)ncl * sc_.prof_words);
+        launch_profiles(HMK_PROF_MEMBER, d_cf_.p, ncl, d_fprof_.p);
+    }
+    size_t hit_cap = d_hits_.cap ? d_hits_.cap : (size_t)opt.hit_cap;
+    d_hits_.reserve(hit_cap);
+    size_t cand_cap = std::max<size_t>(1 << 20, (size_t)ns / 2);
+    d_key_q_.reserve(cand_cap); d_key_c_.reserve(cand_cap); d_cand_score_.reserve(cand_cap);
+    size_t ncand = 0;
+    CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
+    const int chunk = (int)std::max<int64_t>(1024, opt.p2_chunk);
+    for (int c0 = 0; c0 < ns;) {
+        const int cn = std::min(chunk, ns - c0);
+        CK(cudaMemsetAsync(d_counts_.p, 0, sizeof(unsigned int), st_));
+        HmkBulkArgs a{};
+        a.prof = d_fprof_.p; a.nq = ncl;
+        a.packed = d_packed_.p; a.db_ids = d_singles_.p + c0; a.db_begin = 0; a.ndb = cn;
+        a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
+        launch_bulk(HMK_MODE_EMIT, a, d_cf_.p, 0);
+        CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        const size_t nh = (uint32_t)h_scalars_[0];
+        if (nh > hit_cap) {   // redo this chunk with a bigger buffer
+            hit_cap = nh * 5 / 4 + 1024;
+            d_hits_.reserve(hit_cap);
+            continue;
+        }
+        stats.p2_hits += (int64_t)nh;
+        if (nh) {
+            if (ncand + nh > cand_cap) {
+                size_t nc = std::max(cand_cap * 2, ncand + nh);
+                d_key_q_.grow_keep(nc, ncand, st_); d_key_c_.grow_keep(nc, ncand, st_); d_cand_score_.grow_keep(nc, ncand, st_);
+                cand_cap = nc;
+            }
+            HmkCheckArgs c{};
+            c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
+            c.hit_t_is_query = 0; c.qids = d_singles_.p + c0;
+            // candidate keys carry the GLOBAL query index: offset added below
+            c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
+            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
+            c.q_index_offset = c0;
+            hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
+            CK(cudaGetLastError());
+            launches_++;
+            CK(cudaMemcpyAsync(h_scalars_ + 1, d_counts_.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            ncand = (uint32_t)h_scalars_[1];
+        }
+        c0 += cn;
+    }
+    stats.p2_candidates = (int64_t)ncand;
+    if (ncand == 0) return;
+    const int nc = (int)ncand;
+    // group by query (ascending cluster inside a query) and by cluster (ascending query inside a cluster)
+    sort_pairs(d_key_q_.p, d_cand_score_.p, nc, 64);
+    d_cq_c_.reserve(nc); d_cc_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, d_cq_c_.p);
+    hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, d_qstart_.p);
+    {
+        size_t bytes = 0;
+        d_key_tmp_.reserve(nc);
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_key_c_.p, d_key_tmp_.p, nc, 0, 64, st_));
+        d_cub_.reserve(bytes);
+        CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, nc, 0, 64, st_));
+    }
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, d_cc_q_.p);
+    hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, d_cstart_.p);
+    CK(cudaGetLastError());
+    launches_ += 8;
+    d_head_a_.reserve(ncl + 1); d_head_b_.reserve(ncl + 1); d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl);
+    CK(cudaMemcpyAsync(d_head_a_.p, d_cstart_.p, sizeof(int32_t) * ncl, cudaMemcpyDeviceToDevice, st_));
+    CK(cudaMemsetAsync(d_dyn_n_.p, 0, sizeof(int32_t) * ncl, st_));
+    HmkP2 P{};
+    P.ncl = ncl; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_s = d_cand_score_.p;
+    P.cstart = d_cstart_.p; P.cc_q = d_cc_q_.p; P.dyn = d_dyn_.p; P.dyn_n = d_dyn_n_.p;
+    P.remaining = d_flags_.p + 1; P.progress = d_flags_.p + 2;
+    int32_t* cur = d_head_a_.p;
+    int32_t* nxt = d_head_b_.p;
+    const HmkState S = state();
+    const int check = (int)std::max<int64_t>(1, opt.round_check);
+    for (;;) {
+        CK(cudaMemsetAsync(d_flags_.p + 1, 0, 2 * sizeof(int32_t), st_));
+        for (int r = 0; r < check; r++) {
+            P.head_cur = cur; P.head_nxt = nxt;
+            hmk_p2_round_kernel<<<(ncl * 32 + 255) / 256, 256, 0, st_>>>(S, P);
+            std::swap(cur, nxt);
+            stats.p2_rounds++;
+            launches_++;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_scalars_ + 8, d_flags_.p + 1, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        // `remaining` is written by the LAST rounds too, so it is accurate for the final state
+        // only if the last round saw none: re-check with a clean flag when it is set
+        if (!h_scalars_[8]) break;
+        if (!h_scalars_[9]) throw CudaError("phase 2 made no progress (internal error)");
+    }
+}
+
+// ---------------------------------------------------------------- run / download
+int Engine::run() {
+    CK(cudaSetDevice(device_));
+    if (!uploaded_) throw std::invalid_argument("hmk_run before hmk_upload");
+    stats = hmk_stats{};
+    stats.error_step = -1;
+    error_step = -1;
+    launches_ = bulk_launches_ = 0;
+    ev_used_ = 0;
+    ran_ = false;
+    if (bad_residue_) return HMK_ERR_BAD_RESIDUE;
+    stats.fast_path = fast_ ? 1 : 0;
+    stats.lane_bits = fast_ ? (sc_.lane16 ? 16 : 8) : 32;
+    CK(cudaEventRecord(ev_a_, st_));
+    if (n_) {
+        hmk_fill_i32<<<sm_count_ * 2, 256, 0, st_>>>(d_slot_.p, -1, (size_t)n_);
+        hmk_fill_i32<<<sm_count_ * 2, 256, 0, st_>>>(d_next_.p, -1, (size_t)n_);
+        CK(cudaMemsetAsync(d_rank_.p, 0, sizeof(int32_t) * n_, st_));
+        launches_ += 2;
+    }
+    HmkCtl c0{};
+    c0.cur = 0; c0.ncl = 0; c0.unproc_alive = n_; c0.status = HMK_P1_CONTINUE; c0.npe_step = -1;
+    *h_ctl_ = c0;
+    CK(cudaMemcpyAsync(d_ctl_.p, h_ctl_, sizeof(HmkCtl), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemsetAsync(d_pairctr_.p, 0, 2 * sizeof(unsigned long long), st_));
+    // DataException "Shift too big" (ShiftedScorer.java:59-62): thrown by the first pair score
+    // touching a sequence not longer than maxShift; step 0 of phase 1 scores every sequence.
+    if (K_ > 0 && n_ >= 2 && X_ >= min_len_) return HMK_ERR_SHIFT_TOO_BIG;
+    int rc = phase1();
+    CK(cudaEventRecord(ev_b_, st_));
+    if (rc == HMK_OK) phase2();
+    if (rc == HMK_OK && n_) {
+        hmk_finalize<<<(n_ + 255) / 256, 256, 0, st_>>>(n_, d_slot_.p, d_rank_.p, d_cf_.p, d_cluster_id_.p, d_member_rank_.p);
+        CK(cudaGetLastError());
+        launches_++;
+        n_unassigned_ = compact_unassigned(d_singles_.p);
+    }
+    CK(cudaEventRecord(ev_c_, st_));
+    fetch_ctl();
+    unsigned long long pc[2] = {0, 0};
+    CK(cudaMemcpyAsync(pc, d_pairctr_.p, sizeof(pc), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    float ms1 = 0, ms2 = 0;
+    CK(cudaEventElapsedTime(&ms1, ev_a_, ev_b_));
+    CK(cudaEventElapsedTime(&ms2, ev_b_, ev_c_));
+    stats.phase1_ms = ms1; stats.phase2_ms = ms2; stats.total_ms = ms1 + ms2;
+    double bulk_ms = 0;
+    for (size_t i = 0; i + 1 < ev_used_; i += 2) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev_pool_[i], ev_pool_[i + 1]));
+        bulk_ms += ms;
+    }
+    stats.bulk_kernel_ms = bulk_ms;
+    stats.bulk_pairs = (int64_t)pc[0];
+    stats.scalar_pairs = h_ctl_->scalar_pairs;
+    if (min_len_ == max_len_) {
+        stats.bulk_cells = stats.bulk_pairs * hmk_pair_cells(max_len_, max_len_, X_);
+        stats.bulk_ops = stats.bulk_cells + stats.bulk_pairs * (2 * (int64_t)X_ + 1);
+    }
+    stats.bulk_launches = bulk_launches_; stats.total_launches = launches_;
+    stats.p1_steps = h_ctl_->steps; stats.p1_joins = h_ctl_->joins; stats.p1_new_clusters = h_ctl_->creates;
+    stats.p1_orphans = h_ctl_->orphans; stats.p1_restarts = h_ctl_->restarts;
+    if (rc == HMK_OK) {
+        stats.p2_assigned = stats.p2_queries - n_unassigned_;
+        ran_ = true;
+    }
+    return rc;
+}
+
+void Engine::download(hmk_greedy_out* out) {
+    CK(cudaSetDevice(device_));
+    if (!ran_) throw std::invalid_argument("hmk_download without a successful hmk_run");
+    const int ncl = h_ctl_->ncl;
+    if (n_) {
+        CK(cudaMemcpyAsync(out->cluster_id, d_cluster_id_.p, sizeof(int32_t) * n_, cudaMemcpyDeviceToHost, st_));
+        CK(cudaMemcpyAsync(out->member_rank, d_member_rank_.p, sizeof(int32_t) * n_, cudaMemcpyDeviceToHost, st_));
+        if (ncl) CK(cudaMemcpyAsync(out->result_order, d_cf_.p, sizeof(int32_t) * ncl, cudaMemcpyDeviceToHost, st_));
+        if (n_unassigned_)
+            CK(cudaMemcpyAsync(out->result_order + ncl, d_singles_.p, sizeof(int32_t) * n_unassigned_, cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+    }
+    out->n_result = ncl + n_unassigned_;
+    out->n_multi = ncl;
+    out->error_step = -1;
+}
+
+void Engine::score_block(const int32_t* first, int32_t nf, const int32_t* second, int32_t ns, int32_t* scores) {
+    CK(cudaSetDevice(device_));
+    if (!uploaded_) throw std::invalid_argument("hmk_score_block before hmk_upload");
+    if (nf <= 0 || ns <= 0) return;
+    DevBuf<int32_t> d_first, d_second, d_out;
+    DevBuf<uint32_t> d_prof;
+    const int chunk = 256;
+    d_first.reserve(nf); d_second.reserve(chunk); d_out.reserve((size_t)chunk * nf);
+    if (fast_) d_prof.reserve((size_t)chunk * sc_.prof_words);
+    CK(cudaMemcpyAsync(d_first.p, first, sizeof(int32_t) * nf, cudaMemcpyHostToDevice, st_));
+    std::vector<int32_t> tmp((size_t)chunk * nf);
+    for (int s0 = 0; s0 < ns; s0 += chunk) {
+        const int sn = std::min(chunk, ns - s0);
+        CK(cudaMemcpyAsync(d_second.p, second + s0, sizeof(int32_t) * sn, cudaMemcpyHostToDevice, st_));
+        if (fast_) launch_profiles(HMK_PROF_QUERY, d_second.p, sn, d_prof.p);
+        HmkBulkArgs a{};
+        a.prof = d_prof.p; a.nq = sn;
+        a.packed = d_packed_.p; a.db_ids = d_first.p; a.db_begin = 0; a.ndb = nf;
+        a.dense = d_out.p; a.dense_stride = nf;
+        launch_bulk(HMK_MODE_DENSE, a, d_second.p, 1);
+        CK(cudaMemcpyAsync(tmp.data(), d_out.p, sizeof(int32_t) * (size_t)sn * nf, cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        for (int b = 0; b < sn; b++)
+            for (int a2 = 0; a2 < nf; a2++) scores[(size_t)a2 * ns + s0 + b] = tmp[(size_t)b * nf + a2];
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- C ABI
+struct hmk_ctx {
+    Engine engine;
+    explicit hmk_ctx(int device) : engine(device) {}
+};
+
+static void set_err(char* errbuf, size_t errlen, const char* msg) {
+    if (errbuf && errlen) {
+        std::strncpy(errbuf, msg, errlen - 1);
+        errbuf[errlen - 1] = 0;
+    }
+}
+
+template <class F>
+static int guarded(char* errbuf, size_t errlen, F&& f) {
+    try {
+        return f();
+    } catch (const CudaError& e) {
+        set_err(errbuf, errlen, e.what());
+        return HMK_STATUS_CUDA;
+    } catch (const std::invalid_argument& e) {
+        set_err(errbuf, errlen, e.what());
+        return HMK_STATUS_BAD_ARG;
+    } catch (const std::exception& e) {
+        set_err(errbuf, errlen, e.what());
+        return HMK_STATUS_CUDA;
+    }
+}
+
+static const char* status_text(int rc) {
+    switch (rc) {
+        case HMK_STATUS_SHIFT_TOO_BIG: return "DataException: Shift too big (max_shift >= length of the shortest sequence)";
+        case HMK_STATUS_NULL_CLUSTER: return "NullPointerException: nearest cluster object without a cluster (see error_step)";
+        case HMK_STATUS_BAD_RESIDUE: return "FileFormatException: residue code outside 0..23";
+        default: return "";
+    }
+}
+
+extern "C" {
+
+int hmk_abi_version(void) { return HMK_ABI_VERSION; }
+
+int hmk_create(hmk_ctx** ctx, int device, char* errbuf, size_t errlen) {
+    if (!ctx) return HMK_STATUS_BAD_ARG;
+    *ctx = nullptr;
+    return guarded(errbuf, errlen, [&] {
+        *ctx = new hmk_ctx(device);
+        return HMK_STATUS_OK;
+    });
+}
+
+void hmk_destroy(hmk_ctx* ctx) { delete ctx; }
+
+int hmk_upload(hmk_ctx* ctx, const hmk_greedy_in* in, char* errbuf, size_t errlen) {
+    if (!ctx) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        ctx->engine.upload(in);
+        return HMK_STATUS_OK;
+    });
+}
+
+int hmk_run(hmk_ctx* ctx, char* errbuf, size_t errlen) {
+    if (!ctx) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        int rc = ctx->engine.run();
+        if (rc) set_err(errbuf, errlen, status_text(rc));
+        return rc;
+    });
+}
+
+int hmk_download(hmk_ctx* ctx, hmk_greedy_out* out, char* errbuf, size_t errlen) {
+    if (!ctx || !out) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        ctx->engine.download(out);
+        return HMK_STATUS_OK;
+    });
+}
+
+int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats) {
+    if (!ctx || !stats) return HMK_STATUS_BAD_ARG;
+    *stats = ctx->engine.stats;
+    return HMK_STATUS_OK;
+}
+
+int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return HMK_STATUS_BAD_ARG;
+    Options& o = ctx->engine.opt;
+    std::string s(name);
+    if (s == "batch") o.batch = value;
+    else if (s == "qt") o.qt = value;
+    else if (s == "kb") o.kb = value;
+    else if (s == "waves") o.waves = value;
+    else if (s == "p2_chunk") o.p2_chunk = value;
+    else if (s == "hit_cap") o.hit_cap = value;
+    else if (s == "force_generic") o.force_generic = value;
+    else if (s == "profile") o.profile = value;
+    else if (s == "round_check") o.round_check = value;
+    else return HMK_STATUS_BAD_ARG;
+    return HMK_STATUS_OK;
+}
+
+int hmk_score_block(hmk_ctx* ctx, const int32_t* first_ids, int32_t n_first, const int32_t* second_ids,
+                    int32_t n_second, int32_t* scores, char* errbuf, size_t errlen) {
+    if (!ctx) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        ctx->engine.score_block(first_ids, n_first, second_ids, n_second, scores);
+        return HMK_STATUS_OK;
+    });
+}
+
+int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen) {
+    if (!in || !out) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        hmk_ctx ctx(device);
+        ctx.engine.upload(in);
+        int rc = ctx.engine.run();
+        out->n_result = 0; out->n_multi = 0; out->error_step = ctx.engine.error_step;
+        if (rc) { set_err(errbuf, errlen, status_text(rc)); return rc; }
+        ctx.engine.download(out);
+        return HMK_STATUS_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+/*
+ * hammock_b200.h -- C ABI of the B200-native greedy-clustering stage of Hammock.
+ *
+ * Drop-in boundary.  The reference has no FFI layer; its narrowest seam for this path is
+ * the Java interface
+ *     SequenceClusterer { List<Cluster> cluster(List<UniqueSequence>) }
+ *         (reference src/cz/krejciadam/hammock/SequenceClusterer.java:15-26)
+ * instantiated for greedy in exactly one place
+ *         new ShiftedScorer(scoringMatrix, shiftPenalty, maxShift)           Hammock.java:402
+ *         new LimitedGreedySequenceClusterer(scorer, threshold, limit)       Hammock.java:403
+ *         clusterer.cluster(sequences)                                       Hammock.java:409
+ * hmk_greedy_cluster() replaces that call: the host hands over the (already ordered,
+ * UniqueSequence.sortSequences, UniqueSequence.java:176-203) sequences as residue codes plus
+ * the scorer/clusterer constructor arguments and rebuilds List<Cluster> from cluster_id /
+ * member_rank / result_order.  INTEGRATION.md shows the JNI / FFM stub.
+ *
+ * Everything runs on the GPU (CUDA, sm_100a).  There is NO CPU fallback: without a usable
+ * device every entry point returns HMK_ERR_CUDA.
+ *
+ * All pointers are host memory owned by the caller and only read/written during the call.
+ */
+#ifndef HAMMOCK_B200_H
+#define HAMMOCK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMK_ABI_VERSION 1
+
+/* status codes: the reference's failure modes on this path */
+#define HMK_STATUS_OK 0
+#define HMK_STATUS_SHIFT_TOO_BIG 1 /* DataException "Shift too big"      ShiftedScorer.java:59-62 */
+#define HMK_STATUS_NULL_CLUSTER 2  /* NullPointerException               LimitedGreedySequenceClusterer.java:104,108 */
+#define HMK_STATUS_BAD_RESIDUE 3   /* residue code >= 24                  UniqueSequence.java:51-54 */
+#define HMK_STATUS_CUDA 4          /* CUDA / NCCL failure (no CPU fallback) */
+#define HMK_STATUS_BAD_ARG 5
+
+typedef struct {
+    int32_t n;                /* sequences, ALREADY in clustering order                              */
+    const uint8_t* residues;  /* concatenated codes 0..23, alphabet "ARNDCQEGHILKMFPSTWYVBZX*"        */
+                              /*   (UniqueSequence.java:23-26)                                        */
+    const int32_t* offsets;   /* n+1 prefix offsets into residues                                    */
+    const int32_t* abundance; /* UniqueSequence.size() (UniqueSequence.java:81-88), Java int          */
+    const int32_t* matrix;    /* 24*24 row-major, as FileIOManager.loadScoringMatrix returns it       */
+                              /*   (FileIOManager.java:46-81)                                         */
+    int32_t threshold;        /* LimitedGreedySequenceClusterer ctor  (...Clusterer.java:22-26)       */
+    int32_t max_shift;        /* ShiftedScorer ctor                   (ShiftedScorer.java:28-32)      */
+    int32_t shift_penalty;    /* ShiftedScorer ctor                                                   */
+    int32_t max_clusters;     /* LimitedGreedySequenceClusterer ctor                                  */
+} hmk_greedy_in;
+
+typedef struct {
+    int32_t* cluster_id;      /* [n] Cluster.getId() of the sequence's cluster = founder's index      */
+    int32_t* member_rank;     /* [n] position in Cluster.getSequences() (0 founder, 1 partner, ...)   */
+    int32_t* result_order;    /* [n] ids of the returned List<Cluster>, in list order                 */
+    int32_t n_result;         /* length of that list                                                  */
+    int32_t n_multi;          /* multi-member clusters (they form the list's prefix)                  */
+    int32_t error_step;       /* phase-1 step index for HMK_STATUS_NULL_CLUSTER, else -1              */
+} hmk_greedy_out;
+
+/* executed-work and timing report of the last run */
+typedef struct {
+    int64_t bulk_pairs;       /* pair scores executed by the bulk kernels                             */
+    int64_t scalar_pairs;     /* pair scores executed one at a time (member checks, resolvers)        */
+    int64_t bulk_cells;       /* matrix cells summed by the bulk kernels                              */
+    int64_t bulk_ops;         /* algorithmic int ops = cells + shifts                  */
+    double bulk_kernel_ms;    /* sum of CUDA-event durations of the bulk scoring launches             */
+    double total_ms;          /* whole hmk_run, device timed                                          */
+    double phase1_ms, phase2_ms;
+    int32_t bulk_launches;    /* bulk scoring kernel launches                                         */
+    int32_t total_launches;   /* all kernel launches                                                  */
+    int32_t p1_steps, p1_joins, p1_new_clusters, p1_orphans, p1_batches, p1_restarts;
+    int32_t p2_queries, p2_assigned, p2_rounds;
+    int64_t p2_hits, p2_candidates;
+    int32_t fast_path;        /* 1: packed SWAR kernel, 0: generic scalar kernel                      */
+    int32_t lane_bits;        /* 8 or 16 on the fast path                                             */
+    int32_t error_step;       /* phase-1 step of HMK_STATUS_NULL_CLUSTER in the last run, else -1     */
+    int32_t pad_;
+} hmk_stats;
+
+typedef struct hmk_ctx hmk_ctx;
+
+int hmk_abi_version(void);
+
+/* One blocking call == SequenceClusterer.cluster(sequences).  Uses CUDA device `device`. */
+int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen);
+
+/* Handle API: the same work split into upload / device-resident run / download, so that a
+ * host can keep the sequences resident and time the stages separately. */
+int hmk_create(hmk_ctx** ctx, int device, char* errbuf, size_t errlen);
+void hmk_destroy(hmk_ctx* ctx);
+int hmk_upload(hmk_ctx* ctx, const hmk_greedy_in* in, char* errbuf, size_t errlen);
+int hmk_run(hmk_ctx* ctx, char* errbuf, size_t errlen);
+int hmk_download(hmk_ctx* ctx, hmk_greedy_out* out, char* errbuf, size_t errlen);
+int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats);
+/* tuning knobs (batch size, tile sizes, ...); unknown names return HMK_STATUS_BAD_ARG */
+int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value);
+
+/* SequenceScorer.sequenceScore over a block of pairs (SequenceScorer.java:12-15,
+ * ShiftedScorer.java:97-100): scores[a * n_second + b] = sequenceScore(seq1 = first_ids[a],
+ * seq2 = second_ids[b]) for the uploaded sequences.  Used by the parity tests of the kernel. */
+int hmk_score_block(hmk_ctx* ctx, const int32_t* first_ids, int32_t n_first, const int32_t* second_ids,
+                    int32_t n_second, int32_t* scores, char* errbuf, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
