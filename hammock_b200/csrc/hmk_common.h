@@ -1,9 +1,6 @@
 // hmk_common.h -- shared host/device primitives of the B200 greedy-clustering engine.
 //
-// Compiles under nvcc (device + host) and under plain g++ (tests/emu builds the resolver
-// logic for the CPU so that the speculate+repair control flow can be checked against the
-// oracle at full scale without a GPU; that harness is test-only and is not part of
-// libhammock_b200.so).
+// Compiles under nvcc (device + host) and under plain g++.
 #pragma once
 #include <stdint.h>
 
@@ -88,7 +85,8 @@ enum {
     HMK_P1_CONTINUE = 0,  // batch fully consumed, more work
     HMK_P1_DONE = 1,      // K clusters reached or list exhausted
     HMK_P1_NPE = 2,       // reference would throw NullPointerException at this step
-    HMK_P1_RESTART = 3    // partner list exhausted but truncated: rescore from ctl.cur
+    HMK_P1_RESTART = 3,   // partner list exhausted but truncated: rescore from ctl.cur
+    HMK_P1_GROW = 4       // per-query cluster-candidate arrays too small: grow and rescore from ctl.cur
 };
 
 struct HmkCtl {

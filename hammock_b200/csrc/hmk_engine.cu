@@ -67,8 +67,12 @@ struct DevBuf {
     }
 };
 
+enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_RESOLVE, SEC_P2_SETUP, SEC_P2_FILTER,
+       SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
+
 struct Options {
-    int64_t batch = 192;        // phase-1 queries per batch
+    int64_t batch = 0;          // phase-1 queries per batch (0 = two profile tiles)
+    int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
     int64_t kb = 8;             // partner candidates kept per query
     int64_t waves = 2;          // CTAs per SM targeted by the stripe split
@@ -76,7 +80,7 @@ struct Options {
     int64_t hit_cap = 1 << 22;  // initial founder-hit capacity
     int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
-    int64_t round_check = 4;    // phase-2 rounds between host checks
+    int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
 };
 
 class Engine {
@@ -130,6 +134,7 @@ private:
     int32_t min_len_ = 0, max_len_ = 0;
     bool uploaded_ = false, ran_ = false, bad_residue_ = false;
     bool fast_ = false;
+    bool fast_scalar_ = false;   // uniform length <= 12: packed scalar scorer usable
     HmkScheme sc_{};
     std::vector<int32_t> h_off_;
     DevBuf<uint8_t> d_res_;
@@ -142,8 +147,10 @@ private:
     HmkCtl* h_ctl_ = nullptr;
     int32_t* h_scalars_ = nullptr;
     // ---- phase-1 scratch
-    DevBuf<int32_t> d_qid_, d_nq_, d_tk_cnt_, d_tk_ovf_, d_bk_cnt_, d_bk_ovf_, d_ib_, d_bm_slot_, d_bm_ref_,
-        d_nf_b_, d_nf_slot_, d_ac_head_, d_ac_next_, d_ac_slot_, d_ac_score_;
+    DevBuf<int32_t> d_qid_, d_nq_, d_tk_cnt_, d_tk_ovf_, d_bk_cnt_, d_bk_ovf_, d_ib_,
+        d_ac_cnt_, d_ac_slot_, d_ac_score_, d_c_stamp_, d_c_tidx_, d_dirty_a_, d_dirty_b_;
+    DevBuf<uint32_t> d_ibm_;
+    int batch_id_ = 0;
     DevBuf<uint64_t> d_tk_key_, d_bk_key_;
     DevBuf<uint32_t> d_prof_;
     DevBuf<int4> d_hits_;
@@ -151,7 +158,7 @@ private:
     DevBuf<unsigned long long> d_pairctr_;
     // ---- phase-2 scratch
     DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cc_q_, d_qstart_, d_cstart_,
-        d_head_a_, d_head_b_, d_dyn_, d_dyn_n_, d_flags_;
+        d_a0_, d_a1_, d_dyn_, d_dyn_n_, d_flags_, d_base_cl_, d_wlo_, d_tent_, d_tent_n_;
     DevBuf<unsigned long long> d_key_q_, d_key_c_, d_key_tmp_;
     DevBuf<unsigned char> d_cub_;
     DevBuf<uint32_t> d_fprof_;
@@ -162,6 +169,7 @@ private:
     cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
     std::vector<cudaEvent_t> ev_pool_;
     size_t ev_used_ = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> bulk_events_;
     int launches_ = 0, bulk_launches_ = 0;
     int64_t bulk_pairs_host_ = 0;
 
@@ -180,6 +188,21 @@ private:
     void launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof);
     void launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query);
     cudaEvent_t next_event();
+    // per-section device timers (only with opt.profile)
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> sections_;
+    int sec_open_ = -1;
+    cudaEvent_t sec_start_ = nullptr;
+    void sec(int id) {   // close the open section and start section `id` (-1: just close)
+        if (!opt.profile) return;
+        cudaEvent_t e = next_event();
+        CK(cudaEventRecord(e, st_));
+        if (sec_open_ >= 0) sections_.push_back({sec_open_, {sec_start_, e}});
+        sec_open_ = id;
+        sec_start_ = e;
+    }
+public:
+    double section_ms[HMK_NSECTIONS] = {0};
+private:
     void fetch_ctl() {
         CK(cudaMemcpyAsync(h_ctl_, d_ctl_.p, sizeof(HmkCtl), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
@@ -256,6 +279,7 @@ void Engine::upload(const hmk_greedy_in* in) {
         CK(cudaStreamSynchronize(st_));
     }
     choose_scheme(in->matrix);
+    fast_scalar_ = n_ > 0 && min_len_ == max_len_ && max_len_ >= 1 && max_len_ <= HMK_MAXL1 && X_ >= 0 && X_ < max_len_;
     // validate residues + pack 5 bits/residue on the device
     d_packed_.reserve(std::max(n_, 1));
     d_flags_.reserve(8);
@@ -291,7 +315,8 @@ int Engine::qt_max() const {
     if (opt.qt > 0) return (int)opt.qt;
     const size_t pwb = (size_t)sc_.prof_words * 4;
     const size_t per = pwb + (size_t)opt.kb * 8 + 8 + 12;
-    return (int)std::max<size_t>(1, (smem_optin_ - 64) / per);
+    const size_t fixed = 64 + (HMK_BULK_THREADS / 32) * HMK_QCAP * 8;
+    return (int)std::min<size_t>(255, std::max<size_t>(1, (smem_optin_ - fixed) / per));
 }
 
 void Engine::launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof) {
@@ -330,7 +355,7 @@ static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, 
         CK(cudaFuncSetAttribute(hmk_bulk_generic<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_smem = smem;
     }
-    hmk_bulk_generic<MODE><<<grid, 256, smem, st>>>(g);
+    hmk_bulk_generic<MODE><<<grid, HMK_GENERIC_THREADS, smem, st>>>(g);
 }
 
 // fills in the tiling fields of `a` (nqt, qt, nstripes, chunk) and launches
@@ -339,15 +364,21 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
     a.sc = sc_;
     a.pair_counter = d_pairctr_.p;
     a.kb = (int)opt.kb;
-    const int threads = fast_ ? HMK_BULK_THREADS : 256;
+    const int threads = fast_ ? HMK_BULK_THREADS : HMK_GENERIC_THREADS;
     const int qmax = fast_ ? qt_max() : 128;
     a.nqt = (a.nq + qmax - 1) / qmax;
     a.qt = (a.nq + a.nqt - 1) / a.nqt;
+    // grid = nqt * nstripes: an exact multiple of the SM count whenever the database is large
+    // enough (one CTA per SM is resident: the profile tile fills shared memory)
     int want = (int)((sm_count_ * opt.waves + a.nqt - 1) / a.nqt);
+    if (a.nqt <= sm_count_ * opt.waves && (sm_count_ * opt.waves) % a.nqt != 0) {
+        // nqt does not divide waves*SMs: round the total up to the next multiple of the SM count
+        int total = (int)((((int64_t)want * a.nqt + sm_count_ - 1) / sm_count_) * sm_count_);
+        want = std::max(1, total / a.nqt);
+    }
     int max_stripes = (a.ndb + threads - 1) / threads;
     a.nstripes = std::max(1, std::min(want, max_stripes));
     a.chunk = (a.ndb + a.nstripes - 1) / a.nstripes;
-    a.chunk = (a.chunk + threads - 1) / threads * threads;
     a.nstripes = (a.ndb + a.chunk - 1) / a.chunk;
     if (mode == HMK_MODE_TOPK) {
         const size_t slots = (size_t)a.nstripes * a.nq;
@@ -358,8 +389,8 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, st_)); }
     if (fast_) {
-        size_t smem = (((size_t)a.qt * sc_.prof_words * 4 + 15) & ~(size_t)15) + 16 + (size_t)a.qt * a.kb * 8 +
-                      (size_t)a.qt * 8 + (size_t)a.qt * 12;
+        size_t smem = (((size_t)a.qt * sc_.prof_words * 4 + 15) & ~(size_t)15) + 16 +
+                      hmk_carve_bytes(a.qt, a.kb, HMK_BULK_THREADS, false);
         if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, st_);
         else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, st_);
         else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, st_);
@@ -367,14 +398,14 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
         HmkGenericArgs g;
         g.b = a; g.prof_ids = prof_ids; g.prof_is_query = prof_is_query;
         g.res = d_res_.p; g.off = d_off_.p; g.M = d_M_.p; g.maxlen = std::max(max_len_, 1);
-        size_t smem = HMK_NRES * HMK_NRES * 4 + (size_t)a.qt * 4 + 8 + (size_t)a.qt * a.kb * 8 + (size_t)a.qt * 8 +
-                      (size_t)a.qt * 12 + (size_t)a.qt * g.maxlen + 16;
+        size_t smem = HMK_NRES * HMK_NRES * 4 + hmk_carve_bytes(a.qt, a.kb, HMK_GENERIC_THREADS, true) +
+                      (size_t)a.qt * 4 + (size_t)a.qt * g.maxlen + 16;
         if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(g, grid, smem, st_);
         else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(g, grid, smem, st_);
         else launch_generic_mode<HMK_MODE_DENSE>(g, grid, smem, st_);
     }
     CK(cudaGetLastError());
-    if (opt.profile) CK(cudaEventRecord(e1, st_));
+    if (opt.profile) { CK(cudaEventRecord(e1, st_)); bulk_events_.push_back({e0, e1}); }
     launches_++;
     bulk_launches_++;
     if (mode == HMK_MODE_TOPK) {
@@ -414,24 +445,33 @@ void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_
 
 // ---------------------------------------------------------------- phase 1
 int Engine::phase1() {
-    const int B = (int)std::max<int64_t>(1, opt.batch);
+    int B = (int)opt.batch;
+    if (B <= 0) B = fast_ ? 2 * qt_max() : 192;
+    B = std::max(1, std::min(B, HMK_MAXBATCH));
+    opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
+    size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
+    const int nwmax = (B + 31) / 32;
     d_qid_.reserve(B); d_nq_.reserve(1);
     d_ib_.reserve((size_t)B * B);
-    d_bm_slot_.reserve(2 * B); d_bm_ref_.reserve(2 * B); d_nf_b_.reserve(B); d_nf_slot_.reserve(B);
-    d_ac_head_.reserve(B);
+    d_ibm_.reserve((size_t)B * nwmax);
+    d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
+    d_c_stamp_.reserve(std::max(K_, 1)); d_c_tidx_.reserve(std::max(K_, 1));
+    CK(cudaMemsetAsync(d_c_stamp_.p, 0, sizeof(int32_t) * std::max(K_, 1), st_));
+    batch_id_ = 0;
     if (fast_) d_prof_.reserve((size_t)B * sc_.prof_words);
     size_t hit_cap = (size_t)opt.hit_cap;
     d_hits_.reserve(hit_cap);
-    d_ac_next_.reserve(hit_cap); d_ac_slot_.reserve(hit_cap); d_ac_score_.reserve(hit_cap);
     fetch_ctl();
     while (h_ctl_->ncl < K_ && h_ctl_->unproc_alive > 0) {
         const int nq = std::min(B, h_ctl_->unproc_alive);
         const int cur = h_ctl_->cur, ncl = h_ctl_->ncl;
+        sec(SEC_P1_SELECT);
         hmk_select_queries<<<1, 1024, 0, st_>>>(d_slot_.p, n_, d_ctl_.p, nq, d_qid_.p, d_nq_.p);
         CK(cudaGetLastError());
         launches_++;
         if (fast_) launch_profiles(HMK_PROF_QUERY, d_qid_.p, nq, d_prof_.p);
         // B: partner search over all later singletons
+        sec(SEC_P1_PARTNER);
         {
             HmkBulkArgs a{};
             a.prof = d_prof_.p; a.nq = nq;
@@ -446,8 +486,9 @@ int Engine::phase1() {
             }
         }
         // A: clusters whose founder scores >= T, then complete linkage over their members
+        sec(SEC_P1_CLUSTER);
         CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
-        CK(cudaMemsetAsync(d_ac_head_.p, 0xff, sizeof(int32_t) * nq, st_));
+        CK(cudaMemsetAsync(d_ac_cnt_.p, 0, sizeof(int32_t) * nq, st_));
         if (ncl > 0) {
             HmkBulkArgs a{};
             a.prof = d_prof_.p; a.nq = nq;
@@ -457,13 +498,15 @@ int Engine::phase1() {
             HmkCheckArgs c{};
             c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
             c.hit_t_is_query = 1; c.qids = d_qid_.p;
-            c.ac_head = d_ac_head_.p; c.ac_next = d_ac_next_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p;
-            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)hit_cap; c.linked = 1;
+            c.ac_cnt = d_ac_cnt_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p; c.capq = (int32_t)capq;
+            c.cand_count = d_counts_.p + 1; c.cand_cap = 0; c.linked = 1;
+            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
             hmk_member_check<<<sm_count_ * 2, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
             launches_++;
         }
         // intra-batch scores S(member = q_b2, query = q_b)
+        sec(SEC_P1_INTRA);
         {
             HmkBulkArgs a{};
             a.prof = d_prof_.p; a.nq = nq;
@@ -471,27 +514,37 @@ int Engine::phase1() {
             a.dense = d_ib_.p; a.dense_stride = nq;
             launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
         }
+        const int nw = (nq + 31) / 32;
+        hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, st_>>>(nq, nw, T_, d_ib_.p, nq, d_ibm_.p);
+        launches_++;
         HmkP1Batch pb{};
-        pb.nq = nq; pb.qid = d_qid_.p; pb.kb = (int)opt.kb;
+        pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid_.p; pb.kb = (int)opt.kb;
         pb.bk_key = d_bk_key_.p; pb.bk_cnt = d_bk_cnt_.p; pb.bk_ovf = d_bk_ovf_.p;
-        pb.ac_head = d_ac_head_.p; pb.ac_next = d_ac_next_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
-        pb.ib = d_ib_.p; pb.ib_stride = nq;
-        pb.bm_slot = d_bm_slot_.p; pb.bm_ref = d_bm_ref_.p; pb.nf_b = d_nf_b_.p; pb.nf_slot = d_nf_slot_.p;
+        pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
+        pb.ib = d_ib_.p; pb.ib_stride = nq; pb.ibm = d_ibm_.p; pb.nw = nw;
+        pb.c_stamp = d_c_stamp_.p; pb.c_tidx = d_c_tidx_.p;
+        pb.packed = fast_scalar_ ? d_packed_.p : nullptr; pb.L = max_len_;
         // the resolver must not run on truncated hit lists: checked on the host first
         CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
         if ((size_t)(uint32_t)h_scalars_[0] > hit_cap) {   // grow and redo this batch (state untouched)
             hit_cap = (size_t)(uint32_t)h_scalars_[0] * 5 / 4 + 1024;
-            d_hits_.reserve(hit_cap); d_ac_next_.reserve(hit_cap); d_ac_slot_.reserve(hit_cap); d_ac_score_.reserve(hit_cap);
+            d_hits_.reserve(hit_cap);
             continue;
         }
+        sec(SEC_P1_RESOLVE);
         hmk_p1_resolve_kernel<<<1, 32, 0, st_>>>(state(), pb);
         CK(cudaGetLastError());
         launches_++;
         stats.p1_batches++;
+        sec(-1);
         fetch_ctl();
         if (h_ctl_->status == HMK_P1_NPE) { error_step = h_ctl_->npe_step; stats.error_step = error_step; return HMK_ERR_NULL_CLUSTER; }
         if (h_ctl_->status == HMK_P1_DONE) break;
+        if (h_ctl_->status == HMK_P1_GROW) {   // a query had more valid clusters than its arrays hold
+            capq *= 2;
+            d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
+        }
     }
     return HMK_OK;
 }
@@ -499,9 +552,10 @@ int Engine::phase1() {
 // ---------------------------------------------------------------- phase 2
 void Engine::phase2() {
     const int ncl = h_ctl_->ncl;
+    sec(SEC_P2_SETUP);
     const int ns = compact_unassigned(d_singles_.p);
     stats.p2_queries = ns;
-    if (ncl == 0 || ns == 0) return;
+    if (ncl == 0 || ns == 0) { sec(-1); return; }
     // founder profiles (member side), built once: founders are fixed during phase 2
     if (fast_) {
         d_fprof_.reserve((size_t)ncl * sc_.prof_words);
@@ -516,12 +570,14 @@ void Engine::phase2() {
     const int chunk = (int)std::max<int64_t>(1024, opt.p2_chunk);
     for (int c0 = 0; c0 < ns;) {
         const int cn = std::min(chunk, ns - c0);
+        sec(SEC_P2_FILTER);
         CK(cudaMemsetAsync(d_counts_.p, 0, sizeof(unsigned int), st_));
         HmkBulkArgs a{};
         a.prof = d_fprof_.p; a.nq = ncl;
         a.packed = d_packed_.p; a.db_ids = d_singles_.p + c0; a.db_begin = 0; a.ndb = cn;
         a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
         launch_bulk(HMK_MODE_EMIT, a, d_cf_.p, 0);
+        sec(SEC_P2_CHECK);
         CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
         const size_t nh = (uint32_t)h_scalars_[0];
@@ -544,6 +600,7 @@ void Engine::phase2() {
             c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
             c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
             c.q_index_offset = c0;
+            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
             hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
             launches_++;
@@ -554,7 +611,8 @@ void Engine::phase2() {
         c0 += cn;
     }
     stats.p2_candidates = (int64_t)ncand;
-    if (ncand == 0) return;
+    sec(SEC_P2_SORT);
+    if (ncand == 0) { sec(-1); return; }
     const int nc = (int)ncand;
     // group by query (ascending cluster inside a query) and by cluster (ascending query inside a cluster)
     sort_pairs(d_key_q_.p, d_cand_score_.p, nc, 64);
@@ -572,34 +630,56 @@ void Engine::phase2() {
     hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, d_cstart_.p);
     CK(cudaGetLastError());
     launches_ += 8;
-    d_head_a_.reserve(ncl + 1); d_head_b_.reserve(ncl + 1); d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl);
-    CK(cudaMemcpyAsync(d_head_a_.p, d_cstart_.p, sizeof(int32_t) * ncl, cudaMemcpyDeviceToDevice, st_));
+    d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_wlo_.reserve(ncl); d_tent_.reserve(nc);
+    d_tent_n_.reserve(ncl); d_a0_.reserve(ns); d_a1_.reserve(ns); d_dirty_a_.reserve(ncl); d_dirty_b_.reserve(ncl);
     CK(cudaMemsetAsync(d_dyn_n_.p, 0, sizeof(int32_t) * ncl, st_));
+    CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * ns, st_));
+    CK(cudaMemsetAsync(d_a1_.p, 0xff, sizeof(int32_t) * ns, st_));
     HmkP2 P{};
-    P.ncl = ncl; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_s = d_cand_score_.p;
+    P.S = state(); P.packed = fast_scalar_ ? d_packed_.p : nullptr; P.L = max_len_;
+    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_s = d_cand_score_.p;
     P.cstart = d_cstart_.p; P.cc_q = d_cc_q_.p; P.dyn = d_dyn_.p; P.dyn_n = d_dyn_n_.p;
-    P.remaining = d_flags_.p + 1; P.progress = d_flags_.p + 2;
-    int32_t* cur = d_head_a_.p;
-    int32_t* nxt = d_head_b_.p;
-    const HmkState S = state();
-    const int check = (int)std::max<int64_t>(1, opt.round_check);
-    for (;;) {
-        CK(cudaMemsetAsync(d_flags_.p + 1, 0, 2 * sizeof(int32_t), st_));
-        for (int r = 0; r < check; r++) {
-            P.head_cur = cur; P.head_nxt = nxt;
-            hmk_p2_round_kernel<<<(ncl * 32 + 255) / 256, 256, 0, st_>>>(S, P);
-            std::swap(cur, nxt);
+    P.base_cl = d_base_cl_.p; P.wlo = d_wlo_.p; P.tent = d_tent_.p; P.tent_n = d_tent_n_.p;
+    P.changed = d_flags_.p + 1;
+    int32_t* cur = d_a0_.p;
+    int32_t* nxt = d_a1_.p;
+    const int W = (int)std::max<int64_t>(1, opt.p2_window);
+    const int cgrid = (ncl + 255) / 256;
+    for (int qa = 0; qa < ns; qa += W) {
+        const int qb = std::min(ns, qa + W);
+        P.qa = qa; P.qb = qb;
+        sec(SEC_P2_BASE);
+        hmk_p2_window_lo<<<cgrid, 256, 0, st_>>>(P);
+        hmk_p2_base<<<sm_count_ * 8, 256, 0, st_>>>(P);
+        launches_ += 2;
+        const int qgrid = (qb - qa + 7) / 8;      // one warp per query, 8 warps per block
+        sec(SEC_P2_ITERATE);
+        int32_t* dcur = d_dirty_a_.p;
+        int32_t* dnxt = d_dirty_b_.p;
+        CK(cudaMemsetAsync(dcur, 0xff, sizeof(int32_t) * ncl, st_));      // -1: everything is dirty at first
+        for (;;) {
+            P.a_cur = cur; P.a_new = nxt; P.dirty_cur = dcur; P.dirty_nxt = dnxt;
+            CK(cudaMemsetAsync(dnxt, 0x7f, sizeof(int32_t) * ncl, st_));  // "no change"
+            CK(cudaMemsetAsync(d_tent_n_.p, 0, sizeof(int32_t) * ncl, st_));
+            CK(cudaMemsetAsync(d_flags_.p + 1, 0, sizeof(int32_t), st_));
+            hmk_p2_build_tent<<<(qb - qa + 255) / 256, 256, 0, st_>>>(P);
+            hmk_p2_sort_tent<<<cgrid, 256, 0, st_>>>(P);
+            hmk_p2_decide<<<qgrid, 256, 0, st_>>>(P);
+            CK(cudaGetLastError());
+            launches_ += 3;
             stats.p2_rounds++;
-            launches_++;
+            CK(cudaMemcpyAsync(h_scalars_ + 8, d_flags_.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            if (!h_scalars_[8]) break;          // fixed point: tent lists == final joiners of this window
+            std::swap(cur, nxt);
+            std::swap(dcur, dnxt);
         }
+        sec(SEC_P2_COMMIT);
+        hmk_p2_commit<<<cgrid, 256, 0, st_>>>(P);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_scalars_ + 8, d_flags_.p + 1, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
-        CK(cudaStreamSynchronize(st_));
-        // `remaining` is written by the LAST rounds too, so it is accurate for the final state
-        // only if the last round saw none: re-check with a clean flag when it is set
-        if (!h_scalars_[8]) break;
-        if (!h_scalars_[9]) throw CudaError("phase 2 made no progress (internal error)");
+        launches_++;
     }
+    sec(-1);
 }
 
 // ---------------------------------------------------------------- run / download
@@ -611,6 +691,10 @@ int Engine::run() {
     error_step = -1;
     launches_ = bulk_launches_ = 0;
     ev_used_ = 0;
+    bulk_events_.clear();
+    sections_.clear();
+    sec_open_ = -1;
+    for (double& v : section_ms) v = 0;
     ran_ = false;
     if (bad_residue_) return HMK_ERR_BAD_RESIDUE;
     stats.fast_path = fast_ ? 1 : 0;
@@ -634,10 +718,12 @@ int Engine::run() {
     CK(cudaEventRecord(ev_b_, st_));
     if (rc == HMK_OK) phase2();
     if (rc == HMK_OK && n_) {
+        sec(SEC_FINAL);
         hmk_finalize<<<(n_ + 255) / 256, 256, 0, st_>>>(n_, d_slot_.p, d_rank_.p, d_cf_.p, d_cluster_id_.p, d_member_rank_.p);
         CK(cudaGetLastError());
         launches_++;
         n_unassigned_ = compact_unassigned(d_singles_.p);
+        sec(-1);
     }
     CK(cudaEventRecord(ev_c_, st_));
     fetch_ctl();
@@ -649,10 +735,15 @@ int Engine::run() {
     CK(cudaEventElapsedTime(&ms2, ev_b_, ev_c_));
     stats.phase1_ms = ms1; stats.phase2_ms = ms2; stats.total_ms = ms1 + ms2;
     double bulk_ms = 0;
-    for (size_t i = 0; i + 1 < ev_used_; i += 2) {
+    for (auto& pr : bulk_events_) {
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, ev_pool_[i], ev_pool_[i + 1]));
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
         bulk_ms += ms;
+    }
+    for (auto& sct : sections_) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, sct.second.first, sct.second.second));
+        section_ms[sct.first] += ms;
     }
     stats.bulk_kernel_ms = bulk_ms;
     stats.bulk_pairs = (int64_t)pc[0];
@@ -801,19 +892,26 @@ int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats) {
     return HMK_STATUS_OK;
 }
 
+int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n) {
+    if (!ctx || !out) return HMK_STATUS_BAD_ARG;
+    for (int i = 0; i < n && i < HMK_NSECTIONS; i++) out[i] = ctx->engine.section_ms[i];
+    return HMK_STATUS_OK;
+}
+
 int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return HMK_STATUS_BAD_ARG;
     Options& o = ctx->engine.opt;
     std::string s(name);
     if (s == "batch") o.batch = value;
     else if (s == "qt") o.qt = value;
+    else if (s == "capq") o.capq = value;
     else if (s == "kb") o.kb = value;
     else if (s == "waves") o.waves = value;
     else if (s == "p2_chunk") o.p2_chunk = value;
     else if (s == "hit_cap") o.hit_cap = value;
     else if (s == "force_generic") o.force_generic = value;
     else if (s == "profile") o.profile = value;
-    else if (s == "round_check") o.round_check = value;
+    else if (s == "p2_window") o.p2_window = value;
     else return HMK_STATUS_BAD_ARG;
     return HMK_STATUS_OK;
 }

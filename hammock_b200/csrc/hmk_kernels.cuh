@@ -135,6 +135,11 @@ struct HmkBulkArgs {
 };
 
 // ---------------------------------------------------------------- hit handling
+// The scoring loops are kept free of divergence: a hit (score >= T, rare) is only APPENDED to
+// a per-warp queue in shared memory (slot = ballot rank, no atomics, no branches that split
+// the warp for long); queues are drained by the whole warp at warp-uniform points.
+#define HMK_QCAP 64   // entries per warp queue; drained when fewer than 32 slots remain
+
 struct HmkTopkSmem {
     uint64_t* key;    // [qt][kb]
     uint64_t* minkey; // [qt]
@@ -143,54 +148,115 @@ struct HmkTopkSmem {
     int* ovf;         // [qt]
 };
 
-__device__ __forceinline__ void hmk_topk_insert(const HmkTopkSmem& s, int t, int kb, uint64_t key) {
+struct HmkHitQueue {
+    uint64_t* q;      // this warp's HMK_QCAP entries: (tile-local query << 48) | (score16 << 32) | item
+    int32_t* s32;     // generic kernel only: full int32 scores (NULL on the packed path)
+    int cnt;          // warp-uniform
+};
+
+__device__ __forceinline__ uint64_t hmk_hit_pack(int tl, int32_t score, int32_t i) {
+    return ((uint64_t)(uint32_t)tl << 48) | ((uint64_t)(uint16_t)(int16_t)score << 32) | (uint32_t)i;
+}
+
+// executed by ONE lane of a warp at a time (the others wait at a ballot), so the spin only
+// ever contends with other warps
+__device__ __forceinline__ void hmk_topk_insert_locked(const HmkTopkSmem& s, int t, int kb, uint64_t key) {
     volatile uint64_t* keys = s.key + (size_t)t * kb;
     volatile uint64_t* mink = s.minkey + t;
     volatile int* cnt = s.cnt + t;
-    if (*cnt >= kb && key <= *mink) { s.ovf[t] = 1; return; }   // cheap reject (minkey only grows)
-    bool done = false;
-    while (!done) {
-        if (atomicCAS(s.lock + t, 0, 1) == 0) {
-            __threadfence_block();
-            int c = *cnt;
-            if (c < kb) {
-                keys[c] = key;
-                c++;
-                if (c == kb) {
-                    uint64_t m = keys[0];
-                    for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; m = v < m ? v : m; }
-                    *mink = m;
-                }
-                *cnt = c;
-            } else {
-                s.ovf[t] = 1;
-                if (key > *mink) {
-                    int mi = 0;
-                    uint64_t m = keys[0];
-                    for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; if (v < m) { m = v; mi = i; } }
-                    keys[mi] = key;
-                    m = keys[0];
-                    for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; m = v < m ? v : m; }
-                    *mink = m;
-                }
-            }
-            __threadfence_block();
-            atomicExch(s.lock + t, 0);
-            done = true;
+    while (atomicCAS(s.lock + t, 0, 1) != 0) {}
+    __threadfence_block();
+    int c = *cnt;
+    if (c < kb) {
+        keys[c] = key;
+        c++;
+        if (c == kb) {
+            uint64_t m = keys[0];
+            for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; m = v < m ? v : m; }
+            *mink = m;
+        }
+        *cnt = c;
+    } else {
+        s.ovf[t] = 1;
+        if (key > *mink) {
+            int mi = 0;
+            uint64_t m = keys[0];
+            for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; if (v < m) { m = v; mi = i; } }
+            keys[mi] = key;
+            m = keys[0];
+            for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; m = v < m ? v : m; }
+            *mink = m;
         }
     }
+    __threadfence_block();
+    atomicExch(s.lock + t, 0);
 }
 
+// whole warp, converged
 template <int MODE>
-__device__ __noinline__ void hmk_handle_hit(const HmkBulkArgs& a, const HmkTopkSmem& tk, int tl, int tg,
-                                               int32_t i, int32_t id, int32_t score) {
-    if (MODE == HMK_MODE_TOPK) {
-        if (a.q_minid && id <= a.q_minid[tg]) return;
-        uint32_t rk = a.tierank ? (uint32_t)a.tierank[id] : (uint32_t)id;
-        hmk_topk_insert(tk, tl, a.kb, hmk_key_make(score, rk));
-    } else if (MODE == HMK_MODE_EMIT) {
-        unsigned int pos = atomicAdd(a.hit_count, 1u);
-        if (pos < a.hit_cap) a.hits[pos] = make_int4(tg, i, score, 0);
+__device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopkSmem& tk, int q0, HmkHitQueue& hq) {
+    const int lane = threadIdx.x & 31;
+    const int n = hq.cnt;
+    __syncwarp();
+    if (MODE == HMK_MODE_EMIT) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(a.hit_count, (unsigned int)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int e = lane; e < n; e += 32) {
+            const uint64_t v = hq.q[e];
+            const unsigned int pos = base + e;
+            const int32_t sc = hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32);
+            if (pos < a.hit_cap) a.hits[pos] = make_int4(q0 + (int)(v >> 48), (int32_t)(uint32_t)v, sc, 0);
+        }
+    } else if (MODE == HMK_MODE_TOPK) {
+        for (int e0 = 0; e0 < n; e0 += 32) {
+            const int e = e0 + lane;
+            bool pending = false;
+            int tl = 0;
+            uint64_t key = 0;
+            if (e < n) {
+                const uint64_t v = hq.q[e];
+                tl = (int)(v >> 48);
+                const int32_t i = (int32_t)(uint32_t)v;
+                const int32_t id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
+                pending = !(a.q_minid && id <= a.q_minid[q0 + tl]);   // initialList[index+1 ..] only
+                if (pending) {
+                    const uint32_t rk = a.tierank ? (uint32_t)a.tierank[id] : (uint32_t)id;
+                    key = hmk_key_make(hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32), rk);
+                    // cheap reject without the lock (minkey only grows once the list is full)
+                    if (*(volatile int*)(tk.cnt + tl) >= a.kb && key <= *(volatile uint64_t*)(tk.minkey + tl)) {
+                        tk.ovf[tl] = 1;
+                        pending = false;
+                    }
+                }
+            }
+            unsigned m;
+            while ((m = __ballot_sync(0xffffffffu, pending)) != 0) {
+                if (lane == __ffs(m) - 1) {
+                    hmk_topk_insert_locked(tk, tl, a.kb, key);
+                    pending = false;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    hq.cnt = 0;
+}
+
+// append this lane's hit (if any); must be called by the whole, converged warp
+template <int MODE>
+__device__ __forceinline__ void hmk_queue_push(const HmkBulkArgs& a, const HmkTopkSmem& tk, int q0, HmkHitQueue& hq,
+                                               bool hit, int tl, int32_t score, int32_t i) {
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        if (hit) {
+            const int pos = hq.cnt + __popc(m & ((1u << lane) - 1u));
+            hq.q[pos] = hmk_hit_pack(tl, score, i);
+            if (hq.s32) hq.s32[pos] = score;
+        }
+        hq.cnt += __popc(m);
+        if (hq.cnt > HMK_QCAP - 32) hmk_queue_drain<MODE>(a, tk, q0, hq);
     }
 }
 
@@ -230,11 +296,31 @@ __device__ __forceinline__ void hmk_topk_flush(const HmkBulkArgs& a, const HmkTo
     }
 }
 
+// shared-memory carve-up behind the per-kernel payload (profiles / residues)
+__device__ __forceinline__ void hmk_carve(unsigned char* p, int qt, int kb, bool wide, HmkTopkSmem& tk, HmkHitQueue& hq) {
+    tk.key = reinterpret_cast<uint64_t*>(p);    p += (size_t)qt * kb * 8;
+    tk.minkey = reinterpret_cast<uint64_t*>(p); p += (size_t)qt * 8;
+    hq.q = reinterpret_cast<uint64_t*>(p) + (size_t)(threadIdx.x >> 5) * HMK_QCAP;
+    p += (size_t)(blockDim.x >> 5) * HMK_QCAP * 8;
+    hq.s32 = nullptr;
+    if (wide) {
+        hq.s32 = reinterpret_cast<int32_t*>(p) + (size_t)(threadIdx.x >> 5) * HMK_QCAP;
+        p += (size_t)(blockDim.x >> 5) * HMK_QCAP * 4;
+    }
+    tk.cnt = reinterpret_cast<int*>(p);  p += (size_t)qt * 4;
+    tk.lock = reinterpret_cast<int*>(p); p += (size_t)qt * 4;
+    tk.ovf = reinterpret_cast<int*>(p);
+    hq.cnt = 0;
+}
+__host__ __device__ inline size_t hmk_carve_bytes(int qt, int kb, int threads, bool wide) {
+    return (size_t)qt * kb * 8 + (size_t)qt * 8 + (size_t)(threads / 32) * HMK_QCAP * (wide ? 12 : 8) + (size_t)qt * 12;
+}
+
 // ---------------------------------------------------------------- fast bulk kernel
 #define HMK_ROWB (HMK_NRES * 4)                    // bytes of one (h, j) row: 24 residues x u32
 
 template <int NW, int MODE>
-__global__ void __launch_bounds__(HMK_BULK_THREADS) hmk_bulk_fast(const __grid_constant__ HmkBulkArgs a) {
+__global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __grid_constant__ HmkBulkArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t PWB = NW * HMK_MAXL1 * HMK_ROWB;   // bytes per profile (compile time)
     const int qtile = blockIdx.x % a.nqt, stripe = blockIdx.x / a.nqt;
@@ -246,11 +332,8 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS) hmk_bulk_fast(const __grid_c
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + o);
     o += 16;
     HmkTopkSmem tk;
-    tk.key = reinterpret_cast<uint64_t*>(smem_raw + o);  o += (size_t)a.qt * a.kb * 8;
-    tk.minkey = reinterpret_cast<uint64_t*>(smem_raw + o); o += (size_t)a.qt * 8;
-    tk.cnt = reinterpret_cast<int*>(smem_raw + o);  o += (size_t)a.qt * 4;
-    tk.lock = reinterpret_cast<int*>(smem_raw + o); o += (size_t)a.qt * 4;
-    tk.ovf = reinterpret_cast<int*>(smem_raw + o);
+    HmkHitQueue hq;
+    hmk_carve(smem_raw + o, a.qt, a.kb, false, tk, hq);
 
     // ---- stage the profile tile with the TMA bulk-copy engine
     if (threadIdx.x == 0) hmk_mbar_init(bar, 1);
@@ -276,16 +359,21 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS) hmk_bulk_fast(const __grid_c
     const int32_t dec = a.sc.T - a.sc.half;
     const unsigned char* sbase = smem_raw;
 
-    for (int i = i_begin + threadIdx.x; i < i_end; i += blockDim.x) {
-        const int32_t id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
-        if (a.slot && a.slot[id] >= 0) continue;
-        const uint64_t w = a.packed[id];
+    // warp-uniform trip count; lanes past the end (or whose item is no longer a singleton)
+    // compute on a dummy item and are masked out of the hit test
+    for (int ib = i_begin + (threadIdx.x & ~31); ib < i_end; ib += blockDim.x) {
+        const int i = ib + (threadIdx.x & 31);
+        bool valid = i < i_end;
+        const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
+        if (valid && a.slot && a.slot[id] >= 0) valid = false;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const uint64_t w = valid ? a.packed[id] : 0ull;
         // rowp[j] = &profile[0][h=0][j][residue_j]; later profiles/halves are immediates away
         const unsigned char* rowp[HMK_MAXL1];
 #pragma unroll
         for (int j = 0; j < HMK_MAXL1; j++)
             rowp[j] = sbase + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u;
-        scored += qn;
+        if (valid) scored += qn;
 
         auto score = [&](const int tu, uint32_t (&acc)[NW]) {
 #pragma unroll
@@ -304,9 +392,10 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS) hmk_bulk_fast(const __grid_c
 #pragma unroll
             for (int h = 1; h < NW; h++) any |= acc[h];
             if (MODE == HMK_MODE_DENSE) {
-                a.dense[(size_t)(q0 + t) * a.dense_stride + i] = hmk_lane_max(acc, NW, a.sc.lane16) + dec;
-            } else if (any & topmask) {
-                hmk_handle_hit<MODE>(a, tk, t, q0 + t, i, id, hmk_lane_max(acc, NW, a.sc.lane16) + dec);
+                if (valid) a.dense[(size_t)(q0 + t) * a.dense_stride + i] = hmk_lane_max(acc, NW, a.sc.lane16) + dec;
+            } else {
+                const bool hit = valid && (any & topmask) != 0;
+                hmk_queue_push<MODE>(a, tk, q0, hq, hit, t, hit ? hmk_lane_max(acc, NW, a.sc.lane16) + dec : 0, i);
             }
         };
 
@@ -326,6 +415,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS) hmk_bulk_fast(const __grid_c
             for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += PWB;
         }
     }
+    if (MODE != HMK_MODE_DENSE && hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
     if (a.pair_counter) {
         for (int s = 16; s > 0; s >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, s);
         if ((threadIdx.x & 31) == 0 && scored) atomicAdd(a.pair_counter, scored);
@@ -350,8 +440,10 @@ struct HmkGenericArgs {
     int32_t maxlen;
 };
 
+#define HMK_GENERIC_THREADS 256
+
 template <int MODE>
-__global__ void __launch_bounds__(256) hmk_bulk_generic(const __grid_constant__ HmkGenericArgs g) {
+__global__ void __launch_bounds__(HMK_GENERIC_THREADS) hmk_bulk_generic(const __grid_constant__ HmkGenericArgs g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const HmkBulkArgs& a = g.b;
     const int qtile = blockIdx.x % a.nqt, stripe = blockIdx.x / a.nqt;
@@ -360,13 +452,11 @@ __global__ void __launch_bounds__(256) hmk_bulk_generic(const __grid_constant__ 
     if (qn <= 0) return;
     int32_t* sM = reinterpret_cast<int32_t*>(smem_raw);
     size_t o = HMK_NRES * HMK_NRES * 4;
-    int32_t* slen = reinterpret_cast<int32_t*>(smem_raw + o); o += (size_t)a.qt * 4;
     HmkTopkSmem tk;
-    tk.key = reinterpret_cast<uint64_t*>(smem_raw + ((o + 7) & ~(size_t)7)); o = ((o + 7) & ~(size_t)7) + (size_t)a.qt * a.kb * 8;
-    tk.minkey = reinterpret_cast<uint64_t*>(smem_raw + o); o += (size_t)a.qt * 8;
-    tk.cnt = reinterpret_cast<int*>(smem_raw + o);  o += (size_t)a.qt * 4;
-    tk.lock = reinterpret_cast<int*>(smem_raw + o); o += (size_t)a.qt * 4;
-    tk.ovf = reinterpret_cast<int*>(smem_raw + o);  o += (size_t)a.qt * 4;
+    HmkHitQueue hq;
+    hmk_carve(smem_raw + o, a.qt, a.kb, true, tk, hq);
+    o += hmk_carve_bytes(a.qt, a.kb, HMK_GENERIC_THREADS, true);
+    int32_t* slen = reinterpret_cast<int32_t*>(smem_raw + o); o += (size_t)a.qt * 4;
     uint8_t* sres = smem_raw + o;   // [qt][maxlen]
     for (int i = threadIdx.x; i < HMK_NRES * HMK_NRES; i += blockDim.x) sM[i] = g.M[i];
     for (int t = threadIdx.x; t < qn; t += blockDim.x) {
@@ -380,20 +470,27 @@ __global__ void __launch_bounds__(256) hmk_bulk_generic(const __grid_constant__ 
     const int i_begin = stripe * a.chunk;
     const int i_end = min(a.ndb, i_begin + a.chunk);
     unsigned long long scored = 0;
-    for (int i = i_begin + threadIdx.x; i < i_end; i += blockDim.x) {
-        const int32_t id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
-        if (a.slot && a.slot[id] >= 0) continue;
+    for (int ib = i_begin + (threadIdx.x & ~31); ib < i_end; ib += blockDim.x) {
+        const int i = ib + (threadIdx.x & 31);
+        bool valid = i < i_end;
+        const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
+        if (valid && a.slot && a.slot[id] >= 0) valid = false;
+        if (!__any_sync(0xffffffffu, valid)) continue;
         const uint8_t* dres = g.res + g.off[id];
-        const int dlen = g.off[id + 1] - g.off[id];
-        scored += qn;
+        const int dlen = valid ? g.off[id + 1] - g.off[id] : 0;
+        if (valid) scored += qn;
         for (int t = 0; t < qn; t++) {
             const uint8_t* pres = sres + (size_t)t * g.maxlen;
-            int32_t s = g.prof_is_query ? hmk_pair_score(dres, dlen, pres, slen[t], sM, a.sc.X, a.sc.P)
-                                        : hmk_pair_score(pres, slen[t], dres, dlen, sM, a.sc.X, a.sc.P);
-            if (MODE == HMK_MODE_DENSE) a.dense[(size_t)(q0 + t) * a.dense_stride + i] = s;
-            else if (s >= a.sc.T) hmk_handle_hit<MODE>(a, tk, t, q0 + t, i, id, s);
+            int32_t s = 0;
+            if (valid)
+                s = g.prof_is_query ? hmk_pair_score(dres, dlen, pres, slen[t], sM, a.sc.X, a.sc.P)
+                                    : hmk_pair_score(pres, slen[t], dres, dlen, sM, a.sc.X, a.sc.P);
+            __syncwarp();
+            if (MODE == HMK_MODE_DENSE) { if (valid) a.dense[(size_t)(q0 + t) * a.dense_stride + i] = s; }
+            else hmk_queue_push<MODE>(a, tk, q0, hq, valid && s >= a.sc.T, t, s, i);
         }
     }
+    if (MODE != HMK_MODE_DENSE && hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
     if (a.pair_counter) {
         for (int s = 16; s > 0; s >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, s);
         if ((threadIdx.x & 31) == 0 && scored) atomicAdd(a.pair_counter, scored);
@@ -463,6 +560,39 @@ __global__ void hmk_select_queries(const int32_t* __restrict__ slot, int n, cons
     if (threadIdx.x == 0) *nq_out = base < want ? base : want;
 }
 
+// ---------------------------------------------------------------- one-at-a-time pair scores
+// S(member, query) for the irregular parts of the path (member checks, phase-2 resolution).
+// Uniform length <= 12: residues come from the two packed words and the matrix from shared
+// memory; otherwise the generic byte path.  Java-int arithmetic either way.
+struct HmkScalar {
+    const uint64_t* packed;   // NULL -> generic path
+    const int32_t* sM;        // 24x24 in shared memory
+    int32_t L;
+};
+
+__device__ __forceinline__ void hmk_load_matrix_smem(int32_t* sM, const int32_t* M) {
+    for (int i = threadIdx.x; i < HMK_NRES * HMK_NRES; i += blockDim.x) sM[i] = M[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ int32_t hmk_scalar_score(const HmkState& S, const HmkScalar& sc, int32_t member, int32_t query) {
+    if (!sc.packed) return hmk_state_score(S, member, query);
+    const uint64_t wm = sc.packed[member], wq = sc.packed[query];
+    const int L = sc.L;
+    int32_t best = HMK_JMIN;
+    for (int k = -S.X; k <= S.X; k++) {       // equal lengths: shorter = query (second argument)
+        const int j0 = k > 0 ? k : 0, j1 = k < 0 ? L + k : L;
+        int32_t v = 0;
+        for (int j = j0; j < j1; j++) {
+            const uint32_t rq = (uint32_t)(wq >> (5 * (j - k))) & 31u, rm = (uint32_t)(wm >> (5 * j)) & 31u;
+            v = hmk_wadd(v, sc.sM[rq * HMK_NRES + rm]);
+        }
+        v = hmk_wadd(v, hmk_wmul(2 * (k < 0 ? -k : k), S.P));
+        if (v > best) best = v;
+    }
+    return best;
+}
+
 // ---------------------------------------------------------------- member check (complete linkage)
 // One thread per founder hit: does the query also score >= T against every other current
 // member of that cluster?  (ClinkageClusterScorer.java:30-49; early exit keeps it cheap.)
@@ -473,8 +603,8 @@ struct HmkCheckArgs {
     unsigned int hit_cap;
     int32_t hit_t_is_query;      // 1: hit.x = query index, hit.y = cluster slot; 0: the reverse
     const int32_t* qids;         // query index -> sequence id
-    // phase 1 output: linked lists per query
-    int32_t* ac_head; int32_t* ac_next; int32_t* ac_slot; int32_t* ac_score;
+    // phase 1 output: per-query arrays ac_slot/ac_score[qi * capq + k], k < ac_cnt[qi]
+    int32_t* ac_cnt; int32_t* ac_slot; int32_t* ac_score; int32_t capq;
     // phase 2 output: flat candidate arrays
     unsigned long long* cand_key_q;   // (query index << 32) | slot
     unsigned long long* cand_key_c;   // (slot << 32) | query index
@@ -483,9 +613,15 @@ struct HmkCheckArgs {
     unsigned int cand_cap;
     int32_t linked;
     int32_t q_index_offset;      // added to the query index in the flat candidate keys
+    const uint64_t* packed;      // non-NULL: uniform length <= 12, use the packed scalar scorer
+    int32_t L;
 };
 
 __global__ void hmk_member_check(const HmkCheckArgs a) {
+    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    hmk_load_matrix_smem(sM, a.S.M);
+    HmkScalar sc;
+    sc.packed = a.packed; sc.sM = sM; sc.L = a.L;
     const unsigned int nh = min(*a.hit_count, a.hit_cap);
     long long npairs = 0;
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < nh; e += gridDim.x * blockDim.x) {
@@ -495,19 +631,23 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         int32_t cl = h.z;
         bool ok = true;
         for (int32_t m = a.S.next[a.S.c_founder[c]]; m >= 0; m = a.S.next[m]) {
-            int32_t s = hmk_state_score(a.S, m, q);
+            int32_t s = hmk_scalar_score(a.S, sc, m, q);
             npairs++;
             if (s < cl) cl = s;
             if (s < a.S.T) { ok = false; break; }
         }
         if (!ok) continue;
+        if (a.linked) {
+            const int k = atomicAdd(a.ac_cnt + qi, 1);     // the resolver checks ac_cnt against capq
+            if (k < a.capq) {
+                a.ac_slot[(size_t)qi * a.capq + k] = c;
+                a.ac_score[(size_t)qi * a.capq + k] = cl;
+            }
+            continue;
+        }
         unsigned int pos = atomicAdd(a.cand_count, 1u);
         if (pos >= a.cand_cap) continue;
-        if (a.linked) {
-            a.ac_slot[pos] = c;
-            a.ac_score[pos] = cl;
-            a.ac_next[pos] = atomicExch(a.ac_head + qi, (int32_t)pos);
-        } else {
+        {
             const uint32_t gq = (uint32_t)(qi + a.q_index_offset);
             a.cand_key_q[pos] = ((unsigned long long)gq << 32) | (uint32_t)c;
             a.cand_key_c[pos] = ((unsigned long long)(uint32_t)c << 32) | gq;
@@ -518,16 +658,413 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
     if ((threadIdx.x & 31) == 0 && npairs) atomicAdd((unsigned long long*)&a.S.ctl->scalar_pairs, (unsigned long long)npairs);
 }
 
-// ---------------------------------------------------------------- resolvers
-__global__ void hmk_p1_resolve_kernel(const HmkState S, const HmkP1Batch B) {
-    HmkWarp w;
-    hmk_p1_resolve(S, B, w);
+// ---------------------------------------------------------------- phase-1 resolver
+// Replays firstPhase (LimitedGreedySequenceClusterer.java:90-116) for one batch in reference
+// order.  One warp; every per-query step is lane-parallel (partner list, static cluster
+// candidates, bitmask tests) so a step costs a few dependent memory round trips.
+// Bookkeeping of what changed inside the batch lives in shared memory:
+//   touched table: clusters that received members in this batch -> bitmask of the batch
+//   queries that joined/founded them (+ the partner's sequence id for clusters born here)
+//   founder mask : batch queries that founded a cluster in this batch
+// ibm[b] is the bitmask of earlier batch queries b2 with S(q_b2, q_b) >= T, so "every added
+// member scores >= T" is (member mask & ~ibm[b]) == 0.
+#define HMK_MAXBATCH 512
+#define HMK_MAXW (HMK_MAXBATCH / 32)
+
+struct HmkP1Batch {
+    int32_t nq, batch_id;
+    const int32_t* qid;       // [nq] ascending ids, all singletons at batch start
+    int32_t kb;               // <= 32
+    const uint64_t* bk_key;   // [nq][kb] best later singletons at batch start, descending
+    const int32_t* bk_cnt;    // [nq]
+    const int32_t* bk_ovf;    // [nq] 1 = more hits existed than the list holds
+    int32_t capq;
+    const int32_t* ac_cnt;    // [nq] pre-batch clusters whose every pre-batch member scores >= T
+    const int32_t* ac_slot;   // [nq][capq]
+    const int32_t* ac_score;  // min over the pre-batch members
+    const int32_t* ib;        // ib[b*ib_stride + b2] = S(member = qid[b2], query = qid[b])
+    int32_t ib_stride;
+    const uint32_t* ibm;      // [nq][nw]
+    int32_t nw;
+    int32_t* c_stamp;         // [K] batch id of the cluster's last change
+    int32_t* c_tidx;          // [K] its row in the touched table
+    const uint64_t* packed;   // scalar scorer (NULL -> generic)
+    int32_t L;
+};
+
+__global__ void hmk_ib_mask(int nq, int nw, int32_t T, const int32_t* __restrict__ ib, int stride, uint32_t* __restrict__ ibm) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * nw) return;
+    const int b = idx / nw, w = idx % nw;
+    uint32_t m = 0;
+    for (int k = 0; k < 32; k++) {
+        const int b2 = w * 32 + k;
+        if (b2 < b && ib[(size_t)b * stride + b2] >= T) m |= 1u << k;
+    }
+    ibm[idx] = m;
 }
 
-__global__ void hmk_p2_round_kernel(const HmkState S, const HmkP2 P) {
-    HmkWarp w;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c < P.ncl) hmk_p2_round(S, P, w, c);
+__device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        HmkBestCluster o;
+        o.score = __shfl_xor_sync(0xffffffffu, b.score, s);
+        o.size = __shfl_xor_sync(0xffffffffu, b.size, s);
+        o.fid = __shfl_xor_sync(0xffffffffu, b.fid, s);
+        o.slot = __shfl_xor_sync(0xffffffffu, b.slot, s);
+        if (o.slot >= 0) hmk_consider(b, o.score, o.size, o.fid, o.slot);
+    }
+}
+
+__global__ void __launch_bounds__(32) hmk_p1_resolve_kernel(const HmkState S, const HmkP1Batch B) {
+    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    __shared__ int32_t t_partner[HMK_MAXBATCH], f_slot[HMK_MAXBATCH];
+    __shared__ uint32_t t_mask[HMK_MAXBATCH][HMK_MAXW];
+    const int lane = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    hmk_load_matrix_smem(sM, S.M);
+    HmkScalar sc;
+    sc.packed = B.packed; sc.sM = sM; sc.L = B.L;
+    HmkCtl* ctl = S.ctl;
+    int32_t ncl = ctl->ncl, unproc = ctl->unproc_alive;
+    int32_t steps = ctl->steps, joins = ctl->joins, creates = ctl->creates, orphans = ctl->orphans;
+    int32_t status = HMK_P1_CONTINUE, npe_step = -1, cur = ctl->cur;
+    int32_t tn = 0;                 // rows of the touched table
+    uint32_t fmask = 0;             // this lane's word of the founder mask
+    long long npairs = 0;
+    const int nw = B.nw;
+
+    // complete linkage over the members cluster row `tidx` received in this batch
+    auto eval_touched = [&](int tidx, uint32_t hm, int b, int32_t q, int32_t& cl) -> bool {
+        uint32_t tm = lane < nw ? t_mask[tidx][lane] : 0u;
+        bool fail = (tm & ~hm) != 0;
+        int32_t mn = cl;
+        while (tm) {
+            const int b2 = lane * 32 + __ffs(tm) - 1;
+            tm &= tm - 1;
+            const int32_t s = B.ib[(size_t)b * B.ib_stride + b2];
+            mn = s < mn ? s : mn;
+        }
+        fail = __any_sync(FULL, fail);
+        mn = __reduce_min_sync(FULL, mn);
+        const int32_t partner = t_partner[tidx];
+        if (!fail && partner >= 0) {
+            int32_t s = 0;
+            if (lane == 0) { s = hmk_scalar_score(S, sc, partner, q); npairs++; }
+            s = __shfl_sync(FULL, s, 0);
+            if (s < S.T) fail = true;
+            mn = s < mn ? s : mn;
+        }
+        cl = mn;
+        return !fail;
+    };
+
+    for (int b = 0; b < B.nq; b++) {
+        const int32_t q = B.qid[b];
+        if (ncl >= S.K) { status = HMK_P1_DONE; cur = q; break; }                   // :90
+        if (__ldcg(S.slot + q) >= 0) continue;   // consumed as a partner earlier in this batch (:101,110)
+        const int32_t acnt = B.ac_cnt[b];
+        if (acnt > B.capq) { status = HMK_P1_GROW; cur = q; break; }   // candidate arrays too small: host grows them
+
+        // ---- B: nearest among initialList[index+1 ..]                               (:93)
+        int bkind = 0;   // 0 = Java null, 1 = found, 2 = (null cluster, MIN_VALUE) object
+        int32_t bscore = HMK_JMIN, bid = -1;
+        if (unproc - 1 == 0) bkind = 2;            // empty sub-list (ClinkageSequenceClusterer.java:138-140)
+        else {
+            const int32_t cnt = B.bk_cnt[b];
+            uint64_t key = 0;
+            int32_t id = -1;
+            bool alive = false;
+            if (lane < cnt) {
+                key = B.bk_key[(size_t)b * B.kb + lane];
+                const uint32_t r = hmk_key_rank(key);
+                id = S.id_of_rank ? S.id_of_rank[r] : (int32_t)r;
+                alive = __ldcg(S.slot + id) < 0;
+            }
+            const unsigned am = __ballot_sync(FULL, alive);
+            if (am) {
+                const int src = __ffs(am) - 1;      // list is sorted: first alive entry wins
+                bid = __shfl_sync(FULL, id, src);
+                bscore = hmk_key_score(__shfl_sync(FULL, key, src));
+                bkind = 1;
+            } else if (B.bk_ovf[b]) {
+                status = HMK_P1_RESTART; cur = q; break;    // list truncated: rescore from q
+            }
+        }
+
+        // ---- A: nearest among actualClusters (complete linkage)                      (:92)
+        int akind = 0;
+        HmkBestCluster best;
+        best.score = HMK_JMIN; best.size = 0; best.fid = 0; best.slot = -1;
+        if (ncl == 0) akind = 2;
+        else {
+            const uint32_t hm = lane < nw ? B.ibm[(size_t)b * nw + lane] : 0u;
+            // pre-batch clusters: untouched ones are final, touched ones need the batch members too
+            for (int e0 = 0; e0 < acnt; e0 += 32) {
+                const int e = e0 + lane;
+                int32_t c = -1, cl = 0;
+                bool touched = false;
+                if (e < acnt) {
+                    c = B.ac_slot[(size_t)b * B.capq + e];
+                    cl = B.ac_score[(size_t)b * B.capq + e];
+                    touched = __ldcg(B.c_stamp + c) == B.batch_id;
+                    if (!touched) hmk_consider(best, cl, __ldcg(S.c_size + c), __ldcg(S.c_founder + c), c);
+                }
+                unsigned tmk = __ballot_sync(FULL, touched);
+                while (tmk) {
+                    const int src = __ffs(tmk) - 1;
+                    tmk &= tmk - 1;
+                    const int32_t c2 = __shfl_sync(FULL, c, src);
+                    int32_t cl2 = __shfl_sync(FULL, cl, src);
+                    if (eval_touched(__ldcg(B.c_tidx + c2), hm, b, q, cl2) && lane == 0)
+                        hmk_consider(best, cl2, __ldcg(S.c_size + c2), __ldcg(S.c_founder + c2), c2);
+                }
+            }
+            // clusters born in this batch whose founder scores >= T
+            unsigned fm = __ballot_sync(FULL, (fmask & hm) != 0);
+            while (fm) {
+                const int src = __ffs(fm) - 1;
+                fm &= fm - 1;
+                uint32_t bits = __shfl_sync(FULL, fmask & hm, src);
+                while (bits) {
+                    const int b2 = src * 32 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int32_t c2 = f_slot[b2];
+                    int32_t cl2 = HMK_JMAX;
+                    if (eval_touched(__ldcg(B.c_tidx + c2), hm, b, q, cl2) && lane == 0)
+                        hmk_consider(best, cl2, __ldcg(S.c_size + c2), __ldcg(S.c_founder + c2), c2);
+                }
+            }
+            hmk_best_reduce(best);
+            if (best.slot >= 0) akind = 1;
+        }
+
+        // ---- decision                                                               (:94-114)
+        const int32_t ascore = akind == 1 ? best.score : HMK_JMIN;
+        bool join = false, create = false;
+        if (akind != 0) {
+            if (bkind != 0) { if (ascore >= bscore) join = true; else create = true; }
+            else join = true;
+        } else if (bkind != 0) create = true;
+        if ((join && akind == 2) || (create && bkind == 2)) {    // null.insertAll / null.getSequences
+            status = HMK_P1_NPE; npe_step = steps; cur = q; break;
+        }
+        if (join || create) {
+            const int32_t c = join ? best.slot : ncl;
+            int tidx;
+            const bool fresh = create || __ldcg(B.c_stamp + c) != B.batch_id;
+            tidx = fresh ? tn : __ldcg(B.c_tidx + c);
+            if (fresh) {
+                if (lane < HMK_MAXW) t_mask[tidx][lane] = 0;
+                if (lane == 0) { t_partner[tidx] = create ? bid : -1; B.c_stamp[c] = B.batch_id; B.c_tidx[c] = tidx; }
+                tn++;
+            }
+            __syncwarp();
+            if (lane == (b >> 5)) t_mask[tidx][lane] |= 1u << (b & 31);
+            if (create) {
+                if (lane == (b >> 5)) fmask |= 1u << (b & 31);
+                if (lane == 0) f_slot[b] = c;
+            }
+            if (lane == 0) {
+                if (join) {
+                    const int32_t tail = S.c_tail[c];
+                    S.next[tail] = q; S.next[q] = -1; S.c_tail[c] = q;
+                    const int32_t cnt = S.c_count[c];
+                    S.rank[q] = cnt; S.c_count[c] = cnt + 1;
+                    S.c_size[c] = hmk_wadd(__ldcg(S.c_size + c), S.ab[q]);
+                    S.slot[q] = c;
+                } else {
+                    S.c_founder[c] = q; S.c_tail[c] = bid; S.c_count[c] = 2;
+                    S.c_size[c] = hmk_wadd(S.ab[q], S.ab[bid]);
+                    S.next[q] = bid; S.next[bid] = -1;
+                    S.slot[q] = c; S.rank[q] = 0; S.slot[bid] = c; S.rank[bid] = 1;
+                }
+            }
+        }
+        if (join) joins++;
+        else if (create) { ncl++; unproc--; creates++; }
+        else orphans++;
+        steps++;
+        unproc--;
+        cur = q + 1;
+        __threadfence_block();
+        __syncwarp();
+    }
+    if (status == HMK_P1_CONTINUE && (ncl >= S.K || unproc <= 0)) status = HMK_P1_DONE;
+    if (lane == 0) {
+        ctl->cur = cur; ctl->ncl = ncl; ctl->unproc_alive = unproc; ctl->status = status;
+        if (npe_step >= 0) ctl->npe_step = npe_step;
+        ctl->steps = steps; ctl->joins = joins; ctl->creates = creates; ctl->orphans = orphans;
+        if (status == HMK_P1_RESTART) ctl->restarts += 1;
+        if (npairs) atomicAdd((unsigned long long*)&ctl->scalar_pairs, (unsigned long long)npairs);
+    }
+}
+
+// ---------------------------------------------------------------- phase 2: windowed resolution
+// Candidate pairs (query q, cluster c) -- founder and every phase-1 member score >= T -- are
+// held grouped by query (cq_*) and grouped by cluster in query order (cc_q).  Queries are
+// resolved in windows of consecutive queries.  Inside a window the reference's sequential
+// decisions (LimitedGreedySequenceClusterer.java:59-66) are the unique fixed point of
+//     A[q] = best valid cluster of q given { q' < q : A[q'] = c } as extra members of c,
+// reached by iterating that map from A = "nobody joins" (after t iterations the first t
+// queries are final; in practice a handful of iterations suffice).  Members that joined in
+// earlier windows are final and folded into base_cl once per window.
+struct HmkP2 {
+    HmkState S;
+    const uint64_t* packed;   // NULL -> generic scalar scorer
+    int32_t L;
+    int32_t ncl, ns;
+    const int32_t* singles;   // [ns] ascending ids of the phase-2 queries
+    const int32_t* qstart;    // [ns+1] into cq_*
+    const int32_t* cq_c;      // candidate cluster slot (ascending inside a query)
+    const int32_t* cq_s;      // complete-linkage min over the phase-1 members
+    const int32_t* cstart;    // [ncl+1] into cc_q / dyn / tent
+    const int32_t* cc_q;      // query index (into singles), ascending inside a cluster
+    int32_t* dyn;             // final phase-2 members (sequence ids): dyn[cstart[c] + t]
+    int32_t* dyn_n;           // [ncl]
+    int32_t* base_cl;         // per pair: min over phase-1 and final phase-2 members, JMIN = invalid
+    int32_t* wlo;             // [ncl] first cc_q position of the current window
+    int32_t* tent;            // tentative in-window joiners (query indices): tent[wlo[c] + t]
+    int32_t* tent_n;          // [ncl]
+    const int32_t* a_cur;     // [ns] tentative assignment of this iteration (-1 = none)
+    int32_t* a_new;
+    int32_t* changed;
+    const int32_t* dirty_cur; // [ncl] smallest query whose tentative assignment to/from c changed last iteration
+    int32_t* dirty_nxt;
+    int32_t qa, qb;           // window = queries [qa, qb)
+};
+
+// fold the members that joined in earlier windows into the per-pair base value
+__global__ void hmk_p2_base(const HmkP2 P) {
+    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    hmk_load_matrix_smem(sM, P.S.M);
+    HmkScalar sc;
+    sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
+    const int e0 = P.qstart[P.qa], e1 = P.qstart[P.qb];
+    long long npairs = 0;
+    for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+        // query of pair e: binary search in qstart
+        int lo = P.qa, hi = P.qb - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.qstart[mid] <= e) lo = mid; else hi = mid - 1; }
+        const int32_t q = P.singles[lo];
+        const int32_t c = P.cq_c[e];
+        int32_t cl = P.cq_s[e];
+        const int32_t* dm = P.dyn + P.cstart[c];
+        const int32_t nd = P.dyn_n[c];
+        for (int t = 0; t < nd; t++) {
+            int32_t s = hmk_scalar_score(P.S, sc, dm[t], q);   // ClinkageClusterScorer.java:36-44
+            npairs++;
+            if (s < cl) cl = s;
+            if (s < P.S.T) { cl = HMK_JMIN; break; }
+        }
+        P.base_cl[e] = cl;
+    }
+    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
+    if ((threadIdx.x & 31) == 0 && npairs) atomicAdd((unsigned long long*)&P.S.ctl->scalar_pairs, (unsigned long long)npairs);
+}
+
+__global__ void hmk_p2_window_lo(const HmkP2 P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncl) return;
+    int lo = P.cstart[c], hi = P.cstart[c + 1];
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cc_q[mid] < P.qa) lo = mid + 1; else hi = mid; }
+    P.wlo[c] = lo;
+}
+
+__global__ void hmk_p2_build_tent(const HmkP2 P) {
+    const int qi = P.qa + blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= P.qb) return;
+    const int32_t c = P.a_cur[qi];
+    if (c < 0) return;
+    const int pos = atomicAdd(P.tent_n + c, 1);
+    P.tent[P.wlo[c] + pos] = qi;
+}
+
+__global__ void hmk_p2_sort_tent(const HmkP2 P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncl) return;
+    const int n = P.tent_n[c];
+    int32_t* t = P.tent + P.wlo[c];
+    for (int i = 1; i < n; i++) {
+        int32_t v = t[i];
+        int j = i - 1;
+        while (j >= 0 && t[j] > v) { t[j + 1] = t[j]; j--; }
+        t[j + 1] = v;
+    }
+}
+
+// one warp per window query: its decision given the tentative joiners before it.  A query is
+// re-evaluated only if one of its candidate clusters changed (tentatively) at a position
+// before it in the previous iteration (dirty_cur[c] < qi).
+__global__ void hmk_p2_decide(const HmkP2 P) {
+    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    hmk_load_matrix_smem(sM, P.S.M);
+    HmkScalar sc;
+    sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
+    const int lane = threadIdx.x & 31;
+    const int qi = P.qa + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (qi >= P.qb) return;
+    const int e0 = P.qstart[qi], e1 = P.qstart[qi + 1];
+    const int32_t old = P.a_cur[qi];
+    bool dirty = false;
+    for (int e = e0 + lane; e < e1; e += 32) dirty |= P.dirty_cur[P.cq_c[e]] < qi;
+    if (!__any_sync(0xffffffffu, dirty)) {
+        if (lane == 0) P.a_new[qi] = old;
+        return;
+    }
+    const int32_t q = P.singles[qi];
+    long long npairs = 0;
+    HmkBestCluster best;
+    best.score = HMK_JMIN; best.size = 0; best.fid = 0; best.slot = -1;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        int32_t cl = P.base_cl[e];
+        if (cl == HMK_JMIN) continue;
+        const int32_t c = P.cq_c[e];
+        int32_t size = P.S.c_size[c];
+        const int32_t* t = P.tent + P.wlo[c];
+        const int32_t nt = P.tent_n[c];
+        bool ok = true;
+        for (int i = 0; i < nt; i++) {
+            const int32_t mi = t[i];
+            if (mi >= qi) break;
+            const int32_t m = P.singles[mi];
+            const int32_t s = hmk_scalar_score(P.S, sc, m, q);
+            npairs++;
+            if (s < P.S.T) { ok = false; break; }
+            if (s < cl) cl = s;
+            size = hmk_wadd(size, P.S.ab[m]);
+        }
+        if (ok) hmk_consider(best, cl, size, P.S.c_founder[c], c);
+    }
+    hmk_best_reduce(best);
+    if (lane == 0) {
+        P.a_new[qi] = best.slot;
+        if (best.slot != old) {
+            *P.changed = 1;
+            if (old >= 0) atomicMin(P.dirty_nxt + old, qi);
+            if (best.slot >= 0) atomicMin(P.dirty_nxt + best.slot, qi);
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
+    if (lane == 0 && npairs) atomicAdd((unsigned long long*)&P.S.ctl->scalar_pairs, (unsigned long long)npairs);
+}
+
+// window converged: the tentative joiners become final members, in query order
+__global__ void hmk_p2_commit(const HmkP2 P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncl) return;
+    const int n = P.tent_n[c];
+    if (n == 0) return;
+    const int32_t* t = P.tent + P.wlo[c];
+    int32_t nd = P.dyn_n[c], cnt = P.S.c_count[c], size = P.S.c_size[c];
+    for (int i = 0; i < n; i++) {
+        const int32_t q = P.singles[t[i]];
+        P.dyn[P.cstart[c] + nd++] = q;
+        P.S.rank[q] = cnt++;
+        size = hmk_wadd(size, P.S.ab[q]);
+        P.S.slot[q] = c;
+    }
+    P.dyn_n[c] = nd; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
 }
 
 // ---------------------------------------------------------------- small utilities

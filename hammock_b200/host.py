@@ -487,6 +487,11 @@ class GreedyContext:
         self._L.hmk_get_stats(self._h, C.byref(st))
         return st.as_dict()
 
+    def section_ms(self) -> dict:
+        buf = (C.c_double * len(_lib.SECTIONS))()
+        self._L.hmk_get_section_ms(self._h, buf, len(_lib.SECTIONS))
+        return {k: float(buf[i]) for i, k in enumerate(_lib.SECTIONS)}
+
     def score_block(self, first_ids, second_ids) -> np.ndarray:
         """scores[a, b] = ShiftedScorer.sequenceScore(seq1 = first_ids[a], seq2 = second_ids[b])."""
         f = np.ascontiguousarray(first_ids, dtype=np.int32)

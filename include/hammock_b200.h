@@ -96,6 +96,11 @@ int hmk_upload(hmk_ctx* ctx, const hmk_greedy_in* in, char* errbuf, size_t errle
 int hmk_run(hmk_ctx* ctx, char* errbuf, size_t errlen);
 int hmk_download(hmk_ctx* ctx, hmk_greedy_out* out, char* errbuf, size_t errlen);
 int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats);
+/* device time per section of the last run (only filled when option "profile" is 1):
+ * p1_select, p1_partner, p1_cluster, p1_intra, p1_resolve, p2_setup, p2_filter, p2_check, p2_sort,
+ * p2_base, p2_iterate, p2_commit, final */
+#define HMK_NSECTIONS 13
+int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n);
 /* tuning knobs (batch size, tile sizes, ...); unknown names return HMK_STATUS_BAD_ARG */
 int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value);
 

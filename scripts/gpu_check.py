@@ -66,7 +66,7 @@ for generic in (0, 1):
 
 T, X, P, K = (int(v) for v in z["params"])
 ref = (0, z["cluster_id"], z["member_rank"], z["result_order"])
-for opts in ({}, {"force_generic": 1}, {"batch": 7, "kb": 1}, {"batch": 64, "kb": 2, "qt": 16}, {"p2_chunk": 1024, "hit_cap": 2048, "round_check": 1}):
+for opts in ({}, {"force_generic": 1}, {"batch": 7, "kb": 1}, {"batch": 64, "kb": 2, "qt": 16}, {"p2_chunk": 1024, "hit_cap": 2048, "p2_window": 100, "capq": 1}):
     cmp("musi", z, T, X, P, K, ref, **opts)
 d = synth.generate(3000, 7, 12, seed=5)
 T2, X2, K2 = synth.default_params(d["lengths"])

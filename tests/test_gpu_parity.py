@@ -156,7 +156,7 @@ def test_empty_and_tiny_inputs(blosum62):
 
 
 @pytest.mark.parametrize("opts", [{}, {"force_generic": 1}, {"batch": 7, "kb": 1}, {"batch": 64, "kb": 2, "qt": 16},
-                                  {"batch": 1000, "waves": 1}, {"p2_chunk": 1024, "hit_cap": 2048, "round_check": 1}])
+                                  {"batch": 1000, "waves": 1}, {"p2_chunk": 1024, "hit_cap": 2048, "p2_window": 100, "capq": 1}])
 def test_musi_golden_gpu(golden_dir, blosum62, opts):
     z = np.load(os.path.join(golden_dir, "musi.npz"))
     T, X, P, K = (int(v) for v in z["params"])
