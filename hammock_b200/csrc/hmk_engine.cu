@@ -103,6 +103,8 @@ public:
         CK(cudaEventCreate(&ev_a_));
         CK(cudaEventCreate(&ev_b_));
         CK(cudaEventCreate(&ev_c_));
+        CK(cudaEventCreate(&ev_t0_));
+        CK(cudaEventCreate(&ev_t1_));
     }
     ~Engine() {
         cudaSetDevice(device_);
@@ -110,6 +112,8 @@ public:
         if (ev_a_) cudaEventDestroy(ev_a_);
         if (ev_b_) cudaEventDestroy(ev_b_);
         if (ev_c_) cudaEventDestroy(ev_c_);
+        if (ev_t0_) cudaEventDestroy(ev_t0_);
+        if (ev_t1_) cudaEventDestroy(ev_t1_);
         if (h_ctl_) cudaFreeHost(h_ctl_);
         if (h_scalars_) cudaFreeHost(h_scalars_);
         if (st_) cudaStreamDestroy(st_);
@@ -123,6 +127,16 @@ public:
     void score_block(const int32_t* first, int32_t nf, const int32_t* second, int32_t ns, int32_t* scores);
     hmk_stats stats{};
     int error_step = -1;
+    void timer_begin() { CK(cudaSetDevice(device_)); CK(cudaEventRecord(ev_t0_, st_)); }
+    double timer_end() {
+        CK(cudaSetDevice(device_));
+        CK(cudaEventRecord(ev_t1_, st_));
+        CK(cudaEventSynchronize(ev_t1_));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev_t0_, ev_t1_));
+        return ms;
+    }
+    void measure_peaks(double* out);
 
 private:
     // ---- problem
@@ -166,7 +180,7 @@ private:
     DevBuf<int32_t> d_cluster_id_, d_member_rank_;
     int32_t n_unassigned_ = 0;
     // ---- timing
-    cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
+    cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr, ev_t0_ = nullptr, ev_t1_ = nullptr;
     std::vector<cudaEvent_t> ev_pool_;
     size_t ev_used_ = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> bulk_events_;
@@ -806,6 +820,38 @@ void Engine::score_block(const int32_t* first, int32_t nf, const int32_t* second
     }
 }
 
+// out[0] = IADD3 lane-instructions/s, out[1] = lane-instructions/s of an IADD3 + IMAD mix,
+// out[2] = shared-memory LDS.32 bytes/s (conflict free), out[3] = SM count
+void Engine::measure_peaks(double* out) {
+    CK(cudaSetDevice(device_));
+    DevBuf<int32_t> sink;
+    const int blocks = sm_count_ * 2, threads = 1024, iters = 2000;
+    sink.reserve((size_t)blocks * threads);
+    auto time_it = [&](int which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(ev_t0_, st_));
+            if (which == 0) hmk_peak_iadd<<<blocks, threads, 0, st_>>>(iters, sink.p);
+            else if (which == 1) hmk_peak_imix<<<blocks, threads, 0, st_>>>(iters, 1, sink.p);
+            else hmk_peak_lds<<<blocks, threads, 0, st_>>>(iters, sink.p);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ev_t1_, st_));
+            CK(cudaEventSynchronize(ev_t1_));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ev_t0_, ev_t1_));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        return (double)best * 1e-3;
+    };
+    const double lanes = (double)blocks * threads;
+    // lane-instructions per second: 128 adds -> 64 IADD3 per unrolled body; the mixed kernel
+    // issues 32 IADD3 (4 add chains, fused in pairs) + 64 IMAD (4 mad chains)
+    out[0] = lanes * iters * 64 / time_it(0);
+    out[1] = lanes * iters * 96 / time_it(1);
+    out[2] = lanes * iters * 32 * 4.0 / time_it(2);
+    out[3] = sm_count_;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- C ABI
@@ -890,6 +936,21 @@ int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats) {
     if (!ctx || !stats) return HMK_STATUS_BAD_ARG;
     *stats = ctx->engine.stats;
     return HMK_STATUS_OK;
+}
+
+int hmk_timer_begin(hmk_ctx* ctx) {
+    if (!ctx) return HMK_STATUS_BAD_ARG;
+    return guarded(nullptr, 0, [&] { ctx->engine.timer_begin(); return HMK_STATUS_OK; });
+}
+
+int hmk_timer_end(hmk_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return HMK_STATUS_BAD_ARG;
+    return guarded(nullptr, 0, [&] { *ms = ctx->engine.timer_end(); return HMK_STATUS_OK; });
+}
+
+int hmk_measure_peaks(hmk_ctx* ctx, double* out4, char* errbuf, size_t errlen) {
+    if (!ctx || !out4) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] { ctx->engine.measure_peaks(out4); return HMK_STATUS_OK; });
 }
 
 int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n) {

@@ -1147,3 +1147,67 @@ __global__ void hmk_finalize(int n, const int32_t* __restrict__ slot, const int3
     cluster_id[i] = s >= 0 ? c_founder[s] : i;
     member_rank[i] = s >= 0 ? rank[i] : 0;
 }
+
+// ---------------------------------------------------------------- roofline microbenchmarks
+// Measured denominators for the roofline report ("PEAK_INT32 must be measured on
+// the box").  (a) dependent-free integer adds, 8 independent chains per thread -- ptxas fuses
+// each pair of adds into one IADD3 (checked with cuobjdump), so instructions = adds / 2;
+// (a') the same with every other chain on mad.lo (IMAD, the FMA pipe): the dual-pipe ceiling;
+// (b) conflict-free 32-bit shared-memory loads (the pipe that actually bounds hmk_bulk_fast).
+__global__ void __launch_bounds__(1024) hmk_peak_iadd(int iters, int32_t* out) {
+    int32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const int32_t b = blockIdx.x + 1;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a0) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a1) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a2) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a3) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a4) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a5) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a6) : "r"(b));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a7) : "r"(b));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+// half of the chains as add (ALU pipe), half as mad.lo (FMA pipe): the dual-pipe integer ceiling
+__global__ void __launch_bounds__(1024) hmk_peak_imix(int iters, int32_t one, int32_t* out) {
+    int32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const int32_t b = blockIdx.x + 1;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a0) : "r"(b));
+            asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a1) : "r"(b), "r"(one));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a2) : "r"(b));
+            asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a3) : "r"(b), "r"(one));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a4) : "r"(b));
+            asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a5) : "r"(b), "r"(one));
+            asm volatile("add.s32 %0, %0, %1;" : "+r"(a6) : "r"(b));
+            asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a7) : "r"(b), "r"(one));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+__global__ void __launch_bounds__(1024) hmk_peak_lds(int iters, int32_t* out) {
+    __shared__ uint32_t tab[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) tab[i] = i * 2654435761u;
+    __syncthreads();
+    uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    uint32_t idx = threadIdx.x & 31;           // distinct banks inside a warp: conflict free
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            acc0 += tab[(idx + u * 128) & 4095];
+            acc1 += tab[(idx + u * 128 + 32) & 4095];
+            acc2 += tab[(idx + u * 128 + 64) & 4095];
+            acc3 += tab[(idx + u * 128 + 96) & 4095];
+        }
+        idx = (idx + 1024) & 4095 & ~31u | (threadIdx.x & 31);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (int32_t)(acc0 ^ acc1 ^ acc2 ^ acc3);
+}

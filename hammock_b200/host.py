@@ -378,6 +378,14 @@ def initial_clusters_limit(sequences) -> int:                  # Hammock.java:39
 
 
 # ---------------------------------------------------------------- packing + C ABI
+def shard_range(n: int, world: int, rank: int):
+    """Contiguous share [lo, hi) of n work items for `rank` of `world` (same split as the library's
+    hmk_shard_range: sizes differ by at most one)."""
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return lo, hi
+
+
 def pack_sequences(sequences: Sequence[UniqueSequence]):
     n = len(sequences)
     offs = np.zeros(n + 1, dtype=np.int32)
@@ -486,6 +494,23 @@ class GreedyContext:
         st = _lib.Stats()
         self._L.hmk_get_stats(self._h, C.byref(st))
         return st.as_dict()
+
+    def timer_begin(self):
+        self._L.hmk_timer_begin(self._h)
+
+    def timer_end(self) -> float:
+        ms = C.c_double(0)
+        self._L.hmk_timer_end(self._h, C.byref(ms))
+        return float(ms.value)
+
+    def measure_peaks(self) -> dict:
+        buf = (C.c_double * 4)()
+        err = C.create_string_buffer(512)
+        rc = self._L.hmk_measure_peaks(self._h, buf, err, 512)
+        if rc:
+            _raise_status(rc, err.value)
+        return {"int32_iadd3_per_s": buf[0], "int32_mix_per_s": buf[1], "smem_lds_bytes_per_s": buf[2],
+                "sm_count": int(buf[3])}
 
     def section_ms(self) -> dict:
         buf = (C.c_double * len(_lib.SECTIONS))()

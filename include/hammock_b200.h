@@ -96,6 +96,14 @@ int hmk_upload(hmk_ctx* ctx, const hmk_greedy_in* in, char* errbuf, size_t errle
 int hmk_run(hmk_ctx* ctx, char* errbuf, size_t errlen);
 int hmk_download(hmk_ctx* ctx, hmk_greedy_out* out, char* errbuf, size_t errlen);
 int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats);
+/* CUDA-event stopwatch on the library's stream (brackets upload + run + download for end-to-end
+ * timing); hmk_timer_end synchronises and returns milliseconds. */
+int hmk_timer_begin(hmk_ctx* ctx);
+int hmk_timer_end(hmk_ctx* ctx, double* ms);
+/* roofline denominators measured on this device: out4[0] IADD3 lane-instructions/s (the INT32 ALU
+ * peak), out4[1] lane-instructions/s of an IADD3 + IMAD mix (both integer pipes), out4[2]
+ * conflict-free shared-memory load bytes/s, out4[3] SM count */
+int hmk_measure_peaks(hmk_ctx* ctx, double* out4, char* errbuf, size_t errlen);
 /* device time per section of the last run (only filled when option "profile" is 1):
  * p1_select, p1_partner, p1_cluster, p1_intra, p1_resolve, p2_setup, p2_filter, p2_check, p2_sort,
  * p2_base, p2_iterate, p2_commit, final */

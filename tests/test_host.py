@@ -1,0 +1,188 @@
+"""CPU tests of the host-side mirror (hammock_b200/host.py) against the oracle, and of the C-ABI
+library's exports.  No compute calls: there is no GPU here and no CPU fallback to call."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hammock_b200 as hb
+from hammock_b200 import _lib, build as hb_build, synth
+from oracle import oracle as O
+from tests import kats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = hb_build.build()
+    L = ctypes.CDLL(lib)
+    hdr = open(os.path.join(ROOT, "include", "hammock_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|void)\s+(hmk_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS)
+    for sym in declared:
+        assert getattr(L, sym) is not None
+    assert L.hmk_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    """without a usable CUDA device the product must fail loudly (status 4), never compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hb.CudaError):
+        hb.GreedyContext(0)
+    res, offs = O.pack(["WVTAPRSLPVLP", "WVTAPRSLPVLA"])
+    rc, r, _, err = hb.greedy_cluster_arrays(res, offs, np.array([2, 1], np.int32), synth.blosum62(), 20, 3, 0, 1)
+    assert rc == _lib.STATUS_CUDA and r is None and b"no CPU fallback" in err
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hammock_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in txt.replace("the oracle", "").lower() or fn == "synth.py" or "import oracle" not in txt, fn
+                assert "from oracle" not in txt and "import oracle" not in txt and "hmko_" not in txt, fn
+
+
+def test_unique_sequence_and_cluster_model():
+    s = hb.UniqueSequence("wvtaPRSLPVLP", {"a": 3, "b": 4})
+    assert s.get_sequence_string() == "WVTAPRSLPVLP" and s.size() == 7
+    assert (s.get_sequence() == O.encode("WVTAPRSLPVLP")).all()
+    with pytest.raises(hb.FileFormatException):
+        hb.UniqueSequence("ACDJ")
+    c = hb.Cluster([s], 5)
+    t = hb.UniqueSequence("ACDEFGHIKLMN")
+    c.insert(t)
+    assert c.get_id() == 5 and c.size() == 8 and c.get_unique_size() == 2
+    with pytest.raises(hb.DataException):
+        c.insert(hb.UniqueSequence("ACDEFGHIKLMN"))
+    big = hb.Cluster([hb.UniqueSequence("AAAAAAA", {"x": 2 ** 31 - 1})], 0)
+    big.insert(hb.UniqueSequence("CCCCCCC", {"x": 1}))
+    assert big.size() == -2 ** 31                                   # Java int wrap (Cluster.java:57)
+
+
+def test_matrix_loader_matches_oracle(tmp_path, blosum62):
+    rows = ["# comment", "   A  R  N"] + [f"{O.ALPHABET[i]} " + "  ".join(str(int(v)) for v in blosum62[i]) + " " for i in range(24)]
+    p = tmp_path / "m.txt"
+    p.write_text("\n".join(rows) + "\n")
+    assert (hb.load_scoring_matrix(str(p)) == O.load_matrix(str(p))).all()
+    assert (hb.load_scoring_matrix(str(p)) == blosum62).all()
+    for bad in (rows + [rows[2]], rows[:5] + [""] + rows[5:], rows[:5] + ["A 1 2 3"] + rows[5:],
+                rows[:3] + [rows[3].replace("-1", "x", 1)] + rows[4:]):
+        p.write_text("\n".join(bad) + "\n")
+        with pytest.raises(hb.FileFormatException):
+            hb.load_scoring_matrix(str(p))
+        with pytest.raises(O.OracleError):
+            O.load_matrix(str(p))
+    p.write_text("\r\n".join(rows[:12]) + "\r\n")                    # CRLF, fewer rows
+    assert (hb.load_scoring_matrix(str(p)) == O.load_matrix(str(p))).all()
+
+
+FASTA = """>a|3|lab1
+WVTAPRSLPVLP
+>b|0x2|lab2
+wvtaprslpvlp
+>c
+GSWVVDIS
+NVED
+>d|2|lab1
+WVTAPRSLPVLP
+>e|1
+RSLPVLP
+>f|4|lab2|
+GSWVVDISNVED
+"""
+
+
+def test_fasta_loader_matches_oracle(tmp_path):
+    p = tmp_path / "in.fa"
+    p.write_text(FASTA)
+    seqs = hb.load_unique_sequences_from_fasta(str(p))
+    strs, res, offs, ab = O.load_fasta(str(p))
+    assert [s.get_sequence_string() for s in seqs] == strs
+    assert [s.size() for s in seqs] == ab.tolist() == [5, 2, 5, 1]
+    assert seqs[0].labels_map == {"lab1": 5} and seqs[2].labels_map == {"no_label": 1, "lab2": 4}
+    # the raw case-sensitive string is the key: "wvtaprslpvlp" is a separate (equal) UniqueSequence
+    assert seqs[0] == seqs[1]
+    for bad in (">x|0|l\nACD\n", "ACD\n", ">x|1\nACDJ\n", ">x|abc\nACD\n"):
+        p.write_text(bad)
+        with pytest.raises(hb.FileFormatException):
+            hb.load_unique_sequences_from_fasta(str(p))
+        with pytest.raises(O.OracleError):
+            O.load_fasta(str(p))
+
+
+def test_sort_sequences_orders():
+    strs = [s for s, _ in kats.MICRO]
+    seqs = [hb.UniqueSequence(s, {"x": a}) for s, a in kats.MICRO]
+    assert [s.get_sequence_string() for s in hb.sort_sequences(seqs, "size")] == kats.MICRO_ORDER
+    res, offs = O.pack(strs)
+    perm = O.sort_order_size(res, offs, np.array([a for _, a in kats.MICRO], np.int32))
+    assert [strs[i] for i in perm] == kats.MICRO_ORDER
+    alpha = hb.sort_sequences(seqs, "alphabetic")
+    assert [s.get_sequence_string() for s in alpha] == sorted(strs, reverse=True)
+    assert hb.sort_sequences(seqs, "input") == seqs
+    r1 = hb.sort_sequences(seqs, "random", seed=42)
+    assert sorted(s.get_sequence_string() for s in r1) == sorted(strs) and r1 != seqs
+    assert [s.get_sequence_string() for s in r1] == [s.get_sequence_string() for s in hb.sort_sequences(seqs, "random", seed=42)]
+    lab = [hb.UniqueSequence("AAAAAAA", {"p": 1, "q": 9}), hb.UniqueSequence("CCCCCCC", {"p": 5}), hb.UniqueSequence("DDDDDDD", {"q": 2})]
+    assert [s.get_sequence_string() for s in hb.sort_sequences(lab, "p", labels=["p", "q"])] == ["CCCCCCC", "AAAAAAA", "DDDDDDD"]
+    with pytest.raises(hb.DataException):
+        hb.sort_sequences(lab, "zzz", labels=["p", "q"])
+    # stability for equal keys: identical sequences keep input order
+    dup = [hb.UniqueSequence("acd", {"x": 1}), hb.UniqueSequence("ACD", {"x": 1})]
+    assert hb.sort_sequences(dup, "size")[0] is dup[0]
+
+
+def test_java_random_shuffle_known_values():
+    """java.util.Random(42): first nextInt(10) values are 0, 3, 8, 4, 0 (well-known sequence)"""
+    from hammock_b200.host import _JavaRandom
+    r = _JavaRandom(42)
+    assert [r.next_int(10) for _ in range(5)] == [0, 3, 8, 4, 0]
+
+
+def test_defaults_match_oracle():
+    for lo, hi, n in ((12, 12, 2457), (7, 12, 1000), (7, 30, 333), (5, 5, 10)):
+        d = synth.generate(n, lo, hi, seed=lo * 100 + hi)
+        seqs = [hb.UniqueSequence(s) for s in synth.to_strings(d["residues"], d["offsets"])]
+        exp = O.default_params(d["offsets"])
+        assert (hb.set_greedy_threshold(seqs), hb.get_max_shift(seqs), hb.initial_clusters_limit(seqs)) == exp
+        assert synth.default_params(d["lengths"]) == exp
+        assert hb.check_max_shift(seqs, 100) == O.check_max_shift(d["offsets"], 100) == lo - 1
+
+
+def test_pack_and_rebuild_roundtrip():
+    seqs = [hb.UniqueSequence(s, {"x": a}) for s, a in kats.MICRO]
+    seqs = hb.sort_sequences(seqs, "size")
+    res, offs, ab = hb.pack_sequences(seqs)
+    r2, o2 = O.pack(kats.MICRO_ORDER)
+    assert (res == r2).all() and (offs == o2).all()
+    R = O.greedy_cluster(res, offs, ab, synth.blosum62(), 24, 2, 0, 2)
+    clusters = hb.rebuild_clusters(seqs, hb.GreedyResult(R.cluster_id, R.member_rank, R.result_order, R.n_multi, {}))
+    got = [[kats.MICRO_ORDER.index(s.get_sequence_string()) for s in c.get_sequences()] for c in clusters]
+    assert got[:2] == kats.MICRO_EXPECT[2][0] and [g[0] for g in got[2:]] == kats.MICRO_EXPECT[2][1]
+    assert [c.size() for c in clusters[:2]] == [30, 10]
+
+
+def test_synth_generator_is_deterministic_and_ordered():
+    a, b = synth.generate(5000, 7, 12, seed=3), synth.generate(5000, 7, 12, seed=3)
+    assert all((a[k] == b[k]).all() for k in a)
+    assert (np.diff(a["abundance"]) <= 0).all()
+    strs = synth.to_strings(a["residues"], a["offsets"])
+    assert len(set(strs)) == 5000
+    perm = O.sort_order_size(a["residues"], a["offsets"], a["abundance"])
+    assert (perm == np.arange(5000)).all()
+
+
+def test_shard_ranges_tile_the_work():
+    from hammock_b200.host import shard_range
+    for n in (0, 1, 7, 1000, 999983):
+        for world in (1, 2, 3, 8):
+            parts = [shard_range(n, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
