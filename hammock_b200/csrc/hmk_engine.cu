@@ -71,7 +71,7 @@ enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_R
        SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
 
 struct Options {
-    int64_t batch = 0;          // phase-1 queries per batch (0 = two profile tiles)
+    int64_t batch = 0;          // phase-1 queries per batch (0 = four profile tiles)
     int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
     int64_t kb = 8;             // partner candidates kept per query
@@ -164,6 +164,7 @@ private:
     DevBuf<int32_t> d_qid_, d_nq_, d_tk_cnt_, d_tk_ovf_, d_bk_cnt_, d_bk_ovf_, d_ib_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_c_stamp_, d_c_tidx_, d_dirty_a_, d_dirty_b_;
     DevBuf<uint32_t> d_ibm_;
+    DevBuf<int32_t> d_pcand_, d_pd_;
     int batch_id_ = 0;
     DevBuf<uint64_t> d_tk_key_, d_bk_key_;
     DevBuf<uint32_t> d_prof_;
@@ -460,7 +461,7 @@ void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_
 // ---------------------------------------------------------------- phase 1
 int Engine::phase1() {
     int B = (int)opt.batch;
-    if (B <= 0) B = fast_ ? 2 * qt_max() : 192;
+    if (B <= 0) B = fast_ ? 4 * qt_max() : 192;
     B = std::max(1, std::min(B, HMK_MAXBATCH));
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
@@ -468,6 +469,7 @@ int Engine::phase1() {
     d_qid_.reserve(B); d_nq_.reserve(1);
     d_ib_.reserve((size_t)B * B);
     d_ibm_.reserve((size_t)B * nwmax);
+    d_pcand_.reserve((size_t)B * opt.kb); d_pd_.reserve((size_t)B * B * opt.kb);
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
     d_c_stamp_.reserve(std::max(K_, 1)); d_c_tidx_.reserve(std::max(K_, 1));
     CK(cudaMemsetAsync(d_c_stamp_.p, 0, sizeof(int32_t) * std::max(K_, 1), st_));
@@ -531,13 +533,26 @@ int Engine::phase1() {
         const int nw = (nq + 31) / 32;
         hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, st_>>>(nq, nw, T_, d_ib_.p, nq, d_ibm_.p);
         launches_++;
+        // S(partner candidate, query) for every candidate of the batch: clusters born inside the
+        // batch have one of these as their second member
+        {
+            const int npc = nq * (int)opt.kb;
+            hmk_partner_ids<<<(npc + 127) / 128, 128, 0, st_>>>(nq, (int)opt.kb, d_bk_key_.p, d_bk_cnt_.p,
+                                                                 identity_rank_ ? nullptr : d_id_of_rank_.p, d_qid_.p, d_pcand_.p);
+            launches_++;
+            HmkBulkArgs a{};
+            a.prof = d_prof_.p; a.nq = nq;
+            a.packed = d_packed_.p; a.db_ids = d_pcand_.p; a.db_begin = 0; a.ndb = npc;
+            a.dense = d_pd_.p; a.dense_stride = npc;
+            launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
+        }
         HmkP1Batch pb{};
         pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid_.p; pb.kb = (int)opt.kb;
         pb.bk_key = d_bk_key_.p; pb.bk_cnt = d_bk_cnt_.p; pb.bk_ovf = d_bk_ovf_.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
         pb.ib = d_ib_.p; pb.ib_stride = nq; pb.ibm = d_ibm_.p; pb.nw = nw;
         pb.c_stamp = d_c_stamp_.p; pb.c_tidx = d_c_tidx_.p;
-        pb.packed = fast_scalar_ ? d_packed_.p : nullptr; pb.L = max_len_;
+        pb.pd = d_pd_.p; pb.pd_stride = nq * (int)opt.kb;
         // the resolver must not run on truncated hit lists: checked on the host first
         CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
@@ -547,7 +562,19 @@ int Engine::phase1() {
             continue;
         }
         sec(SEC_P1_RESOLVE);
-        hmk_p1_resolve_kernel<<<1, 32, 0, st_>>>(state(), pb);
+        {
+            const size_t fixed = hmk_resolve_fixed_bytes(nq, nw, (int)opt.kb) + 64;
+            const size_t avail = smem_optin_ - 8192;     // leave room for the kernel's static shared memory
+            const size_t room = avail > fixed ? avail - fixed : 0;
+            const int cache_entries = (int)std::min<size_t>(room / 8, (size_t)nq * capq);
+            const size_t smem = fixed + (size_t)cache_entries * 8;
+            static size_t configured = 0;
+            if (smem > configured) {
+                CK(cudaFuncSetAttribute(hmk_p1_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+                configured = avail;
+            }
+            hmk_p1_resolve_kernel<<<1, HMK_RESOLVE_THREADS, smem, st_>>>(state(), pb, cache_entries);
+        }
         CK(cudaGetLastError());
         launches_++;
         stats.p1_batches++;

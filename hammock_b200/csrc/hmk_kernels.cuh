@@ -688,9 +688,24 @@ struct HmkP1Batch {
     int32_t nw;
     int32_t* c_stamp;         // [K] batch id of the cluster's last change
     int32_t* c_tidx;          // [K] its row in the touched table
-    const uint64_t* packed;   // scalar scorer (NULL -> generic)
-    int32_t L;
+    const int32_t* pd;        // pd[b*pd_stride + b2*kb + j] = S(member = j-th partner candidate of b2, query = qid[b])
+    int32_t pd_stride;
 };
+
+// ids of every query's partner candidates (padding: the query itself)
+__global__ void hmk_partner_ids(int nq, int kb, const uint64_t* __restrict__ bk_key, const int32_t* __restrict__ bk_cnt,
+                                const int32_t* __restrict__ id_of_rank, const int32_t* __restrict__ qid,
+                                int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * kb) return;
+    const int b = i / kb, j = i % kb;
+    int32_t id = qid[b];
+    if (j < bk_cnt[b]) {
+        const uint32_t r = hmk_key_rank(bk_key[i]);
+        id = id_of_rank ? id_of_rank[r] : (int32_t)r;
+    }
+    out[i] = id;
+}
 
 __global__ void hmk_ib_mask(int nq, int nw, int32_t T, const int32_t* __restrict__ ib, int stride, uint32_t* __restrict__ ibm) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -716,78 +731,149 @@ __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
     }
 }
 
-__global__ void __launch_bounds__(32) hmk_p1_resolve_kernel(const HmkState S, const HmkP1Batch B) {
-    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
-    __shared__ int32_t t_partner[HMK_MAXBATCH], f_slot[HMK_MAXBATCH];
-    __shared__ uint32_t t_mask[HMK_MAXBATCH][HMK_MAXW];
+#define HMK_RESOLVE_THREADS 256
+
+// shared-memory bytes of the resolver for a batch of nq queries, before the candidate cache
+__host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb) {
+    size_t o = (size_t)nq * 4 * 4;           // qid, bk_cnt, bk_ovf, ac_raw
+    o += (size_t)(nq + 1) * 4;               // ac_off
+    o += (size_t)nq * nw * 4 * 2;            // ibm, t_mask
+    o += (size_t)nq * 4 * 4;                 // t_fb, f_slot, f_pick, f_tidx
+    o = (o + 7) & ~(size_t)7;
+    o += (size_t)nq * kb * 8;                // bk_key
+    return o;
+}
+
+// The CTA first stages every immutable per-batch input in shared memory (all warps), then warp 0
+// replays the steps: a step then needs ONE round of global loads (the mutable state: which
+// candidates are still singletons, sizes / stamps of the candidate clusters).
+__global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(const HmkState S, const HmkP1Batch B, int cache_entries) {
+    extern __shared__ __align__(128) unsigned char rs_raw[];
+    const int nq = B.nq, nw = B.nw, kb = B.kb;
+    unsigned char* p = rs_raw;
+    int32_t* s_qid = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
+    int32_t* s_bkcnt = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
+    int32_t* s_bkovf = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
+    int32_t* s_acraw = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
+    int32_t* s_acoff = reinterpret_cast<int32_t*>(p);   p += (size_t)(nq + 1) * 4;
+    uint32_t* s_ibm = reinterpret_cast<uint32_t*>(p);   p += (size_t)nq * nw * 4;
+    uint32_t* t_mask = reinterpret_cast<uint32_t*>(p);  p += (size_t)nq * nw * 4;   // [row][nw]
+    int32_t* t_fb = reinterpret_cast<int32_t*>(p);      p += (size_t)nq * 4;   // founder's batch index, -1 = pre-batch cluster
+    int32_t* f_slot = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;
+    int32_t* f_pick = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // which of its candidates the founder took
+    int32_t* f_tidx = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // touched-table row of the cluster it founded
+    p = rs_raw + ((size_t)(p - rs_raw + 7) & ~(size_t)7);
+    uint64_t* s_bkkey = reinterpret_cast<uint64_t*>(p); p += (size_t)nq * kb * 8;
+    int32_t* s_acslot = reinterpret_cast<int32_t*>(p);  p += (size_t)cache_entries * 4;
+    int32_t* s_acscore = reinterpret_cast<int32_t*>(p);
+    __shared__ int s_cached;
+    __shared__ int32_t tc_c[HMK_MAXBATCH + 64], tc_cl[HMK_MAXBATCH + 64], tc_row[HMK_MAXBATCH + 64];   // per-step list of touched candidates
+
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        s_qid[i] = B.qid[i]; s_bkcnt[i] = B.bk_cnt[i]; s_bkovf[i] = B.bk_ovf[i]; s_acraw[i] = B.ac_cnt[i];
+    }
+    for (int i = threadIdx.x; i < nq * nw; i += blockDim.x) s_ibm[i] = B.ibm[i];
+    for (int i = threadIdx.x; i < nq * kb; i += blockDim.x) s_bkkey[i] = B.bk_key[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < nq; i++) { s_acoff[i] = run; run += min(s_acraw[i], B.capq); }
+        s_acoff[nq] = run;
+        s_cached = run <= cache_entries;
+    }
+    __syncthreads();
+    const bool cached = s_cached != 0;
+    if (cached) {
+        const int total = s_acoff[nq];
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            int lo = 0, hi = nq - 1;          // query of entry e
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_acoff[mid] <= e) lo = mid; else hi = mid - 1; }
+            const size_t g = (size_t)lo * B.capq + (e - s_acoff[lo]);
+            s_acslot[e] = B.ac_slot[g];
+            s_acscore[e] = B.ac_score[g];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
-    hmk_load_matrix_smem(sM, S.M);
-    HmkScalar sc;
-    sc.packed = B.packed; sc.sM = sM; sc.L = B.L;
     HmkCtl* ctl = S.ctl;
     int32_t ncl = ctl->ncl, unproc = ctl->unproc_alive;
     int32_t steps = ctl->steps, joins = ctl->joins, creates = ctl->creates, orphans = ctl->orphans;
     int32_t status = HMK_P1_CONTINUE, npe_step = -1, cur = ctl->cur;
     int32_t tn = 0;                 // rows of the touched table
     uint32_t fmask = 0;             // this lane's word of the founder mask
-    long long npairs = 0;
-    const int nw = B.nw;
 
-    // complete linkage over the members cluster row `tidx` received in this batch
-    auto eval_touched = [&](int tidx, uint32_t hm, int b, int32_t q, int32_t& cl) -> bool {
-        uint32_t tm = lane < nw ? t_mask[tidx][lane] : 0u;
-        bool fail = (tm & ~hm) != 0;
+    // complete linkage over the members cluster row `row` received in this batch, evaluated by ONE
+    // lane (lanes work on different candidate clusters in parallel): every batch query that joined
+    // must be in the hit mask of query b, a partner must score >= T (table pd), then the minimum
+    auto eval_touched = [&](int row, int b, int32_t& cl) -> bool {
+        const uint32_t* tm = t_mask + row * nw;
+        const uint32_t* hm = s_ibm + b * nw;
+        for (int w = 0; w < nw; w++)
+            if (tm[w] & ~hm[w]) return false;
         int32_t mn = cl;
-        while (tm) {
-            const int b2 = lane * 32 + __ffs(tm) - 1;
-            tm &= tm - 1;
-            const int32_t s = B.ib[(size_t)b * B.ib_stride + b2];
+        const int32_t fb = t_fb[row];
+        if (fb >= 0) {     // cluster born in this batch: its partner was one of the founder's candidates
+            const int32_t s = B.pd[(size_t)b * B.pd_stride + fb * kb + f_pick[fb]];
+            if (s < S.T) return false;
             mn = s < mn ? s : mn;
         }
-        fail = __any_sync(FULL, fail);
-        mn = __reduce_min_sync(FULL, mn);
-        const int32_t partner = t_partner[tidx];
-        if (!fail && partner >= 0) {
-            int32_t s = 0;
-            if (lane == 0) { s = hmk_scalar_score(S, sc, partner, q); npairs++; }
-            s = __shfl_sync(FULL, s, 0);
-            if (s < S.T) fail = true;
-            mn = s < mn ? s : mn;
+        for (int w = 0; w < nw; w++) {
+            uint32_t m = tm[w];
+            while (m) {
+                const int b2 = w * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const int32_t s = B.ib[(size_t)b * B.ib_stride + b2];
+                mn = s < mn ? s : mn;
+            }
         }
         cl = mn;
-        return !fail;
+        return true;
     };
 
-    for (int b = 0; b < B.nq; b++) {
-        const int32_t q = B.qid[b];
+    for (int b = 0; b < nq; b++) {
+        const int32_t q = s_qid[b];
         if (ncl >= S.K) { status = HMK_P1_DONE; cur = q; break; }                   // :90
-        if (__ldcg(S.slot + q) >= 0) continue;   // consumed as a partner earlier in this batch (:101,110)
-        const int32_t acnt = B.ac_cnt[b];
+        const int32_t acnt = s_acraw[b];
+        const int32_t bcnt = s_bkcnt[b];
+        const int32_t* acs = cached ? s_acslot + s_acoff[b] : B.ac_slot + (size_t)b * B.capq;
+        const int32_t* acv = cached ? s_acscore + s_acoff[b] : B.ac_score + (size_t)b * B.capq;
+        const int32_t ause = acnt < B.capq ? acnt : B.capq;
+
+        // ---- one round of global loads: everything mutable this step depends on
+        const int32_t slotq = __ldcg(S.slot + q);
+        uint64_t key = 0;
+        int32_t id = -1, idslot = 0;
+        if (lane < bcnt) {
+            key = s_bkkey[b * kb + lane];
+            const uint32_t r = hmk_key_rank(key);
+            id = S.id_of_rank ? S.id_of_rank[r] : (int32_t)r;
+            idslot = __ldcg(S.slot + id);
+        }
+        int32_t c0 = -1, cl0 = 0, st0 = 0, sz0 = 0, fd0 = 0;
+        if (lane < ause) {
+            c0 = acs[lane]; cl0 = acv[lane];
+            st0 = __ldcg(B.c_stamp + c0); sz0 = __ldcg(S.c_size + c0); fd0 = __ldcg(S.c_founder + c0);
+        }
+
+        if (slotq >= 0) continue;   // consumed as a partner earlier in this batch (:101,110)
         if (acnt > B.capq) { status = HMK_P1_GROW; cur = q; break; }   // candidate arrays too small: host grows them
 
         // ---- B: nearest among initialList[index+1 ..]                               (:93)
         int bkind = 0;   // 0 = Java null, 1 = found, 2 = (null cluster, MIN_VALUE) object
-        int32_t bscore = HMK_JMIN, bid = -1;
+        int32_t bscore = HMK_JMIN, bid = -1, bpick = 0;
         if (unproc - 1 == 0) bkind = 2;            // empty sub-list (ClinkageSequenceClusterer.java:138-140)
         else {
-            const int32_t cnt = B.bk_cnt[b];
-            uint64_t key = 0;
-            int32_t id = -1;
-            bool alive = false;
-            if (lane < cnt) {
-                key = B.bk_key[(size_t)b * B.kb + lane];
-                const uint32_t r = hmk_key_rank(key);
-                id = S.id_of_rank ? S.id_of_rank[r] : (int32_t)r;
-                alive = __ldcg(S.slot + id) < 0;
-            }
-            const unsigned am = __ballot_sync(FULL, alive);
+            const unsigned am = __ballot_sync(FULL, lane < bcnt && idslot < 0);
             if (am) {
                 const int src = __ffs(am) - 1;      // list is sorted: first alive entry wins
+                bpick = src;
                 bid = __shfl_sync(FULL, id, src);
                 bscore = hmk_key_score(__shfl_sync(FULL, key, src));
                 bkind = 1;
-            } else if (B.bk_ovf[b]) {
+            } else if (s_bkovf[b]) {
                 status = HMK_P1_RESTART; cur = q; break;    // list truncated: rescore from q
             }
         }
@@ -798,43 +884,59 @@ __global__ void __launch_bounds__(32) hmk_p1_resolve_kernel(const HmkState S, co
         best.score = HMK_JMIN; best.size = 0; best.fid = 0; best.slot = -1;
         if (ncl == 0) akind = 2;
         else {
-            const uint32_t hm = lane < nw ? B.ibm[(size_t)b * nw + lane] : 0u;
+            const uint32_t hm = lane < nw ? s_ibm[b * nw + lane] : 0u;
+            int nt = 0;   // touched candidates collected for this step (warp-uniform)
             // pre-batch clusters: untouched ones are final, touched ones need the batch members too
-            for (int e0 = 0; e0 < acnt; e0 += 32) {
+            for (int e0 = 0; e0 < ause; e0 += 32) {
                 const int e = e0 + lane;
                 int32_t c = -1, cl = 0;
                 bool touched = false;
-                if (e < acnt) {
-                    c = B.ac_slot[(size_t)b * B.capq + e];
-                    cl = B.ac_score[(size_t)b * B.capq + e];
-                    touched = __ldcg(B.c_stamp + c) == B.batch_id;
-                    if (!touched) hmk_consider(best, cl, __ldcg(S.c_size + c), __ldcg(S.c_founder + c), c);
+                if (e < ause) {
+                    int32_t st, sz, fd;
+                    if (e0 == 0) { c = c0; cl = cl0; st = st0; sz = sz0; fd = fd0; }
+                    else {
+                        c = acs[e]; cl = acv[e];
+                        st = __ldcg(B.c_stamp + c); sz = __ldcg(S.c_size + c); fd = __ldcg(S.c_founder + c);
+                    }
+                    touched = st == B.batch_id;
+                    if (!touched) hmk_consider(best, cl, sz, fd, c);
                 }
-                unsigned tmk = __ballot_sync(FULL, touched);
-                while (tmk) {
-                    const int src = __ffs(tmk) - 1;
-                    tmk &= tmk - 1;
-                    const int32_t c2 = __shfl_sync(FULL, c, src);
-                    int32_t cl2 = __shfl_sync(FULL, cl, src);
-                    if (eval_touched(__ldcg(B.c_tidx + c2), hm, b, q, cl2) && lane == 0)
-                        hmk_consider(best, cl2, __ldcg(S.c_size + c2), __ldcg(S.c_founder + c2), c2);
+                const unsigned tmk = __ballot_sync(FULL, touched);
+                if (touched) {
+                    const int pos = nt + __popc(tmk & ((1u << lane) - 1u));
+                    tc_c[pos] = c; tc_cl[pos] = cl; tc_row[pos] = -1;     // row looked up below
                 }
+                nt += __popc(tmk);
             }
             // clusters born in this batch whose founder scores >= T
-            unsigned fm = __ballot_sync(FULL, (fmask & hm) != 0);
-            while (fm) {
-                const int src = __ffs(fm) - 1;
-                fm &= fm - 1;
-                uint32_t bits = __shfl_sync(FULL, fmask & hm, src);
-                while (bits) {
-                    const int b2 = src * 32 + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int32_t c2 = f_slot[b2];
-                    int32_t cl2 = HMK_JMAX;
-                    if (eval_touched(__ldcg(B.c_tidx + c2), hm, b, q, cl2) && lane == 0)
-                        hmk_consider(best, cl2, __ldcg(S.c_size + c2), __ldcg(S.c_founder + c2), c2);
+            {
+                const uint32_t bits = fmask & hm;
+                int mine = __popc(bits), pre = mine;
+#pragma unroll
+                for (int d2 = 1; d2 < 32; d2 <<= 1) { const int v = __shfl_up_sync(FULL, pre, d2); if (lane >= d2) pre += v; }
+                const int total = __shfl_sync(FULL, pre, 31);
+                int pos = nt + pre - mine;
+                uint32_t m = bits;
+                while (m) {
+                    const int b2 = lane * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    tc_c[pos] = f_slot[b2]; tc_cl[pos] = HMK_JMAX; tc_row[pos] = f_tidx[b2];
+                    pos++;
+                }
+                nt += total;
+            }
+            __syncwarp();
+            for (int i0 = 0; i0 < nt; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < nt) {
+                    const int32_t c2 = tc_c[i];
+                    int32_t cl2 = tc_cl[i];
+                    int row = tc_row[i];
+                    if (row < 0) row = __ldcg(B.c_tidx + c2);
+                    if (eval_touched(row, b, cl2)) hmk_consider(best, cl2, __ldcg(S.c_size + c2), __ldcg(S.c_founder + c2), c2);
                 }
             }
+            __syncwarp();
             hmk_best_reduce(best);
             if (best.slot >= 0) akind = 1;
         }
@@ -855,15 +957,15 @@ __global__ void __launch_bounds__(32) hmk_p1_resolve_kernel(const HmkState S, co
             const bool fresh = create || __ldcg(B.c_stamp + c) != B.batch_id;
             tidx = fresh ? tn : __ldcg(B.c_tidx + c);
             if (fresh) {
-                if (lane < HMK_MAXW) t_mask[tidx][lane] = 0;
-                if (lane == 0) { t_partner[tidx] = create ? bid : -1; B.c_stamp[c] = B.batch_id; B.c_tidx[c] = tidx; }
+                if (lane < nw) t_mask[tidx * nw + lane] = 0;
+                if (lane == 0) { t_fb[tidx] = create ? b : -1; B.c_stamp[c] = B.batch_id; B.c_tidx[c] = tidx; }
                 tn++;
             }
             __syncwarp();
-            if (lane == (b >> 5)) t_mask[tidx][lane] |= 1u << (b & 31);
+            if (lane == (b >> 5)) t_mask[tidx * nw + lane] |= 1u << (b & 31);
             if (create) {
                 if (lane == (b >> 5)) fmask |= 1u << (b & 31);
-                if (lane == 0) f_slot[b] = c;
+                if (lane == 0) { f_slot[b] = c; f_pick[b] = bpick; f_tidx[b] = tidx; }
             }
             if (lane == 0) {
                 if (join) {
@@ -896,7 +998,6 @@ __global__ void __launch_bounds__(32) hmk_p1_resolve_kernel(const HmkState S, co
         if (npe_step >= 0) ctl->npe_step = npe_step;
         ctl->steps = steps; ctl->joins = joins; ctl->creates = creates; ctl->orphans = orphans;
         if (status == HMK_P1_RESTART) ctl->restarts += 1;
-        if (npairs) atomicAdd((unsigned long long*)&ctl->scalar_pairs, (unsigned long long)npairs);
     }
 }
 
