@@ -23,14 +23,61 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/hammock_b200.h"
 #include "hmk_kernels.cuh"
 
 namespace {
 
+// ---------------------------------------------------------------- NCCL, loaded on demand
+// The single-GPU path has no NCCL dependency; hmk_init_distributed dlopen()s libnccl.so.2 (the
+// copy the host process already loaded, e.g. torch's, or the system one).
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void* Comm;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string error;
+    static NcclApi& get() {
+        static NcclApi api;
+        static bool tried = false;
+        if (!tried) {
+            tried = true;
+            void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) { api.error = std::string("cannot load libnccl: ") + dlerror(); return api; }
+            auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) api.error = std::string("libnccl lacks ") + n; return p; };
+            api.GetUniqueId = (int (*)(UniqueId*))sym("ncclGetUniqueId");
+            api.CommInitRank = (int (*)(Comm*, int, UniqueId, int))sym("ncclCommInitRank");
+            api.CommDestroy = (int (*)(Comm))sym("ncclCommDestroy");
+            api.AllGather = (int (*)(const void*, void*, size_t, int, Comm, cudaStream_t))sym("ncclAllGather");
+            api.GroupStart = (int (*)())sym("ncclGroupStart");
+            api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+            api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+            api.ok = api.error.empty();
+        }
+        return api;
+    }
+};
+enum { HMK_NCCL_CHAR = 0 };   // ncclInt8 / ncclChar
+
 struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0)                                                                               \
+            throw CudaError(std::string(#call) + " failed: " + NcclApi::get().GetErrorString(r_)); \
+    } while (0)
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -116,6 +163,7 @@ public:
         if (ev_t1_) cudaEventDestroy(ev_t1_);
         if (h_ctl_) cudaFreeHost(h_ctl_);
         if (h_scalars_) cudaFreeHost(h_scalars_);
+        if (comm_) NcclApi::get().CommDestroy(comm_);
         if (st_) cudaStreamDestroy(st_);
     }
 
@@ -137,10 +185,19 @@ public:
         return ms;
     }
     void measure_peaks(double* out);
+    void init_distributed(int rank, int world, const void* id128);
 
 private:
     // ---- problem
     int device_;
+    int rank_ = 0, world_ = 1;
+    NcclApi::Comm comm_ = nullptr;
+    DevBuf<uint64_t> d_gk_key_;
+    DevBuf<int32_t> d_gk_cnt_, d_gk_ovf_, d_gcount_, d_gs_;
+    DevBuf<unsigned long long> d_gq_, d_gc_;
+    void allgather(const void* send, void* recv, size_t bytes) {
+        NK(NcclApi::get().AllGather(send, recv, bytes, HMK_NCCL_CHAR, comm_, st_));
+    }
     int sm_count_ = 148;
     size_t smem_optin_ = 0;
     cudaStream_t st_ = nullptr;
@@ -162,7 +219,7 @@ private:
     int32_t* h_scalars_ = nullptr;
     // ---- phase-1 scratch
     DevBuf<int32_t> d_qid_, d_nq_, d_tk_cnt_, d_tk_ovf_, d_bk_cnt_, d_bk_ovf_, d_ib_,
-        d_ac_cnt_, d_ac_slot_, d_ac_score_, d_c_stamp_, d_c_tidx_, d_dirty_a_, d_dirty_b_;
+        d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_, d_dirty_b_;
     DevBuf<uint32_t> d_ibm_;
     DevBuf<int32_t> d_pcand_, d_pd_;
     int batch_id_ = 0;
@@ -180,6 +237,7 @@ private:
     // ---- outputs
     DevBuf<int32_t> d_cluster_id_, d_member_rank_;
     int32_t n_unassigned_ = 0;
+    size_t ncand_padded_ = 0;
     // ---- timing
     cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr, ev_t0_ = nullptr, ev_t1_ = nullptr;
     std::vector<cudaEvent_t> ev_pool_;
@@ -467,12 +525,10 @@ int Engine::phase1() {
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
     const int nwmax = (B + 31) / 32;
     d_qid_.reserve(B); d_nq_.reserve(1);
-    d_ib_.reserve((size_t)B * B);
+    d_ib_.reserve((size_t)B * (B + 4));
     d_ibm_.reserve((size_t)B * nwmax);
-    d_pcand_.reserve((size_t)B * opt.kb); d_pd_.reserve((size_t)B * B * opt.kb);
+    d_pcand_.reserve((size_t)B * opt.kb); d_pd_.reserve((size_t)B * (B * opt.kb + 4));
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
-    d_c_stamp_.reserve(std::max(K_, 1)); d_c_tidx_.reserve(std::max(K_, 1));
-    CK(cudaMemsetAsync(d_c_stamp_.p, 0, sizeof(int32_t) * std::max(K_, 1), st_));
     batch_id_ = 0;
     if (fast_) d_prof_.reserve((size_t)B * sc_.prof_words);
     size_t hit_cap = (size_t)opt.hit_cap;
@@ -491,14 +547,32 @@ int Engine::phase1() {
         {
             HmkBulkArgs a{};
             a.prof = d_prof_.p; a.nq = nq;
-            a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = cur; a.ndb = n_ - cur;
+            // this rank's stripe of the later singletons (the whole range on one GPU)
+            const int64_t span = (int64_t)n_ - cur;
+            const int lo = cur + (int)(span * rank_ / world_), hi = cur + (int)(span * (rank_ + 1) / world_);
+            a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = lo; a.ndb = hi - lo;
             a.slot = d_slot_.p; a.q_minid = d_qid_.p;
             a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
+            d_bk_key_.reserve((size_t)nq * opt.kb); d_bk_cnt_.reserve(nq); d_bk_ovf_.reserve(nq);
             if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, d_qid_.p, 1);
             else {
-                d_bk_key_.reserve((size_t)nq * opt.kb); d_bk_cnt_.reserve(nq); d_bk_ovf_.reserve(nq);
                 CK(cudaMemsetAsync(d_bk_cnt_.p, 0, sizeof(int32_t) * nq, st_));
                 CK(cudaMemsetAsync(d_bk_ovf_.p, 0, sizeof(int32_t) * nq, st_));
+            }
+            if (world_ > 1) {
+                // best-hit exchange: every rank contributes its stripe's top-k per query (a few KB),
+                // then every rank merges the same lists -> identical, replicated decisions
+                const int kb = (int)opt.kb;
+                d_gk_key_.reserve((size_t)world_ * nq * kb); d_gk_cnt_.reserve((size_t)world_ * nq); d_gk_ovf_.reserve((size_t)world_ * nq);
+                NK(NcclApi::get().GroupStart());
+                allgather(d_bk_key_.p, d_gk_key_.p, sizeof(uint64_t) * nq * kb);
+                allgather(d_bk_cnt_.p, d_gk_cnt_.p, sizeof(int32_t) * nq);
+                allgather(d_bk_ovf_.p, d_gk_ovf_.p, sizeof(int32_t) * nq);
+                NK(NcclApi::get().GroupEnd());
+                hmk_topk_merge<<<(nq * 32 + 255) / 256, 256, 0, st_>>>(nq, world_, kb, d_gk_key_.p, d_gk_cnt_.p, d_gk_ovf_.p,
+                                                                       d_bk_key_.p, d_bk_cnt_.p, d_bk_ovf_.p);
+                CK(cudaGetLastError());
+                launches_++;
             }
         }
         // A: clusters whose founder scores >= T, then complete linkage over their members
@@ -521,17 +595,18 @@ int Engine::phase1() {
             CK(cudaGetLastError());
             launches_++;
         }
-        // intra-batch scores S(member = q_b2, query = q_b)
+        // intra-batch scores S(member = q_b2, query = q_b); row strides padded to 16 bytes for the TMA row prefetch
+        const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * (int)opt.kb + 3) & ~3;
         sec(SEC_P1_INTRA);
         {
             HmkBulkArgs a{};
             a.prof = d_prof_.p; a.nq = nq;
             a.packed = d_packed_.p; a.db_ids = d_qid_.p; a.db_begin = 0; a.ndb = nq;
-            a.dense = d_ib_.p; a.dense_stride = nq;
+            a.dense = d_ib_.p; a.dense_stride = ib_stride;
             launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
         }
         const int nw = (nq + 31) / 32;
-        hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, st_>>>(nq, nw, T_, d_ib_.p, nq, d_ibm_.p);
+        hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, st_>>>(nq, nw, T_, d_ib_.p, ib_stride, d_ibm_.p);
         launches_++;
         // S(partner candidate, query) for every candidate of the batch: clusters born inside the
         // batch have one of these as their second member
@@ -543,16 +618,16 @@ int Engine::phase1() {
             HmkBulkArgs a{};
             a.prof = d_prof_.p; a.nq = nq;
             a.packed = d_packed_.p; a.db_ids = d_pcand_.p; a.db_begin = 0; a.ndb = npc;
-            a.dense = d_pd_.p; a.dense_stride = npc;
+            a.dense = d_pd_.p; a.dense_stride = pd_stride;
             launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
         }
         HmkP1Batch pb{};
         pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid_.p; pb.kb = (int)opt.kb;
         pb.bk_key = d_bk_key_.p; pb.bk_cnt = d_bk_cnt_.p; pb.bk_ovf = d_bk_ovf_.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
-        pb.ib = d_ib_.p; pb.ib_stride = nq; pb.ibm = d_ibm_.p; pb.nw = nw;
-        pb.c_stamp = d_c_stamp_.p; pb.c_tidx = d_c_tidx_.p;
-        pb.pd = d_pd_.p; pb.pd_stride = nq * (int)opt.kb;
+        pb.ib = d_ib_.p; pb.ib_stride = ib_stride; pb.ibm = d_ibm_.p; pb.nw = nw;
+        pb.pcand = d_pcand_.p;
+        pb.pd = d_pd_.p; pb.pd_stride = pd_stride;
         // the resolver must not run on truncated hit lists: checked on the host first
         CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
@@ -563,11 +638,11 @@ int Engine::phase1() {
         }
         sec(SEC_P1_RESOLVE);
         {
-            const size_t fixed = hmk_resolve_fixed_bytes(nq, nw, (int)opt.kb) + 64;
-            const size_t avail = smem_optin_ - 8192;     // leave room for the kernel's static shared memory
+            const size_t fixed = hmk_resolve_fixed_bytes(nq, nw, (int)opt.kb, ib_stride, pd_stride) + 64;
+            const size_t avail = smem_optin_ - 3 * HMK_HASH_SIZE * 4 - 1024;   // minus the kernel's static shared memory
             const size_t room = avail > fixed ? avail - fixed : 0;
-            const int cache_entries = (int)std::min<size_t>(room / 8, (size_t)nq * capq);
-            const size_t smem = fixed + (size_t)cache_entries * 8;
+            const int cache_entries = (int)std::min<size_t>(room / HMK_RESOLVE_CAND_BYTES, (size_t)nq * capq);
+            const size_t smem = fixed + (size_t)cache_entries * HMK_RESOLVE_CAND_BYTES;
             static size_t configured = 0;
             if (smem > configured) {
                 CK(cudaFuncSetAttribute(hmk_p1_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
@@ -606,11 +681,14 @@ void Engine::phase2() {
     d_hits_.reserve(hit_cap);
     size_t cand_cap = std::max<size_t>(1 << 20, (size_t)ns / 2);
     d_key_q_.reserve(cand_cap); d_key_c_.reserve(cand_cap); d_cand_score_.reserve(cand_cap);
+    cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
     size_t ncand = 0;
     CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
     const int chunk = (int)std::max<int64_t>(1024, opt.p2_chunk);
-    for (int c0 = 0; c0 < ns;) {
-        const int cn = std::min(chunk, ns - c0);
+    // this rank's share of the phase-2 queries (all of them on one GPU)
+    const int my_lo = (int)((int64_t)ns * rank_ / world_), my_hi = (int)((int64_t)ns * (rank_ + 1) / world_);
+    for (int c0 = my_lo; c0 < my_hi;) {
+        const int cn = std::min(chunk, my_hi - c0);
         sec(SEC_P2_FILTER);
         CK(cudaMemsetAsync(d_counts_.p, 0, sizeof(unsigned int), st_));
         HmkBulkArgs a{};
@@ -651,21 +729,61 @@ void Engine::phase2() {
         }
         c0 += cn;
     }
+    if (world_ > 1) {
+        // candidate exchange: all-gather the per-rank candidate lists (padded to the longest; the
+        // padding keys are ~0 and sort to the end)
+        d_gcount_.reserve(world_ + 1);
+        int32_t mine = (int32_t)ncand;
+        CK(cudaMemcpyAsync(d_gcount_.p + world_, &mine, sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        allgather(d_gcount_.p + world_, d_gcount_.p, sizeof(int32_t));
+        std::vector<int32_t> counts(world_);
+        CK(cudaMemcpyAsync(counts.data(), d_gcount_.p, sizeof(int32_t) * world_, cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        size_t maxc = 0, total = 0;
+        for (int r = 0; r < world_; r++) { maxc = std::max<size_t>(maxc, counts[r]); total += counts[r]; }
+        if (maxc > 0) {
+            if (maxc > cand_cap) {
+                d_key_q_.grow_keep(maxc, ncand, st_); d_key_c_.grow_keep(maxc, ncand, st_); d_cand_score_.grow_keep(maxc, ncand, st_);
+                cand_cap = maxc;
+            }
+            if (maxc > ncand) {
+                CK(cudaMemsetAsync(d_key_q_.p + ncand, 0xff, sizeof(unsigned long long) * (maxc - ncand), st_));
+                CK(cudaMemsetAsync(d_key_c_.p + ncand, 0xff, sizeof(unsigned long long) * (maxc - ncand), st_));
+                CK(cudaMemsetAsync(d_cand_score_.p + ncand, 0, sizeof(int32_t) * (maxc - ncand), st_));
+            }
+            DevBuf<unsigned long long>& gq = d_gq_;   // persistent: swapped with the local lists below
+            DevBuf<unsigned long long>& gc = d_gc_;
+            DevBuf<int32_t>& gs = d_gs_;
+            gq.reserve(maxc * world_); gc.reserve(maxc * world_); gs.reserve(maxc * world_);
+            NK(NcclApi::get().GroupStart());
+            allgather(d_key_q_.p, gq.p, sizeof(unsigned long long) * maxc);
+            allgather(d_key_c_.p, gc.p, sizeof(unsigned long long) * maxc);
+            allgather(d_cand_score_.p, gs.p, sizeof(int32_t) * maxc);
+            NK(NcclApi::get().GroupEnd());
+            std::swap(d_key_q_.p, gq.p); std::swap(d_key_q_.cap, gq.cap);
+            std::swap(d_key_c_.p, gc.p); std::swap(d_key_c_.cap, gc.cap);
+            std::swap(d_cand_score_.p, gs.p); std::swap(d_cand_score_.cap, gs.cap);
+        }
+        ncand = total;
+        ncand_padded_ = maxc * world_;
+        cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
+    } else ncand_padded_ = ncand;
     stats.p2_candidates = (int64_t)ncand;
     sec(SEC_P2_SORT);
     if (ncand == 0) { sec(-1); return; }
     const int nc = (int)ncand;
+    const int ncp = (int)ncand_padded_;   // >= nc: padded entries carry key ~0 and sort to the end
     // group by query (ascending cluster inside a query) and by cluster (ascending query inside a cluster)
-    sort_pairs(d_key_q_.p, d_cand_score_.p, nc, 64);
+    sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, 64);
     d_cq_c_.reserve(nc); d_cc_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2);
     hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, d_cq_c_.p);
     hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, d_qstart_.p);
     {
         size_t bytes = 0;
-        d_key_tmp_.reserve(nc);
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_key_c_.p, d_key_tmp_.p, nc, 0, 64, st_));
+        d_key_tmp_.reserve(ncp);
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, 64, st_));
         d_cub_.reserve(bytes);
-        CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, nc, 0, 64, st_));
+        CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, 64, st_));
     }
     hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, d_cc_q_.p);
     hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, d_cstart_.p);
@@ -847,6 +965,19 @@ void Engine::score_block(const int32_t* first, int32_t nf, const int32_t* second
     }
 }
 
+void Engine::init_distributed(int rank, int world, const void* id128) {
+    CK(cudaSetDevice(device_));
+    if (world < 1 || rank < 0 || rank >= world || !id128) throw std::invalid_argument("hmk_init_distributed: bad rank/world/id");
+    NcclApi& api = NcclApi::get();
+    if (!api.ok) throw CudaError("NCCL unavailable: " + api.error);
+    if (comm_) { api.CommDestroy(comm_); comm_ = nullptr; }
+    NcclApi::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    NK(api.CommInitRank(&comm_, world, id, rank));
+    rank_ = rank;
+    world_ = world;
+}
+
 // out[0] = IADD3 lane-instructions/s, out[1] = lane-instructions/s of an IADD3 + IMAD mix,
 // out[2] = shared-memory LDS.32 bytes/s (conflict free), out[3] = SM count
 void Engine::measure_peaks(double* out) {
@@ -963,6 +1094,26 @@ int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats) {
     if (!ctx || !stats) return HMK_STATUS_BAD_ARG;
     *stats = ctx->engine.stats;
     return HMK_STATUS_OK;
+}
+
+int hmk_nccl_unique_id(void* id128, char* errbuf, size_t errlen) {
+    if (!id128) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        NcclApi& api = NcclApi::get();
+        if (!api.ok) throw CudaError("NCCL unavailable: " + api.error);
+        NcclApi::UniqueId id;
+        NK(api.GetUniqueId(&id));
+        std::memcpy(id128, id.internal, 128);
+        return HMK_STATUS_OK;
+    });
+}
+
+int hmk_init_distributed(hmk_ctx* ctx, int rank, int world, const void* id128, char* errbuf, size_t errlen) {
+    if (!ctx) return HMK_STATUS_BAD_ARG;
+    return guarded(errbuf, errlen, [&] {
+        ctx->engine.init_distributed(rank, world, id128);
+        return HMK_STATUS_OK;
+    });
 }
 
 int hmk_timer_begin(hmk_ctx* ctx) {

@@ -686,8 +686,7 @@ struct HmkP1Batch {
     int32_t ib_stride;
     const uint32_t* ibm;      // [nq][nw]
     int32_t nw;
-    int32_t* c_stamp;         // [K] batch id of the cluster's last change
-    int32_t* c_tidx;          // [K] its row in the touched table
+    const int32_t* pcand;     // [nq][kb] sequence ids of the partner candidates (bk_key decoded)
     const int32_t* pd;        // pd[b*pd_stride + b2*kb + j] = S(member = j-th partner candidate of b2, query = qid[b])
     int32_t pd_stride;
 };
@@ -732,65 +731,93 @@ __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
 }
 
 #define HMK_RESOLVE_THREADS 256
+#define HMK_HASH_SIZE 2048          // >= 2 * HMK_MAXBATCH, power of two
 
 // shared-memory bytes of the resolver for a batch of nq queries, before the candidate cache
-__host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb) {
-    size_t o = (size_t)nq * 4 * 4;           // qid, bk_cnt, bk_ovf, ac_raw
+__host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb, int ib_stride, int pd_stride) {
+    size_t o = (size_t)(ib_stride + pd_stride) * 4 * 2;   // double-buffered rows of ib and pd (first: 16-byte aligned)
+    o += (size_t)nq * 4 * 5;                 // qid, qab, bk_cnt, bk_ovf, ac_raw
     o += (size_t)(nq + 1) * 4;               // ac_off
     o += (size_t)nq * nw * 4 * 2;            // ibm, t_mask
-    o += (size_t)nq * 4 * 4;                 // t_fb, f_slot, f_pick, f_tidx
-    o = (o + 7) & ~(size_t)7;
-    o += (size_t)nq * kb * 8;                // bk_key
+    o += (size_t)nq * 4 * 8;                 // t_fb, t_size, t_fid, t_count, t_tail, f_slot, f_pick, f_tidx
+    o += (size_t)nq * kb * 4 * 3;            // bk_id, bk_score, bk_ab
+    o += (size_t)nq * 4 * 3;                 // per-step list of touched candidates (tc_c, tc_cl, tc_row)
     return o;
 }
+#define HMK_RESOLVE_CAND_BYTES 16            // cached candidate: slot, score, size, founder id
 
-// The CTA first stages every immutable per-batch input in shared memory (all warps), then warp 0
-// replays the steps: a step then needs ONE round of global loads (the mutable state: which
-// candidates are still singletons, sizes / stamps of the candidate clusters).
+__device__ __forceinline__ uint32_t hmk_hash(uint32_t x) { return (x * 2654435761u) >> (32 - 11); }   // log2(HMK_HASH_SIZE) = 11
+
+// The CTA first stages every per-batch input in shared memory (all warps, parallel gathers),
+// then warp 0 replays the steps in reference order.  What changes inside the batch is tracked
+// in shared memory too -- a hash set of the partners consumed so far, a hash map cluster ->
+// row for the clusters that received members, and each such cluster's running size / count /
+// tail (written through to global memory) -- so a typical step issues NO global loads.
 __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(const HmkState S, const HmkP1Batch B, int cache_entries) {
     extern __shared__ __align__(128) unsigned char rs_raw[];
     const int nq = B.nq, nw = B.nw, kb = B.kb;
     unsigned char* p = rs_raw;
+    int32_t* s_ibrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.ib_stride * 4 * 2;   // [2][ib_stride]: scores of the step's query
+    int32_t* s_pdrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.pd_stride * 4 * 2;   //   vs batch queries / partner candidates
     int32_t* s_qid = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
+    int32_t* s_qab = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
     int32_t* s_bkcnt = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
     int32_t* s_bkovf = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
     int32_t* s_acraw = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
     int32_t* s_acoff = reinterpret_cast<int32_t*>(p);   p += (size_t)(nq + 1) * 4;
     uint32_t* s_ibm = reinterpret_cast<uint32_t*>(p);   p += (size_t)nq * nw * 4;
-    uint32_t* t_mask = reinterpret_cast<uint32_t*>(p);  p += (size_t)nq * nw * 4;   // [row][nw]
+    uint32_t* t_mask = reinterpret_cast<uint32_t*>(p);  p += (size_t)nq * nw * 4;   // [row][nw] batch queries added to the cluster
     int32_t* t_fb = reinterpret_cast<int32_t*>(p);      p += (size_t)nq * 4;   // founder's batch index, -1 = pre-batch cluster
-    int32_t* f_slot = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;
+    int32_t* t_size = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // running Cluster.size()
+    int32_t* t_fid = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;   // Cluster.getId()
+    int32_t* t_count = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;   // running getUniqueSize()
+    int32_t* t_tail = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;
+    int32_t* f_slot = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // cluster founded by batch query b
     int32_t* f_pick = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // which of its candidates the founder took
-    int32_t* f_tidx = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // touched-table row of the cluster it founded
-    p = rs_raw + ((size_t)(p - rs_raw + 7) & ~(size_t)7);
-    uint64_t* s_bkkey = reinterpret_cast<uint64_t*>(p); p += (size_t)nq * kb * 8;
-    int32_t* s_acslot = reinterpret_cast<int32_t*>(p);  p += (size_t)cache_entries * 4;
-    int32_t* s_acscore = reinterpret_cast<int32_t*>(p);
-    __shared__ int s_cached;
-    __shared__ int32_t tc_c[HMK_MAXBATCH + 64], tc_cl[HMK_MAXBATCH + 64], tc_row[HMK_MAXBATCH + 64];   // per-step list of touched candidates
+    int32_t* f_tidx = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // its row
+    int32_t* s_bkid = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * kb * 4;
+    int32_t* s_bksc = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * kb * 4;
+    int32_t* s_bkab = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * kb * 4;
+    int32_t* tc_c = reinterpret_cast<int32_t*>(p);      p += (size_t)nq * 4;
+    int32_t* tc_cl = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
+    int32_t* tc_row = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;
+    int4* s_cand = reinterpret_cast<int4*>(rs_raw + ((size_t)(p - rs_raw + 15) & ~(size_t)15));   // (slot, score, size, fid)
+    __shared__ int32_t h_cons[HMK_HASH_SIZE];            // set: sequence ids consumed as partners in this batch
+    __shared__ int32_t h_tkey[HMK_HASH_SIZE], h_trow[HMK_HASH_SIZE];   // map: cluster slot -> row
+    __shared__ int s_ncached;                            // queries [0, s_ncached) have their candidates cached
+    __shared__ __align__(8) uint64_t row_bar[2];         // TMA completion barriers of the two row buffers
 
+    for (int i = threadIdx.x; i < HMK_HASH_SIZE; i += blockDim.x) { h_cons[i] = -1; h_tkey[i] = -1; }
     for (int i = threadIdx.x; i < nq; i += blockDim.x) {
-        s_qid[i] = B.qid[i]; s_bkcnt[i] = B.bk_cnt[i]; s_bkovf[i] = B.bk_ovf[i]; s_acraw[i] = B.ac_cnt[i];
+        const int32_t q = B.qid[i];
+        s_qid[i] = q; s_qab[i] = S.ab[q]; s_bkcnt[i] = B.bk_cnt[i]; s_bkovf[i] = B.bk_ovf[i]; s_acraw[i] = B.ac_cnt[i];
     }
     for (int i = threadIdx.x; i < nq * nw; i += blockDim.x) s_ibm[i] = B.ibm[i];
-    for (int i = threadIdx.x; i < nq * kb; i += blockDim.x) s_bkkey[i] = B.bk_key[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < nq; i++) { s_acoff[i] = run; run += min(s_acraw[i], B.capq); }
-        s_acoff[nq] = run;
-        s_cached = run <= cache_entries;
+    for (int i = threadIdx.x; i < nq * kb; i += blockDim.x) {
+        const int32_t id = B.pcand[i];
+        s_bkid[i] = id; s_bksc[i] = hmk_key_score(B.bk_key[i]); s_bkab[i] = S.ab[id];
     }
     __syncthreads();
-    const bool cached = s_cached != 0;
-    if (cached) {
-        const int total = s_acoff[nq];
+    if (threadIdx.x == 0) {
+        int run = 0, nc = 0;
+        for (int i = 0; i < nq; i++) {
+            s_acoff[i] = run;
+            const int c = min(s_acraw[i], B.capq);
+            if (nc == i && run + c <= cache_entries) { run += c; nc = i + 1; }
+        }
+        s_acoff[nq] = run;
+        s_ncached = nc;
+    }
+    __syncthreads();
+    const int ncached = s_ncached;
+    {
+        const int total = ncached ? s_acoff[ncached - 1] + min(s_acraw[ncached - 1], B.capq) : 0;
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            int lo = 0, hi = nq - 1;          // query of entry e
+            int lo = 0, hi = ncached - 1;          // query of entry e
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_acoff[mid] <= e) lo = mid; else hi = mid - 1; }
             const size_t g = (size_t)lo * B.capq + (e - s_acoff[lo]);
-            s_acslot[e] = B.ac_slot[g];
-            s_acscore[e] = B.ac_score[g];
+            const int32_t c = B.ac_slot[g];
+            s_cand[e] = make_int4(c, B.ac_score[g], S.c_size[c], S.c_founder[c]);
         }
     }
     __syncthreads();
@@ -805,18 +832,38 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     int32_t tn = 0;                 // rows of the touched table
     uint32_t fmask = 0;             // this lane's word of the founder mask
 
+    auto consumed = [&](int32_t id) -> bool {
+        uint32_t h = hmk_hash((uint32_t)id);
+        for (;;) {
+            const int32_t v = h_cons[h];
+            if (v == id) return true;
+            if (v < 0) return false;
+            h = (h + 1) & (HMK_HASH_SIZE - 1);
+        }
+    };
+    auto touched_row = [&](int32_t c) -> int {
+        uint32_t h = hmk_hash((uint32_t)c);
+        for (;;) {
+            const int32_t v = h_tkey[h];
+            if (v == c) return h_trow[h];
+            if (v < 0) return -1;
+            h = (h + 1) & (HMK_HASH_SIZE - 1);
+        }
+    };
     // complete linkage over the members cluster row `row` received in this batch, evaluated by ONE
     // lane (lanes work on different candidate clusters in parallel): every batch query that joined
     // must be in the hit mask of query b, a partner must score >= T (table pd), then the minimum
     auto eval_touched = [&](int row, int b, int32_t& cl) -> bool {
         const uint32_t* tm = t_mask + row * nw;
         const uint32_t* hm = s_ibm + b * nw;
+        const int32_t* ibr = s_ibrow + (b & 1) * B.ib_stride;
+        const int32_t* pdr = s_pdrow + (b & 1) * B.pd_stride;
         for (int w = 0; w < nw; w++)
             if (tm[w] & ~hm[w]) return false;
         int32_t mn = cl;
         const int32_t fb = t_fb[row];
         if (fb >= 0) {     // cluster born in this batch: its partner was one of the founder's candidates
-            const int32_t s = B.pd[(size_t)b * B.pd_stride + fb * kb + f_pick[fb]];
+            const int32_t s = pdr[fb * kb + f_pick[fb]];
             if (s < S.T) return false;
             mn = s < mn ? s : mn;
         }
@@ -825,53 +872,49 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             while (m) {
                 const int b2 = w * 32 + __ffs(m) - 1;
                 m &= m - 1;
-                const int32_t s = B.ib[(size_t)b * B.ib_stride + b2];
+                const int32_t s = ibr[b2];
                 mn = s < mn ? s : mn;
             }
         }
         cl = mn;
         return true;
     };
+    // rows b of ib / pd are fetched one step ahead by the TMA bulk-copy engine
+    const uint32_t row_bytes = (uint32_t)(B.ib_stride + B.pd_stride) * 4;
+    auto prefetch_rows = [&](int b) {
+        uint64_t* bar = &row_bar[b & 1];
+        hmk_mbar_expect_tx(bar, row_bytes);
+        hmk_bulk_g2s(s_ibrow + (b & 1) * B.ib_stride, B.ib + (size_t)b * B.ib_stride, (uint32_t)B.ib_stride * 4, bar);
+        hmk_bulk_g2s(s_pdrow + (b & 1) * B.pd_stride, B.pd + (size_t)b * B.pd_stride, (uint32_t)B.pd_stride * 4, bar);
+    };
+    if (lane == 0) {
+        hmk_mbar_init(&row_bar[0], 1);
+        hmk_mbar_init(&row_bar[1], 1);
+        prefetch_rows(0);
+    }
+    __syncwarp();
 
     for (int b = 0; b < nq; b++) {
         const int32_t q = s_qid[b];
+        hmk_mbar_wait(&row_bar[b & 1], (uint32_t)(b >> 1) & 1u);     // rows of this step have landed
+        if (lane == 0 && b + 1 < nq) prefetch_rows(b + 1);            // the other buffer was released by step b-1
         if (ncl >= S.K) { status = HMK_P1_DONE; cur = q; break; }                   // :90
+        if (consumed(q)) continue;   // taken as a partner earlier in this batch (:101,110)
         const int32_t acnt = s_acraw[b];
-        const int32_t bcnt = s_bkcnt[b];
-        const int32_t* acs = cached ? s_acslot + s_acoff[b] : B.ac_slot + (size_t)b * B.capq;
-        const int32_t* acv = cached ? s_acscore + s_acoff[b] : B.ac_score + (size_t)b * B.capq;
-        const int32_t ause = acnt < B.capq ? acnt : B.capq;
-
-        // ---- one round of global loads: everything mutable this step depends on
-        const int32_t slotq = __ldcg(S.slot + q);
-        uint64_t key = 0;
-        int32_t id = -1, idslot = 0;
-        if (lane < bcnt) {
-            key = s_bkkey[b * kb + lane];
-            const uint32_t r = hmk_key_rank(key);
-            id = S.id_of_rank ? S.id_of_rank[r] : (int32_t)r;
-            idslot = __ldcg(S.slot + id);
-        }
-        int32_t c0 = -1, cl0 = 0, st0 = 0, sz0 = 0, fd0 = 0;
-        if (lane < ause) {
-            c0 = acs[lane]; cl0 = acv[lane];
-            st0 = __ldcg(B.c_stamp + c0); sz0 = __ldcg(S.c_size + c0); fd0 = __ldcg(S.c_founder + c0);
-        }
-
-        if (slotq >= 0) continue;   // consumed as a partner earlier in this batch (:101,110)
         if (acnt > B.capq) { status = HMK_P1_GROW; cur = q; break; }   // candidate arrays too small: host grows them
+        const int32_t bcnt = s_bkcnt[b];
 
         // ---- B: nearest among initialList[index+1 ..]                               (:93)
         int bkind = 0;   // 0 = Java null, 1 = found, 2 = (null cluster, MIN_VALUE) object
         int32_t bscore = HMK_JMIN, bid = -1, bpick = 0;
         if (unproc - 1 == 0) bkind = 2;            // empty sub-list (ClinkageSequenceClusterer.java:138-140)
         else {
-            const unsigned am = __ballot_sync(FULL, lane < bcnt && idslot < 0);
+            const bool alive = lane < bcnt && !consumed(s_bkid[b * kb + lane]);
+            const unsigned am = __ballot_sync(FULL, alive);
             if (am) {
-                const int src = __ffs(am) - 1;      // list is sorted: first alive entry wins
-                bpick = src;
-                bid = __shfl_sync(FULL, id, src);
-                bscore = hmk_key_score(__shfl_sync(FULL, key, src));
+                bpick = __ffs(am) - 1;              // list is sorted: first alive entry wins
+                bid = s_bkid[b * kb + bpick];
+                bscore = s_bksc[b * kb + bpick];
                 bkind = 1;
             } else if (s_bkovf[b]) {
                 status = HMK_P1_RESTART; cur = q; break;    // list truncated: rescore from q
@@ -887,56 +930,59 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             const uint32_t hm = lane < nw ? s_ibm[b * nw + lane] : 0u;
             int nt = 0;   // touched candidates collected for this step (warp-uniform)
             // pre-batch clusters: untouched ones are final, touched ones need the batch members too
-            for (int e0 = 0; e0 < ause; e0 += 32) {
+            for (int e0 = 0; e0 < acnt; e0 += 32) {
                 const int e = e0 + lane;
                 int32_t c = -1, cl = 0;
-                bool touched = false;
-                if (e < ause) {
-                    int32_t st, sz, fd;
-                    if (e0 == 0) { c = c0; cl = cl0; st = st0; sz = sz0; fd = fd0; }
+                int row = -1;
+                if (e < acnt) {
+                    int32_t sz, fd;
+                    if (b < ncached) { const int4 v = s_cand[s_acoff[b] + e]; c = v.x; cl = v.y; sz = v.z; fd = v.w; }
                     else {
-                        c = acs[e]; cl = acv[e];
-                        st = __ldcg(B.c_stamp + c); sz = __ldcg(S.c_size + c); fd = __ldcg(S.c_founder + c);
+                        c = B.ac_slot[(size_t)b * B.capq + e]; cl = B.ac_score[(size_t)b * B.capq + e];
+                        sz = __ldcg(S.c_size + c); fd = __ldcg(S.c_founder + c);
                     }
-                    touched = st == B.batch_id;
-                    if (!touched) hmk_consider(best, cl, sz, fd, c);
+                    row = tn ? touched_row(c) : -1;
+                    if (row < 0) hmk_consider(best, cl, sz, fd, c);
                 }
-                const unsigned tmk = __ballot_sync(FULL, touched);
-                if (touched) {
+                const unsigned tmk = __ballot_sync(FULL, row >= 0);
+                if (row >= 0) {
                     const int pos = nt + __popc(tmk & ((1u << lane) - 1u));
-                    tc_c[pos] = c; tc_cl[pos] = cl; tc_row[pos] = -1;     // row looked up below
+                    tc_c[pos] = c; tc_cl[pos] = cl; tc_row[pos] = row;
                 }
                 nt += __popc(tmk);
             }
             // clusters born in this batch whose founder scores >= T
             {
                 const uint32_t bits = fmask & hm;
-                int mine = __popc(bits), pre = mine;
+                const unsigned anyb = __ballot_sync(FULL, bits != 0);
+                if (anyb) {
+                    int mine = __popc(bits), pre = mine;
 #pragma unroll
-                for (int d2 = 1; d2 < 32; d2 <<= 1) { const int v = __shfl_up_sync(FULL, pre, d2); if (lane >= d2) pre += v; }
-                const int total = __shfl_sync(FULL, pre, 31);
-                int pos = nt + pre - mine;
-                uint32_t m = bits;
-                while (m) {
-                    const int b2 = lane * 32 + __ffs(m) - 1;
-                    m &= m - 1;
-                    tc_c[pos] = f_slot[b2]; tc_cl[pos] = HMK_JMAX; tc_row[pos] = f_tidx[b2];
-                    pos++;
-                }
-                nt += total;
-            }
-            __syncwarp();
-            for (int i0 = 0; i0 < nt; i0 += 32) {
-                const int i = i0 + lane;
-                if (i < nt) {
-                    const int32_t c2 = tc_c[i];
-                    int32_t cl2 = tc_cl[i];
-                    int row = tc_row[i];
-                    if (row < 0) row = __ldcg(B.c_tidx + c2);
-                    if (eval_touched(row, b, cl2)) hmk_consider(best, cl2, __ldcg(S.c_size + c2), __ldcg(S.c_founder + c2), c2);
+                    for (int d2 = 1; d2 < 32; d2 <<= 1) { const int v = __shfl_up_sync(FULL, pre, d2); if (lane >= d2) pre += v; }
+                    const int total = __shfl_sync(FULL, pre, 31);
+                    int pos = nt + pre - mine;
+                    uint32_t m = bits;
+                    while (m) {
+                        const int b2 = lane * 32 + __ffs(m) - 1;
+                        m &= m - 1;
+                        tc_c[pos] = f_slot[b2]; tc_cl[pos] = HMK_JMAX; tc_row[pos] = f_tidx[b2];
+                        pos++;
+                    }
+                    nt += total;
                 }
             }
-            __syncwarp();
+            if (nt) {
+                __syncwarp();
+                for (int i0 = 0; i0 < nt; i0 += 32) {
+                    const int i = i0 + lane;
+                    if (i < nt) {
+                        const int row = tc_row[i];
+                        int32_t cl2 = tc_cl[i];
+                        if (eval_touched(row, b, cl2)) hmk_consider(best, cl2, t_size[row], t_fid[row], tc_c[i]);
+                    }
+                }
+                __syncwarp();
+            }
             hmk_best_reduce(best);
             if (best.slot >= 0) akind = 1;
         }
@@ -953,34 +999,41 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         }
         if (join || create) {
             const int32_t c = join ? best.slot : ncl;
-            int tidx;
-            const bool fresh = create || __ldcg(B.c_stamp + c) != B.batch_id;
-            tidx = fresh ? tn : __ldcg(B.c_tidx + c);
+            int row = create ? -1 : (tn ? touched_row(c) : -1);
+            const bool fresh = row < 0;
             if (fresh) {
-                if (lane < nw) t_mask[tidx * nw + lane] = 0;
-                if (lane == 0) { t_fb[tidx] = create ? b : -1; B.c_stamp[c] = B.batch_id; B.c_tidx[c] = tidx; }
-                tn++;
+                row = tn++;
+                if (lane < nw) t_mask[row * nw + lane] = 0;
+                if (lane == 0) {
+                    uint32_t h = hmk_hash((uint32_t)c);
+                    while (h_tkey[h] >= 0) h = (h + 1) & (HMK_HASH_SIZE - 1);
+                    h_tkey[h] = c; h_trow[h] = row;
+                    if (create) { t_fb[row] = b; t_size[row] = 0; t_fid[row] = q; t_count[row] = 0; t_tail[row] = -1; }
+                    else {       // first change of a pre-batch cluster in this batch: fetch its running state
+                        t_fb[row] = -1; t_size[row] = __ldcg(S.c_size + c); t_fid[row] = __ldcg(S.c_founder + c);
+                        t_count[row] = __ldcg(S.c_count + c); t_tail[row] = __ldcg(S.c_tail + c);
+                    }
+                }
             }
             __syncwarp();
-            if (lane == (b >> 5)) t_mask[tidx * nw + lane] |= 1u << (b & 31);
-            if (create) {
-                if (lane == (b >> 5)) fmask |= 1u << (b & 31);
-                if (lane == 0) { f_slot[b] = c; f_pick[b] = bpick; f_tidx[b] = tidx; }
-            }
+            if (lane == (b >> 5)) t_mask[row * nw + lane] |= 1u << (b & 31);
+            if (create && lane == (b >> 5)) fmask |= 1u << (b & 31);
             if (lane == 0) {
-                if (join) {
-                    const int32_t tail = S.c_tail[c];
-                    S.next[tail] = q; S.next[q] = -1; S.c_tail[c] = q;
-                    const int32_t cnt = S.c_count[c];
-                    S.rank[q] = cnt; S.c_count[c] = cnt + 1;
-                    S.c_size[c] = hmk_wadd(__ldcg(S.c_size + c), S.ab[q]);
-                    S.slot[q] = c;
-                } else {
-                    S.c_founder[c] = q; S.c_tail[c] = bid; S.c_count[c] = 2;
-                    S.c_size[c] = hmk_wadd(S.ab[q], S.ab[bid]);
+                if (join) {                                               // insertAll({q})   (:97,104)
+                    S.next[t_tail[row]] = q; S.next[q] = -1;
+                    S.rank[q] = t_count[row]; S.slot[q] = c;
+                    t_tail[row] = q; t_count[row] += 1; t_size[row] = hmk_wadd(t_size[row], s_qab[b]);
+                } else {                                                  // new cluster {q, partner}   (:99-101,108-110)
+                    f_slot[b] = c; f_pick[b] = bpick; f_tidx[b] = row;
+                    S.c_founder[c] = q;
                     S.next[q] = bid; S.next[bid] = -1;
                     S.slot[q] = c; S.rank[q] = 0; S.slot[bid] = c; S.rank[bid] = 1;
+                    t_tail[row] = bid; t_count[row] = 2; t_size[row] = hmk_wadd(s_qab[b], s_bkab[b * kb + bpick]);
+                    uint32_t h = hmk_hash((uint32_t)bid);
+                    while (h_cons[h] >= 0) h = (h + 1) & (HMK_HASH_SIZE - 1);
+                    h_cons[h] = bid;
                 }
+                S.c_tail[c] = t_tail[row]; S.c_count[c] = t_count[row]; S.c_size[c] = t_size[row];   // write through
             }
         }
         if (join) joins++;
@@ -989,7 +1042,6 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         steps++;
         unproc--;
         cur = q + 1;
-        __threadfence_block();
         __syncwarp();
     }
     if (status == HMK_P1_CONTINUE && (ncl >= S.K || unproc <= 0)) status = HMK_P1_DONE;

@@ -495,6 +495,17 @@ class GreedyContext:
         self._L.hmk_get_stats(self._h, C.byref(st))
         return st.as_dict()
 
+    def init_distributed(self, dist, rank: int, world: int):
+        """Join an NCCL communicator of `world` ranks.  `dist` is an initialised torch.distributed
+        (any backend): it is only used to hand rank 0's 128-byte NCCL id to the other ranks."""
+        from . import distributed
+        uid = distributed.exchange_unique_id(dist, rank, nccl_unique_id)
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        err = C.create_string_buffer(512)
+        rc = self._L.hmk_init_distributed(self._h, int(rank), int(world), buf, err, 512)
+        if rc:
+            _raise_status(rc, err.value)
+
     def timer_begin(self):
         self._L.hmk_timer_begin(self._h)
 
@@ -528,6 +539,16 @@ class GreedyContext:
         if rc:
             _raise_status(rc, err.value)
         return out
+
+
+def nccl_unique_id() -> bytes:
+    L = _lib.load()
+    buf = (C.c_char * 128)()
+    err = C.create_string_buffer(512)
+    rc = L.hmk_nccl_unique_id(buf, err, 512)
+    if rc:
+        _raise_status(rc, err.value)
+    return bytes(buf)
 
 
 def greedy_cluster_arrays(residues, offsets, abundance, matrix, threshold, max_shift, shift_penalty, max_clusters,

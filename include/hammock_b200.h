@@ -96,6 +96,15 @@ int hmk_upload(hmk_ctx* ctx, const hmk_greedy_in* in, char* errbuf, size_t errle
 int hmk_run(hmk_ctx* ctx, char* errbuf, size_t errlen);
 int hmk_download(hmk_ctx* ctx, hmk_greedy_out* out, char* errbuf, size_t errlen);
 int hmk_get_stats(hmk_ctx* ctx, hmk_stats* stats);
+/* Multi-GPU: one process per GPU.  Rank 0 obtains a 128-byte NCCL unique id, the host distributes
+ * it (any channel), every rank calls hmk_init_distributed on its own context and then makes the
+ * SAME upload / run / download calls with the SAME input.  Phase 1 stripes the later singletons
+ * across ranks and all-gathers the per-rank best-hit lists; phase 2 shards the queries and
+ * all-gathers the candidate lists; decisions are replicated, so every rank returns the full,
+ * identical result. */
+int hmk_nccl_unique_id(void* id128, char* errbuf, size_t errlen);
+int hmk_init_distributed(hmk_ctx* ctx, int rank, int world, const void* id128, char* errbuf, size_t errlen);
+
 /* CUDA-event stopwatch on the library's stream (brackets upload + run + download for end-to-end
  * timing); hmk_timer_end synchronises and returns milliseconds. */
 int hmk_timer_begin(hmk_ctx* ctx);
