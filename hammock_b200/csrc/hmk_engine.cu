@@ -802,10 +802,14 @@ void Engine::phase2() {
     P.changed = d_flags_.p + 1;
     int32_t* cur = d_a0_.p;
     int32_t* nxt = d_a1_.p;
-    const int W = (int)std::max<int64_t>(1, opt.p2_window);
+    // window size adapts to how hard the fixed point is: dense inputs (everything joins) need many
+    // iterations per window unless few queries per cluster are in flight at a time
+    const int Wmax = (int)std::max<int64_t>(1, opt.p2_window);
+    int W = std::min(Wmax, std::max(1024, 8 * ncl));
     const int cgrid = (ncl + 255) / 256;
-    for (int qa = 0; qa < ns; qa += W) {
+    for (int qa = 0; qa < ns;) {
         const int qb = std::min(ns, qa + W);
+        int iters = 0;
         P.qa = qa; P.qb = qb;
         sec(SEC_P2_BASE);
         hmk_p2_window_lo<<<cgrid, 256, 0, st_>>>(P);
@@ -827,6 +831,7 @@ void Engine::phase2() {
             CK(cudaGetLastError());
             launches_ += 3;
             stats.p2_rounds++;
+            iters++;
             CK(cudaMemcpyAsync(h_scalars_ + 8, d_flags_.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
             CK(cudaStreamSynchronize(st_));
             if (!h_scalars_[8]) break;          // fixed point: tent lists == final joiners of this window
@@ -837,6 +842,9 @@ void Engine::phase2() {
         hmk_p2_commit<<<cgrid, 256, 0, st_>>>(P);
         CK(cudaGetLastError());
         launches_++;
+        qa = qb;
+        if (iters > 8) W = std::max(256, W / 2);
+        else if (iters <= 5) W = std::min(Wmax, W * 2);
     }
     sec(-1);
 }

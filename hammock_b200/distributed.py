@@ -29,3 +29,19 @@ def shard_range(n: int, world: int, rank: int):
     """Contiguous share [lo, hi) of n work items (the split the library uses for the database stripes
     of phase 1 and the query shards of phase 2)."""
     return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def merge_best_hits(per_rank_keys, per_rank_overflow, kb: int):
+    """Host-side statement of what hmk_topk_merge does with the all-gathered per-rank lists
+    (used by the CPU tests of the N > 1 path): the kb largest keys of the union, descending, and
+    whether anything was dropped anywhere."""
+    import numpy as np
+    allk = np.concatenate([np.asarray(k, dtype=np.uint64) for k in per_rank_keys]) if per_rank_keys else np.zeros(0, np.uint64)
+    allk = np.sort(allk)[::-1]
+    overflow = bool(any(per_rank_overflow)) or len(allk) > kb
+    return allk[:kb], overflow
+
+
+def make_key(score: int, tierank: int) -> int:
+    """hmk_key_make (csrc/hmk_common.h): bigger key == preferred partner."""
+    return (((score & 0xFFFFFFFF) ^ 0x80000000) << 32) | ((~tierank) & 0xFFFFFFFF)
