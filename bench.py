@@ -135,6 +135,10 @@ def main():
     ap.add_argument("--n", type=int, default=N_SEQ, help="debug only: smaller synthetic set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version) write to fd 1 too,
+    # so everything but the final line is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,7 +171,7 @@ def main():
                                            f"{vals[0]['seconds']:.1f} s; extrapolated to the >= {need} pair scores "
                                            "the reference needs for the whole job"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
         return 0
 
     # ------------------------------------------------------------ GPU arm
@@ -301,7 +305,7 @@ def main():
                           f"threads: first {s['p1_steps']} phase-1 steps + 2000 phase-2 queries = {s['pairs']} pair scores in "
                           f"{s['seconds']:.1f} s ({s['pairs_per_s'] / 1e6:.1f} M pairs/s), extrapolated to the >= {need} "
                           "pair scores the reference's early-exit evaluation needs for the whole job"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

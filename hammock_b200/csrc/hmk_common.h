@@ -100,4 +100,5 @@ struct HmkCtl {
     int32_t pad0, pad1;
     int64_t scalar_pairs;  // pair scores computed one at a time (resolvers, member checks)
     int64_t scalar_cells;
+    int64_t dbg[8];        // resolver cycle counters (only filled when built with -DHMK_RESOLVE_TIMING)
 };

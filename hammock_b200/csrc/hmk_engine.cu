@@ -118,7 +118,7 @@ enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_R
        SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
 
 struct Options {
-    int64_t batch = 0;          // phase-1 queries per batch (0 = four profile tiles)
+    int64_t batch = 0;          // phase-1 queries per batch (0 = three profile tiles)
     int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
     int64_t kb = 8;             // partner candidates kept per query
@@ -519,7 +519,7 @@ void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_
 // ---------------------------------------------------------------- phase 1
 int Engine::phase1() {
     int B = (int)opt.batch;
-    if (B <= 0) B = fast_ ? 4 * qt_max() : 192;
+    if (B <= 0) B = fast_ ? 3 * qt_max() : 192;
     B = std::max(1, std::min(B, HMK_MAXBATCH));
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
@@ -915,6 +915,9 @@ int Engine::run() {
     stats.bulk_kernel_ms = bulk_ms;
     stats.bulk_pairs = (int64_t)pc[0];
     stats.scalar_pairs = h_ctl_->scalar_pairs;
+    if (getenv("HMK_DEBUG_TIMING"))
+        fprintf(stderr, "resolver cycles: staging %lld rowwait %lld bpart %lld static %lld eval %lld apply %lld loop-top %lld\n", (long long)h_ctl_->dbg[0],
+                (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3], (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5], (long long)h_ctl_->dbg[7]);
     if (min_len_ == max_len_) {
         stats.bulk_cells = stats.bulk_pairs * hmk_pair_cells(max_len_, max_len_, X_);
         stats.bulk_ops = stats.bulk_cells + stats.bulk_pairs * (2 * (int64_t)X_ + 1);

@@ -21,7 +21,12 @@
 #include "hmk_resolve.h"
 
 #define HMK_MAXL1 12           // residues per 64-bit packed word
-#define HMK_BULK_THREADS 512
+#ifndef HMK_BULK_THREADS
+#define HMK_BULK_THREADS 768
+#endif
+#ifndef HMK_LFIX
+#define HMK_LFIX 0               // 12: compile the packed kernel for length-12 data only (no length predicates)
+#endif
 
 enum { HMK_MODE_TOPK = 0, HMK_MODE_EMIT = 1, HMK_MODE_DENSE = 2 };
 enum { HMK_PROF_QUERY = 0, HMK_PROF_MEMBER = 1 };
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __gri
     const int q0 = qtile * a.qt;
     const int qn = min(a.qt, a.nq - q0);
     if (qn <= 0) return;
-    const int L = a.sc.L;
+    const int L = HMK_LFIX ? HMK_LFIX : a.sc.L;
     size_t o = ((size_t)a.qt * PWB + 15) & ~(size_t)15;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + o);
     o += 16;
@@ -718,19 +723,28 @@ __global__ void hmk_ib_mask(int nq, int nw, int32_t T, const int32_t* __restrict
     ibm[idx] = m;
 }
 
+// warp arg-max under the reference's key (score desc, size desc, id asc) with three hardware
+// reductions (REDUX) instead of a 5-round shuffle butterfly over four fields
 __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        HmkBestCluster o;
-        o.score = __shfl_xor_sync(0xffffffffu, b.score, s);
-        o.size = __shfl_xor_sync(0xffffffffu, b.size, s);
-        o.fid = __shfl_xor_sync(0xffffffffu, b.fid, s);
-        o.slot = __shfl_xor_sync(0xffffffffu, b.slot, s);
-        if (o.slot >= 0) hmk_consider(b, o.score, o.size, o.fid, o.slot);
-    }
+    const unsigned FULL = 0xffffffffu;
+    const bool has = b.slot >= 0;
+    const int32_t mx = __reduce_max_sync(FULL, has ? b.score : HMK_JMIN);
+    const bool in1 = has && b.score == mx;
+    if (__ballot_sync(FULL, in1) == 0) { b.slot = -1; return; }
+    const int32_t ms = __reduce_max_sync(FULL, in1 ? b.size : HMK_JMIN);
+    const bool in2 = in1 && b.size == ms;
+    const int32_t mf = __reduce_min_sync(FULL, in2 ? b.fid : HMK_JMAX);
+    const unsigned win = __ballot_sync(FULL, in2 && b.fid == mf);
+    b.slot = __shfl_sync(FULL, b.slot, __ffs(win) - 1);
+    b.score = mx; b.size = ms; b.fid = mf;
 }
 
 #define HMK_RESOLVE_THREADS 256
+#ifdef HMK_RESOLVE_TIMING
+#define HMK_TICK(i) do { long long t_ = clock64(); dbg[i] += t_ - tlast; tlast = t_; } while (0)
+#else
+#define HMK_TICK(i) do {} while (0)
+#endif
 #define HMK_HASH_SIZE 2048          // >= 2 * HMK_MAXBATCH, power of two
 
 // shared-memory bytes of the resolver for a batch of nq queries, before the candidate cache
@@ -739,9 +753,10 @@ __host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb
     o += (size_t)nq * 4 * 5;                 // qid, qab, bk_cnt, bk_ovf, ac_raw
     o += (size_t)(nq + 1) * 4;               // ac_off
     o += (size_t)nq * nw * 4 * 2;            // ibm, t_mask
-    o += (size_t)nq * 4 * 8;                 // t_fb, t_size, t_fid, t_count, t_tail, f_slot, f_pick, f_tidx
+    o += (size_t)nq * 4 * 10;                // t_fb, t_size, t_fid, t_count, t_tail, t_nmem, t_first, f_slot, f_pick, f_tidx
     o += (size_t)nq * kb * 4 * 3;            // bk_id, bk_score, bk_ab
     o += (size_t)nq * 4 * 3;                 // per-step list of touched candidates (tc_c, tc_cl, tc_row)
+    o += (size_t)nq * 16 + (size_t)nw * 4 + 16;   // best untouched static candidate per query, dirty mask
     return o;
 }
 #define HMK_RESOLVE_CAND_BYTES 16            // cached candidate: slot, score, size, founder id
@@ -754,6 +769,9 @@ __device__ __forceinline__ uint32_t hmk_hash(uint32_t x) { return (x * 265443576
 // row for the clusters that received members, and each such cluster's running size / count /
 // tail (written through to global memory) -- so a typical step issues NO global loads.
 __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(const HmkState S, const HmkP1Batch B, int cache_entries) {
+#ifdef HMK_RESOLVE_TIMING
+    long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     extern __shared__ __align__(128) unsigned char rs_raw[];
     const int nq = B.nq, nw = B.nw, kb = B.kb;
     unsigned char* p = rs_raw;
@@ -772,6 +790,8 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     int32_t* t_fid = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;   // Cluster.getId()
     int32_t* t_count = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;   // running getUniqueSize()
     int32_t* t_tail = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;
+    int32_t* t_nmem = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // batch queries the cluster received
+    int32_t* t_first = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;   // the first of them
     int32_t* f_slot = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // cluster founded by batch query b
     int32_t* f_pick = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // which of its candidates the founder took
     int32_t* f_tidx = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // its row
@@ -781,7 +801,10 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     int32_t* tc_c = reinterpret_cast<int32_t*>(p);      p += (size_t)nq * 4;
     int32_t* tc_cl = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
     int32_t* tc_row = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;
-    int4* s_cand = reinterpret_cast<int4*>(rs_raw + ((size_t)(p - rs_raw + 15) & ~(size_t)15));   // (slot, score, size, fid)
+    p = rs_raw + ((size_t)(p - rs_raw + 15) & ~(size_t)15);
+    int4* s_best = reinterpret_cast<int4*>(p);           p += (size_t)nq * 16;   // per query: best static candidate (score, size, fid, slot)
+    uint32_t* s_dirty = reinterpret_cast<uint32_t*>(p);  p += (((size_t)nw * 4 + 15) & ~(size_t)15);   // queries whose static list saw a change
+    int4* s_cand = reinterpret_cast<int4*>(p);           // cache: (slot, score, size, fid)
     __shared__ int32_t h_cons[HMK_HASH_SIZE];            // set: sequence ids consumed as partners in this batch
     __shared__ int32_t h_tkey[HMK_HASH_SIZE], h_trow[HMK_HASH_SIZE];   // map: cluster slot -> row
     __shared__ int s_ncached;                            // queries [0, s_ncached) have their candidates cached
@@ -821,10 +844,26 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         }
     }
     __syncthreads();
+    {   // in parallel: each cached query's best static candidate, valid as long as none of them changes
+        const int wl = threadIdx.x & 31;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) s_dirty[i] = 0;
+        for (int b = threadIdx.x >> 5; b < ncached; b += blockDim.x >> 5) {
+            HmkBestCluster bb;
+            bb.score = HMK_JMIN; bb.size = 0; bb.fid = 0; bb.slot = -1;
+            const int cnt = min(s_acraw[b], B.capq);
+            for (int e = wl; e < cnt; e += 32) { const int4 v = s_cand[s_acoff[b] + e]; hmk_consider(bb, v.y, v.z, v.w, v.x); }
+            hmk_best_reduce(bb);
+            if (wl == 0) s_best[b] = make_int4(bb.score, bb.size, bb.fid, bb.slot);
+        }
+    }
+    __syncthreads();
     if (threadIdx.x >= 32) return;
+    HMK_TICK(0);   // staging
 
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
+    int fresh_joins = 0;            // pre-batch clusters changed in this batch (each costs a scan of the cache)
+    bool all_dirty = false;
     HmkCtl* ctl = S.ctl;
     int32_t ncl = ctl->ncl, unproc = ctl->unproc_alive;
     int32_t steps = ctl->steps, joins = ctl->joins, creates = ctl->creates, orphans = ctl->orphans;
@@ -858,10 +897,22 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         const uint32_t* hm = s_ibm + b * nw;
         const int32_t* ibr = s_ibrow + (b & 1) * B.ib_stride;
         const int32_t* pdr = s_pdrow + (b & 1) * B.pd_stride;
+        const int32_t fb = t_fb[row];
+        if (t_nmem[row] == 1) {     // the usual case: one batch query (+ its partner if the cluster was born here)
+            const int b2 = t_first[row];
+            if (((hm[b2 >> 5] >> (b2 & 31)) & 1u) == 0) return false;
+            int32_t mn1 = ibr[b2];
+            if (fb >= 0) {
+                const int32_t s = pdr[fb * kb + f_pick[fb]];
+                if (s < S.T) return false;
+                mn1 = s < mn1 ? s : mn1;
+            }
+            cl = mn1 < cl ? mn1 : cl;
+            return true;
+        }
         for (int w = 0; w < nw; w++)
             if (tm[w] & ~hm[w]) return false;
         int32_t mn = cl;
-        const int32_t fb = t_fb[row];
         if (fb >= 0) {     // cluster born in this batch: its partner was one of the founder's candidates
             const int32_t s = pdr[fb * kb + f_pick[fb]];
             if (s < S.T) return false;
@@ -896,8 +947,10 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
 
     for (int b = 0; b < nq; b++) {
         const int32_t q = s_qid[b];
+        HMK_TICK(7);
         hmk_mbar_wait(&row_bar[b & 1], (uint32_t)(b >> 1) & 1u);     // rows of this step have landed
         if (lane == 0 && b + 1 < nq) prefetch_rows(b + 1);            // the other buffer was released by step b-1
+        HMK_TICK(1);   // row wait + prefetch issue
         if (ncl >= S.K) { status = HMK_P1_DONE; cur = q; break; }                   // :90
         if (consumed(q)) continue;   // taken as a partner earlier in this batch (:101,110)
         const int32_t acnt = s_acraw[b];
@@ -921,6 +974,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             }
         }
 
+        HMK_TICK(2);   // consumed check + B part
         // ---- A: nearest among actualClusters (complete linkage)                      (:92)
         int akind = 0;
         HmkBestCluster best;
@@ -929,8 +983,13 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         else {
             const uint32_t hm = lane < nw ? s_ibm[b * nw + lane] : 0u;
             int nt = 0;   // touched candidates collected for this step (warp-uniform)
+            const bool clean = b < ncached && !all_dirty && ((s_dirty[b >> 5] >> (b & 31)) & 1u) == 0;
+            if (clean) {   // none of this query's pre-batch candidates changed: the staged best is final
+                const int4 v = s_best[b];
+                if (lane == 0 && v.w >= 0) { best.score = v.x; best.size = v.y; best.fid = v.z; best.slot = v.w; }
+            }
             // pre-batch clusters: untouched ones are final, touched ones need the batch members too
-            for (int e0 = 0; e0 < acnt; e0 += 32) {
+            for (int e0 = 0; !clean && e0 < acnt; e0 += 32) {
                 const int e = e0 + lane;
                 int32_t c = -1, cl = 0;
                 int row = -1;
@@ -951,6 +1010,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 }
                 nt += __popc(tmk);
             }
+            HMK_TICK(3);   // static candidates
             // clusters born in this batch whose founder scores >= T
             {
                 const uint32_t bits = fmask & hm;
@@ -983,10 +1043,14 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 }
                 __syncwarp();
             }
-            hmk_best_reduce(best);
+            if (clean && nt == 0) {      // only lane 0 holds a candidate: broadcast instead of reducing
+                best.score = __shfl_sync(FULL, best.score, 0); best.size = __shfl_sync(FULL, best.size, 0);
+                best.fid = __shfl_sync(FULL, best.fid, 0); best.slot = __shfl_sync(FULL, best.slot, 0);
+            } else hmk_best_reduce(best);
             if (best.slot >= 0) akind = 1;
         }
 
+        HMK_TICK(4);   // founders + touched evaluation + reduce
         // ---- decision                                                               (:94-114)
         const int32_t ascore = akind == 1 ? best.score : HMK_JMIN;
         bool join = false, create = false;
@@ -1008,10 +1072,25 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                     uint32_t h = hmk_hash((uint32_t)c);
                     while (h_tkey[h] >= 0) h = (h + 1) & (HMK_HASH_SIZE - 1);
                     h_tkey[h] = c; h_trow[h] = row;
+                    t_nmem[row] = 0; t_first[row] = b;
                     if (create) { t_fb[row] = b; t_size[row] = 0; t_fid[row] = q; t_count[row] = 0; t_tail[row] = -1; }
                     else {       // first change of a pre-batch cluster in this batch: fetch its running state
                         t_fb[row] = -1; t_size[row] = __ldcg(S.c_size + c); t_fid[row] = __ldcg(S.c_founder + c);
                         t_count[row] = __ldcg(S.c_count + c); t_tail[row] = __ldcg(S.c_tail + c);
+                    }
+                }
+                if (!create && !all_dirty) {
+                    // later queries that list this cluster can no longer use their staged best
+                    if (++fresh_joins > 32) all_dirty = true;
+                    else if (b + 1 < ncached) {
+                        const int e_lo = s_acoff[b + 1], e_hi = s_acoff[ncached - 1] + min(s_acraw[ncached - 1], B.capq);
+                        for (int e = e_lo + lane; e < e_hi; e += 32) {
+                            if (s_cand[e].x == c) {
+                                int lo = b + 1, hi = ncached - 1;
+                                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_acoff[mid] <= e) lo = mid; else hi = mid - 1; }
+                                atomicOr(&s_dirty[lo >> 5], 1u << (lo & 31));
+                            }
+                        }
                     }
                 }
             }
@@ -1019,6 +1098,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             if (lane == (b >> 5)) t_mask[row * nw + lane] |= 1u << (b & 31);
             if (create && lane == (b >> 5)) fmask |= 1u << (b & 31);
             if (lane == 0) {
+                t_nmem[row] += 1;
                 if (join) {                                               // insertAll({q})   (:97,104)
                     S.next[t_tail[row]] = q; S.next[q] = -1;
                     S.rank[q] = t_count[row]; S.slot[q] = c;
@@ -1043,8 +1123,12 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         unproc--;
         cur = q + 1;
         __syncwarp();
+        HMK_TICK(5);   // decision + apply
     }
     if (status == HMK_P1_CONTINUE && (ncl >= S.K || unproc <= 0)) status = HMK_P1_DONE;
+#ifdef HMK_RESOLVE_TIMING
+    if (lane == 0) for (int i = 0; i < 8; i++) ctl->dbg[i] += dbg[i];
+#endif
     if (lane == 0) {
         ctl->cur = cur; ctl->ncl = ncl; ctl->unproc_alive = unproc; ctl->status = status;
         if (npe_step >= 0) ctl->npe_step = npe_step;
