@@ -120,6 +120,7 @@ enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_R
 struct Options {
     int64_t batch = 0;          // phase-1 queries per batch (0 = three profile tiles)
     int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
+    int64_t lookahead = 1;      // 1: prepare the next batch's partner search while the current batch resolves
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
     int64_t kb = 8;             // partner candidates kept per query
     int64_t waves = 2;          // CTAs per SM targeted by the stripe split
@@ -144,7 +145,11 @@ public:
         CK(cudaGetDeviceProperties(&prop, device_));
         sm_count_ = prop.multiProcessorCount;
         smem_optin_ = prop.sharedMemPerBlockOptin;
-        CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&st_, cudaStreamNonBlocking, prio_hi));    // resolvers, small kernels
+        CK(cudaStreamCreateWithPriority(&st2_, cudaStreamNonBlocking, prio_lo));   // look-ahead partner search
+        for (auto& b : bb_) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
         CK(cudaMallocHost(&h_ctl_, sizeof(HmkCtl)));
         CK(cudaMallocHost(&h_scalars_, 16 * sizeof(int32_t)));
         CK(cudaEventCreate(&ev_a_));
@@ -164,6 +169,8 @@ public:
         if (h_ctl_) cudaFreeHost(h_ctl_);
         if (h_scalars_) cudaFreeHost(h_scalars_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
+        for (auto& b : bb_) if (b.ready) cudaEventDestroy(b.ready);
+        if (st2_) cudaStreamDestroy(st2_);
         if (st_) cudaStreamDestroy(st_);
     }
 
@@ -192,11 +199,10 @@ private:
     int device_;
     int rank_ = 0, world_ = 1;
     NcclApi::Comm comm_ = nullptr;
-    DevBuf<uint64_t> d_gk_key_;
-    DevBuf<int32_t> d_gk_cnt_, d_gk_ovf_, d_gcount_, d_gs_;
+    DevBuf<int32_t> d_gcount_, d_gs_;
     DevBuf<unsigned long long> d_gq_, d_gc_;
-    void allgather(const void* send, void* recv, size_t bytes) {
-        NK(NcclApi::get().AllGather(send, recv, bytes, HMK_NCCL_CHAR, comm_, st_));
+    void allgather(const void* send, void* recv, size_t bytes, cudaStream_t s) {
+        NK(NcclApi::get().AllGather(send, recv, bytes, HMK_NCCL_CHAR, comm_, s));
     }
     int sm_count_ = 148;
     size_t smem_optin_ = 0;
@@ -217,13 +223,25 @@ private:
     DevBuf<HmkCtl> d_ctl_;
     HmkCtl* h_ctl_ = nullptr;
     int32_t* h_scalars_ = nullptr;
+    // ---- phase-1 per-batch buffers, double buffered: while batch i is resolved on the main stream the
+    // partner search of batch i+1 already runs on the side stream
+    struct BatchBuf {
+        DevBuf<int32_t> qid, nq_dev, tk_cnt, tk_ovf, bk_cnt, bk_ovf, gk_cnt, gk_ovf;
+        DevBuf<uint64_t> tk_key, bk_key, gk_key;
+        DevBuf<uint32_t> prof;
+        cudaEvent_t ready = nullptr;
+        bool valid = false;      // partner search for the batch starting behind `after` has been issued
+        int nq = 0;
+    };
+    BatchBuf bb_[2];
+    cudaStream_t st2_ = nullptr;
+    void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s);
     // ---- phase-1 scratch
-    DevBuf<int32_t> d_qid_, d_nq_, d_tk_cnt_, d_tk_ovf_, d_bk_cnt_, d_bk_ovf_, d_ib_,
+    DevBuf<int32_t> d_qid_, d_nq_, d_ib_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_, d_dirty_b_;
     DevBuf<uint32_t> d_ibm_;
     DevBuf<int32_t> d_pcand_, d_pd_;
     int batch_id_ = 0;
-    DevBuf<uint64_t> d_tk_key_, d_bk_key_;
     DevBuf<uint32_t> d_prof_;
     DevBuf<int4> d_hits_;
     DevBuf<unsigned int> d_counts_;   // [0] hit_count, [1] cand_count
@@ -259,7 +277,8 @@ private:
     void choose_scheme(const int32_t* M);
     int qt_max() const;
     void launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof);
-    void launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query);
+    void launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s = nullptr,
+                     BatchBuf* bb = nullptr);
     cudaEvent_t next_event();
     // per-section device timers (only with opt.profile)
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> sections_;
@@ -432,8 +451,9 @@ static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, 
 }
 
 // fills in the tiling fields of `a` (nqt, qt, nstripes, chunk) and launches
-void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query) {
+void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s, BatchBuf* bb) {
     if (a.nq <= 0 || a.ndb <= 0) return;
+    if (!s) s = st_;
     a.sc = sc_;
     a.pair_counter = d_pairctr_.p;
     a.kb = (int)opt.kb;
@@ -455,36 +475,35 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
     a.nstripes = (a.ndb + a.chunk - 1) / a.chunk;
     if (mode == HMK_MODE_TOPK) {
         const size_t slots = (size_t)a.nstripes * a.nq;
-        d_tk_key_.reserve(slots * a.kb); d_tk_cnt_.reserve(slots); d_tk_ovf_.reserve(slots);
-        a.tk_key = d_tk_key_.p; a.tk_cnt = d_tk_cnt_.p; a.tk_ovf = d_tk_ovf_.p;
+        bb->tk_key.reserve(slots * a.kb); bb->tk_cnt.reserve(slots); bb->tk_ovf.reserve(slots);
+        a.tk_key = bb->tk_key.p; a.tk_cnt = bb->tk_cnt.p; a.tk_ovf = bb->tk_ovf.p;
     }
     const int grid = a.nqt * a.nstripes;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, st_)); }
+    if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, s)); }
     if (fast_) {
         size_t smem = (((size_t)a.qt * sc_.prof_words * 4 + 15) & ~(size_t)15) + 16 +
                       hmk_carve_bytes(a.qt, a.kb, HMK_BULK_THREADS, false);
-        if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, st_);
-        else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, st_);
-        else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, st_);
+        if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, s);
+        else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, s);
+        else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, s);
     } else {
         HmkGenericArgs g;
         g.b = a; g.prof_ids = prof_ids; g.prof_is_query = prof_is_query;
         g.res = d_res_.p; g.off = d_off_.p; g.M = d_M_.p; g.maxlen = std::max(max_len_, 1);
         size_t smem = HMK_NRES * HMK_NRES * 4 + hmk_carve_bytes(a.qt, a.kb, HMK_GENERIC_THREADS, true) +
                       (size_t)a.qt * 4 + (size_t)a.qt * g.maxlen + 16;
-        if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(g, grid, smem, st_);
-        else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(g, grid, smem, st_);
-        else launch_generic_mode<HMK_MODE_DENSE>(g, grid, smem, st_);
+        if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(g, grid, smem, s);
+        else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(g, grid, smem, s);
+        else launch_generic_mode<HMK_MODE_DENSE>(g, grid, smem, s);
     }
     CK(cudaGetLastError());
-    if (opt.profile) { CK(cudaEventRecord(e1, st_)); bulk_events_.push_back({e0, e1}); }
+    if (opt.profile) { CK(cudaEventRecord(e1, s)); bulk_events_.push_back({e0, e1}); }
     launches_++;
     bulk_launches_++;
     if (mode == HMK_MODE_TOPK) {
-        d_bk_key_.reserve((size_t)a.nq * a.kb); d_bk_cnt_.reserve(a.nq); d_bk_ovf_.reserve(a.nq);
-        hmk_topk_merge<<<(a.nq * 32 + 255) / 256, 256, 0, st_>>>(a.nq, a.nstripes, a.kb, d_tk_key_.p, d_tk_cnt_.p,
-                                                                 d_tk_ovf_.p, d_bk_key_.p, d_bk_cnt_.p, d_bk_ovf_.p);
+        hmk_topk_merge<<<(a.nq * 32 + 255) / 256, 256, 0, s>>>(a.nq, a.nstripes, a.kb, bb->tk_key.p, bb->tk_cnt.p,
+                                                               bb->tk_ovf.p, bb->bk_key.p, bb->bk_cnt.p, bb->bk_ovf.p);
         CK(cudaGetLastError());
         launches_++;
     }
@@ -517,6 +536,53 @@ void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_
 }
 
 // ---------------------------------------------------------------- phase 1
+// select the next batch, build its query profiles and run the partner search (+ the multi-GPU
+// best-hit exchange) on stream `s`; bb.ready fires when the merged lists are in bb.bk_*
+void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s) {
+    const int kb = (int)opt.kb;
+    bb.qid.reserve(HMK_MAXBATCH); bb.nq_dev.reserve(1);
+    bb.bk_key.reserve((size_t)HMK_MAXBATCH * kb); bb.bk_cnt.reserve(HMK_MAXBATCH); bb.bk_ovf.reserve(HMK_MAXBATCH);
+    if (fast_) bb.prof.reserve((size_t)HMK_MAXBATCH * sc_.prof_words);
+    hmk_select_queries<<<1, 1024, 0, s>>>(d_slot_.p, n_, d_ctl_.p, start_after, nq, bb.qid.p, bb.nq_dev.p);
+    CK(cudaGetLastError());
+    launches_++;
+    if (fast_) {
+        hmk_build_profiles<<<nq, 128, 0, s>>>(sc_, HMK_PROF_QUERY, bb.qid.p, nq, d_res_.p, d_off_.p, d_M_.p, bb.prof.p);
+        CK(cudaGetLastError());
+        launches_++;
+    }
+    HmkBulkArgs a{};
+    a.prof = bb.prof.p; a.nq = nq;
+    // this rank's stripe of the later singletons (the whole range on one GPU)
+    const int64_t span = (int64_t)n_ - db_from;
+    const int lo = db_from + (int)(span * rank_ / world_), hi = db_from + (int)(span * (rank_ + 1) / world_);
+    a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = lo; a.ndb = hi - lo;
+    a.slot = d_slot_.p; a.q_minid = bb.qid.p;
+    a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
+    if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, bb.qid.p, 1, s, &bb);
+    else {
+        CK(cudaMemsetAsync(bb.bk_cnt.p, 0, sizeof(int32_t) * nq, s));
+        CK(cudaMemsetAsync(bb.bk_ovf.p, 0, sizeof(int32_t) * nq, s));
+    }
+    if (world_ > 1) {
+        // best-hit exchange: every rank contributes its stripe's top-k per query (a few KB),
+        // then every rank merges the same lists -> identical, replicated decisions
+        bb.gk_key.reserve((size_t)world_ * nq * kb); bb.gk_cnt.reserve((size_t)world_ * nq); bb.gk_ovf.reserve((size_t)world_ * nq);
+        NK(NcclApi::get().GroupStart());
+        allgather(bb.bk_key.p, bb.gk_key.p, sizeof(uint64_t) * nq * kb, s);
+        allgather(bb.bk_cnt.p, bb.gk_cnt.p, sizeof(int32_t) * nq, s);
+        allgather(bb.bk_ovf.p, bb.gk_ovf.p, sizeof(int32_t) * nq, s);
+        NK(NcclApi::get().GroupEnd());
+        hmk_topk_merge<<<(nq * 32 + 255) / 256, 256, 0, s>>>(nq, world_, kb, bb.gk_key.p, bb.gk_cnt.p, bb.gk_ovf.p,
+                                                             bb.bk_key.p, bb.bk_cnt.p, bb.bk_ovf.p);
+        CK(cudaGetLastError());
+        launches_++;
+    }
+    CK(cudaEventRecord(bb.ready, s));
+    bb.valid = true;
+    bb.nq = nq;
+}
+
 int Engine::phase1() {
     int B = (int)opt.batch;
     if (B <= 0) B = fast_ ? 3 * qt_max() : 192;
@@ -524,70 +590,46 @@ int Engine::phase1() {
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
     const int nwmax = (B + 31) / 32;
-    d_qid_.reserve(B); d_nq_.reserve(1);
     d_ib_.reserve((size_t)B * (B + 4));
     d_ibm_.reserve((size_t)B * nwmax);
     d_pcand_.reserve((size_t)B * opt.kb); d_pd_.reserve((size_t)B * (B * opt.kb + 4));
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
     batch_id_ = 0;
-    if (fast_) d_prof_.reserve((size_t)B * sc_.prof_words);
     size_t hit_cap = (size_t)opt.hit_cap;
     d_hits_.reserve(hit_cap);
+    bb_[0].valid = bb_[1].valid = false;
+    int which = 0;
     fetch_ctl();
     while (h_ctl_->ncl < K_ && h_ctl_->unproc_alive > 0) {
-        const int nq = std::min(B, h_ctl_->unproc_alive);
+        BatchBuf& cb = bb_[which];
+        BatchBuf& nb = bb_[which ^ 1];
         const int cur = h_ctl_->cur, ncl = h_ctl_->ncl;
-        sec(SEC_P1_SELECT);
-        hmk_select_queries<<<1, 1024, 0, st_>>>(d_slot_.p, n_, d_ctl_.p, nq, d_qid_.p, d_nq_.p);
-        CK(cudaGetLastError());
-        launches_++;
-        if (fast_) launch_profiles(HMK_PROF_QUERY, d_qid_.p, nq, d_prof_.p);
-        // B: partner search over all later singletons
         sec(SEC_P1_PARTNER);
-        {
-            HmkBulkArgs a{};
-            a.prof = d_prof_.p; a.nq = nq;
-            // this rank's stripe of the later singletons (the whole range on one GPU)
-            const int64_t span = (int64_t)n_ - cur;
-            const int lo = cur + (int)(span * rank_ / world_), hi = cur + (int)(span * (rank_ + 1) / world_);
-            a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = lo; a.ndb = hi - lo;
-            a.slot = d_slot_.p; a.q_minid = d_qid_.p;
-            a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
-            d_bk_key_.reserve((size_t)nq * opt.kb); d_bk_cnt_.reserve(nq); d_bk_ovf_.reserve(nq);
-            if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, d_qid_.p, 1);
-            else {
-                CK(cudaMemsetAsync(d_bk_cnt_.p, 0, sizeof(int32_t) * nq, st_));
-                CK(cudaMemsetAsync(d_bk_ovf_.p, 0, sizeof(int32_t) * nq, st_));
-            }
-            if (world_ > 1) {
-                // best-hit exchange: every rank contributes its stripe's top-k per query (a few KB),
-                // then every rank merges the same lists -> identical, replicated decisions
-                const int kb = (int)opt.kb;
-                d_gk_key_.reserve((size_t)world_ * nq * kb); d_gk_cnt_.reserve((size_t)world_ * nq); d_gk_ovf_.reserve((size_t)world_ * nq);
-                NK(NcclApi::get().GroupStart());
-                allgather(d_bk_key_.p, d_gk_key_.p, sizeof(uint64_t) * nq * kb);
-                allgather(d_bk_cnt_.p, d_gk_cnt_.p, sizeof(int32_t) * nq);
-                allgather(d_bk_ovf_.p, d_gk_ovf_.p, sizeof(int32_t) * nq);
-                NK(NcclApi::get().GroupEnd());
-                hmk_topk_merge<<<(nq * 32 + 255) / 256, 256, 0, st_>>>(nq, world_, kb, d_gk_key_.p, d_gk_cnt_.p, d_gk_ovf_.p,
-                                                                       d_bk_key_.p, d_bk_cnt_.p, d_bk_ovf_.p);
-                CK(cudaGetLastError());
-                launches_++;
-            }
+        if (!cb.valid) stage_partner_search(cb, std::min(B, h_ctl_->unproc_alive), cur, nullptr, st_);   // not prepared ahead
+        else CK(cudaStreamWaitEvent(st_, cb.ready, 0));
+        const int nq = cb.nq;
+        // look ahead: the next batch's partner search runs on the side stream while this batch is
+        // resolved (it only needs this batch's last query id; whatever this batch consumes in the
+        // meantime is filtered by the resolver's consumed set)
+        if (opt.lookahead && !nb.valid && nq == B && h_ctl_->unproc_alive >= nq + 3 * B) {
+            CK(cudaStreamWaitEvent(st2_, cb.ready, 0));
+            stage_partner_search(nb, B, cur, cb.qid.p + (nq - 1), st2_);
         }
+        const int32_t* d_qid = cb.qid.p;
+        const uint32_t* d_prof = cb.prof.p;
         // A: clusters whose founder scores >= T, then complete linkage over their members
         sec(SEC_P1_CLUSTER);
         CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
         CK(cudaMemsetAsync(d_ac_cnt_.p, 0, sizeof(int32_t) * nq, st_));
         if (ncl > 0) {
             HmkBulkArgs a{};
-            a.prof = d_prof_.p; a.nq = nq;
+            a.prof = d_prof; a.nq = nq;
             a.packed = d_packed_.p; a.db_ids = d_cf_.p; a.db_begin = 0; a.ndb = ncl;
             a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
-            launch_bulk(HMK_MODE_EMIT, a, d_qid_.p, 1);
+            launch_bulk(HMK_MODE_EMIT, a, d_qid, 1);
             HmkCheckArgs c{};
             c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
-            c.hit_t_is_query = 1; c.qids = d_qid_.p;
+            c.hit_t_is_query = 1; c.qids = d_qid;
             c.ac_cnt = d_ac_cnt_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p; c.capq = (int32_t)capq;
             c.cand_count = d_counts_.p + 1; c.cand_cap = 0; c.linked = 1;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
@@ -600,10 +642,10 @@ int Engine::phase1() {
         sec(SEC_P1_INTRA);
         {
             HmkBulkArgs a{};
-            a.prof = d_prof_.p; a.nq = nq;
-            a.packed = d_packed_.p; a.db_ids = d_qid_.p; a.db_begin = 0; a.ndb = nq;
+            a.prof = d_prof; a.nq = nq;
+            a.packed = d_packed_.p; a.db_ids = d_qid; a.db_begin = 0; a.ndb = nq;
             a.dense = d_ib_.p; a.dense_stride = ib_stride;
-            launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
+            launch_bulk(HMK_MODE_DENSE, a, d_qid, 1);
         }
         const int nw = (nq + 31) / 32;
         hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, st_>>>(nq, nw, T_, d_ib_.p, ib_stride, d_ibm_.p);
@@ -612,18 +654,18 @@ int Engine::phase1() {
         // batch have one of these as their second member
         {
             const int npc = nq * (int)opt.kb;
-            hmk_partner_ids<<<(npc + 127) / 128, 128, 0, st_>>>(nq, (int)opt.kb, d_bk_key_.p, d_bk_cnt_.p,
-                                                                 identity_rank_ ? nullptr : d_id_of_rank_.p, d_qid_.p, d_pcand_.p);
+            hmk_partner_ids<<<(npc + 127) / 128, 128, 0, st_>>>(nq, (int)opt.kb, cb.bk_key.p, cb.bk_cnt.p,
+                                                                 identity_rank_ ? nullptr : d_id_of_rank_.p, d_qid, d_pcand_.p);
             launches_++;
             HmkBulkArgs a{};
-            a.prof = d_prof_.p; a.nq = nq;
+            a.prof = d_prof; a.nq = nq;
             a.packed = d_packed_.p; a.db_ids = d_pcand_.p; a.db_begin = 0; a.ndb = npc;
             a.dense = d_pd_.p; a.dense_stride = pd_stride;
-            launch_bulk(HMK_MODE_DENSE, a, d_qid_.p, 1);
+            launch_bulk(HMK_MODE_DENSE, a, d_qid, 1);
         }
         HmkP1Batch pb{};
-        pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid_.p; pb.kb = (int)opt.kb;
-        pb.bk_key = d_bk_key_.p; pb.bk_cnt = d_bk_cnt_.p; pb.bk_ovf = d_bk_ovf_.p;
+        pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid; pb.kb = (int)opt.kb;
+        pb.bk_key = cb.bk_key.p; pb.bk_cnt = cb.bk_cnt.p; pb.bk_ovf = cb.bk_ovf.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
         pb.ib = d_ib_.p; pb.ib_stride = ib_stride; pb.ibm = d_ibm_.p; pb.nw = nw;
         pb.pcand = d_pcand_.p;
@@ -634,7 +676,7 @@ int Engine::phase1() {
         if ((size_t)(uint32_t)h_scalars_[0] > hit_cap) {   // grow and redo this batch (state untouched)
             hit_cap = (size_t)(uint32_t)h_scalars_[0] * 5 / 4 + 1024;
             d_hits_.reserve(hit_cap);
-            continue;
+            continue;       // cb stays valid: only the cluster search is redone
         }
         sec(SEC_P1_RESOLVE);
         {
@@ -655,13 +697,22 @@ int Engine::phase1() {
         stats.p1_batches++;
         sec(-1);
         fetch_ctl();
-        if (h_ctl_->status == HMK_P1_NPE) { error_step = h_ctl_->npe_step; stats.error_step = error_step; return HMK_ERR_NULL_CLUSTER; }
-        if (h_ctl_->status == HMK_P1_DONE) break;
-        if (h_ctl_->status == HMK_P1_GROW) {   // a query had more valid clusters than its arrays hold
+        cb.valid = false;
+        const int st = h_ctl_->status;
+        if (st != HMK_P1_CONTINUE && nb.valid) {     // the look-ahead batch does not follow this one after all
+            CK(cudaStreamSynchronize(st2_));
+            nb.valid = false;
+        }
+        if (st == HMK_P1_NPE) { error_step = h_ctl_->npe_step; stats.error_step = error_step; return HMK_ERR_NULL_CLUSTER; }
+        if (st == HMK_P1_DONE) break;
+        if (st == HMK_P1_GROW) {   // a query had more valid clusters than its arrays hold
             capq *= 2;
             d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
         }
+        which ^= 1;
     }
+    CK(cudaStreamSynchronize(st2_));
+    bb_[0].valid = bb_[1].valid = false;
     return HMK_OK;
 }
 
@@ -735,7 +786,7 @@ void Engine::phase2() {
         d_gcount_.reserve(world_ + 1);
         int32_t mine = (int32_t)ncand;
         CK(cudaMemcpyAsync(d_gcount_.p + world_, &mine, sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-        allgather(d_gcount_.p + world_, d_gcount_.p, sizeof(int32_t));
+        allgather(d_gcount_.p + world_, d_gcount_.p, sizeof(int32_t), st_);
         std::vector<int32_t> counts(world_);
         CK(cudaMemcpyAsync(counts.data(), d_gcount_.p, sizeof(int32_t) * world_, cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
@@ -756,9 +807,9 @@ void Engine::phase2() {
             DevBuf<int32_t>& gs = d_gs_;
             gq.reserve(maxc * world_); gc.reserve(maxc * world_); gs.reserve(maxc * world_);
             NK(NcclApi::get().GroupStart());
-            allgather(d_key_q_.p, gq.p, sizeof(unsigned long long) * maxc);
-            allgather(d_key_c_.p, gc.p, sizeof(unsigned long long) * maxc);
-            allgather(d_cand_score_.p, gs.p, sizeof(int32_t) * maxc);
+            allgather(d_key_q_.p, gq.p, sizeof(unsigned long long) * maxc, st_);
+            allgather(d_key_c_.p, gc.p, sizeof(unsigned long long) * maxc, st_);
+            allgather(d_cand_score_.p, gs.p, sizeof(int32_t) * maxc, st_);
             NK(NcclApi::get().GroupEnd());
             std::swap(d_key_q_.p, gq.p); std::swap(d_key_q_.cap, gq.cap);
             std::swap(d_key_c_.p, gc.p); std::swap(d_key_c_.cap, gc.cap);
@@ -1155,6 +1206,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
     if (s == "batch") o.batch = value;
     else if (s == "qt") o.qt = value;
     else if (s == "capq") o.capq = value;
+    else if (s == "lookahead") o.lookahead = value;
     else if (s == "kb") o.kb = value;
     else if (s == "waves") o.waves = value;
     else if (s == "p2_chunk") o.p2_chunk = value;

@@ -540,16 +540,19 @@ __global__ void hmk_topk_merge(int nq, int nstripes, int kb, const uint64_t* __r
 
 // ---------------------------------------------------------------- batch selection (phase 1)
 // single CTA: the next `want` ids >= cur that are still singletons, ascending
-__global__ void hmk_select_queries(const int32_t* __restrict__ slot, int n, const HmkCtl* ctl, int want,
-                                   int32_t* __restrict__ qid, int32_t* __restrict__ nq_out) {
+// `start_after` (optional): start right behind that id (the last query of the previous batch) instead
+// of at ctl->cur -- used when the next batch is prepared while the current one is still resolving
+__global__ void hmk_select_queries(const int32_t* __restrict__ slot, int n, const HmkCtl* ctl, const int32_t* start_after,
+                                   int want, int32_t* __restrict__ qid, int32_t* __restrict__ nq_out) {
     __shared__ int warp_cnt[32];
     __shared__ int base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (threadIdx.x == 0) base = 0;
     __syncthreads();
-    for (int start = ctl->cur; start < n; start += blockDim.x) {
+    const int first = start_after ? *start_after + 1 : ctl->cur;
+    for (int start = first; start < n; start += blockDim.x) {
         const int i = start + threadIdx.x;
-        const bool f = i < n && slot[i] < 0;
+        const bool f = i < n && __ldcg(slot + i) < 0;
         const unsigned m = __ballot_sync(0xffffffffu, f);
         if (lane == 0) warp_cnt[wid] = __popc(m);
         __syncthreads();
@@ -562,6 +565,8 @@ __global__ void hmk_select_queries(const int32_t* __restrict__ slot, int n, cons
         __syncthreads();
         if (base >= want) break;
     }
+    // a speculative batch near the end of the list may find fewer ids: pad with the last one found (the
+    // resolver skips duplicates because the first occurrence is processed or consumed by then)
     if (threadIdx.x == 0) *nq_out = base < want ? base : want;
 }
 
@@ -819,6 +824,21 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     for (int i = threadIdx.x; i < nq * kb; i += blockDim.x) {
         const int32_t id = B.pcand[i];
         s_bkid[i] = id; s_bksc[i] = hmk_key_score(B.bk_key[i]); s_bkab[i] = S.ab[id];
+    }
+    __syncthreads();
+    // The partner lists may have been computed while the previous batch was still resolving: whatever
+    // stopped being a singleton since (queries or candidates) enters the consumed set up front.
+    for (int i = threadIdx.x; i < nq * (kb + 1); i += blockDim.x) {
+        const int b = i / (kb + 1), j = i % (kb + 1);
+        if (j > 0 && j - 1 >= s_bkcnt[b]) continue;
+        const int32_t id = j == 0 ? s_qid[b] : s_bkid[b * kb + j - 1];
+        if (__ldcg(S.slot + id) < 0) continue;
+        uint32_t h = hmk_hash((uint32_t)id);
+        for (;;) {
+            const int32_t v = atomicCAS(&h_cons[h], -1, id);
+            if (v == -1 || v == id) break;
+            h = (h + 1) & (HMK_HASH_SIZE - 1);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
