@@ -14,6 +14,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1080,6 +1083,11 @@ struct hmk_ctx {
     explicit hmk_ctx(int device) : engine(device) {}
 };
 
+static std::map<int, std::unique_ptr<hmk_ctx>>& cached_ctx() {
+    static std::map<int, std::unique_ptr<hmk_ctx>> m;
+    return m;
+}
+
 static void set_err(char* errbuf, size_t errlen, const char* msg) {
     if (errbuf && errlen) {
         std::strncpy(errbuf, msg, errlen - 1);
@@ -1115,6 +1123,8 @@ static const char* status_text(int rc) {
 extern "C" {
 
 int hmk_abi_version(void) { return HMK_ABI_VERSION; }
+
+void hmk_release_cached(void) { cached_ctx().clear(); }
 
 int hmk_create(hmk_ctx** ctx, int device, char* errbuf, size_t errlen) {
     if (!ctx) return HMK_STATUS_BAD_ARG;
@@ -1229,8 +1239,14 @@ int hmk_score_block(hmk_ctx* ctx, const int32_t* first_ids, int32_t n_first, con
 
 int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen) {
     if (!in || !out) return HMK_STATUS_BAD_ARG;
+    // one cached context per device: repeated calls reuse its device buffers (released by
+    // hmk_release_cached or at process exit); calls are serialised
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     return guarded(errbuf, errlen, [&] {
-        hmk_ctx ctx(device);
+        auto& slot = cached_ctx()[device];
+        if (!slot) slot.reset(new hmk_ctx(device));
+        hmk_ctx& ctx = *slot;
         ctx.engine.upload(in);
         int rc = ctx.engine.run();
         out->n_result = 0; out->n_multi = 0; out->error_step = ctx.engine.error_step;

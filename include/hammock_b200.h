@@ -85,8 +85,11 @@ typedef struct hmk_ctx hmk_ctx;
 
 int hmk_abi_version(void);
 
-/* One blocking call == SequenceClusterer.cluster(sequences).  Uses CUDA device `device`. */
+/* One blocking call == SequenceClusterer.cluster(sequences).  Uses CUDA device `device`.  The library
+ * keeps one context per device between calls (device buffers stay allocated, so repeated calls do not
+ * pay allocation again); hmk_release_cached frees them. */
 int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen);
+void hmk_release_cached(void);
 
 /* Handle API: the same work split into upload / device-resident run / download, so that a
  * host can keep the sequences resident and time the stages separately. */
