@@ -214,6 +214,12 @@ private:
     int32_t min_len_ = 0, max_len_ = 0;
     bool uploaded_ = false, ran_ = false, bad_residue_ = false;
     bool fast_ = false;
+    bool mixed_ = false;         // lengths differ but all <= 12 and every (m, n) pair fits the packed lanes
+    int nw_len_[HMK_MAXL1 + 1] = {0};
+    std::vector<int32_t> h_bucket_[HMK_MAXL1 + 1];   // ids per length, ascending
+    DevBuf<int32_t> d_bucket_[HMK_MAXL1 + 1];
+    DevBuf<int32_t> d_sidx_, d_sb_ids_, d_sb_cnt_;
+    DevBuf<uint32_t> d_pcells_, d_pops_;
     bool fast_scalar_ = false;   // uniform length <= 12: packed scalar scorer usable
     HmkScheme sc_{};
     std::vector<int32_t> h_off_;
@@ -232,6 +238,7 @@ private:
         DevBuf<int32_t> qid, nq_dev, tk_cnt, tk_ovf, bk_cnt, bk_ovf, gk_cnt, gk_ovf;
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
         DevBuf<uint32_t> prof;
+        DevBuf<uint32_t> prof_len[HMK_MAXL1 + 1], pcells[HMK_MAXL1 + 1], pops[HMK_MAXL1 + 1];   // mixed lengths: per thread-side length
         cudaEvent_t ready = nullptr;
         bool valid = false;      // partner search for the batch starting behind `after` has been issued
         int nq = 0;
@@ -278,8 +285,13 @@ private:
         return S;
     }
     void choose_scheme(const int32_t* M);
-    int qt_max() const;
-    void launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof);
+    int qt_max() const { return qt_max(sc_); }
+    int qt_max(const HmkScheme& sc) const;
+    HmkScheme scheme_for(int n) const;
+    void launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof, const HmkScheme& sc, cudaStream_t s,
+                         uint32_t* cells = nullptr, uint32_t* ops = nullptr);
+    void plan_bulk(HmkBulkArgs& a, const HmkScheme* sch) const;
+    void launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const int32_t* prof_ids, int prof_is_query, cudaStream_t s);
     void launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s = nullptr,
                      BatchBuf* bb = nullptr);
     cudaEvent_t next_event();
@@ -311,30 +323,52 @@ private:
 // ---------------------------------------------------------------- upload
 void Engine::choose_scheme(const int32_t* M) {
     fast_ = false;
+    mixed_ = false;
     sc_ = HmkScheme{};
     sc_.L = max_len_; sc_.X = X_; sc_.P = P_; sc_.T = T_;
     if (opt.force_generic) return;
-    if (n_ <= 0 || min_len_ != max_len_ || max_len_ < 1 || max_len_ > HMK_MAXL1) return;
-    if (X_ < 0 || X_ >= max_len_) return;
+    if (n_ <= 0 || min_len_ < 1 || max_len_ > HMK_MAXL1) return;
+    if (X_ < 0 || X_ >= min_len_) return;
     int64_t mmin = M[0], mmax = M[0];
     for (int i = 0; i < HMK_NRES * HMK_NRES; i++) { mmin = std::min<int64_t>(mmin, M[i]); mmax = std::max<int64_t>(mmax, M[i]); }
     const int64_t bias = mmin < 0 ? -mmin : 0;
-    const int lanes = 2 * X_ + 1;
+    bool present[HMK_MAXL1 + 1] = {false};
+    for (int i = 0; i < n_; i++) present[h_off_[i + 1] - h_off_[i]] = true;
+    // every pair of lengths (m, n) that occurs must fit the packed lanes: 2X+1+|n-m| lanes, and for each
+    // shift k the lane value stays inside [0, top] with "score >= T" at the lane's top bit
     for (int lane16 = 0; lane16 <= 1; lane16++) {
         const int64_t half = lane16 ? 32768 : 128, top = lane16 ? 65535 : 255;
-        const int nw = lane16 ? (lanes + 1) / 2 : (lanes + 3) / 4;
-        if (nw > 4) continue;
+        const int lpw = lane16 ? 2 : 4;
         bool ok = true;
-        for (int k = -X_; k <= X_ && ok; k++) {
-            const int64_t ak = k < 0 ? -k : k, nk = max_len_ - ak;
-            const int64_t init = 2 * (int64_t)P_ * ak + half - (int64_t)T_ - nk * bias;
-            const int64_t hi = init + nk * (mmax + bias);
-            if (init < 0 || hi > top || init > top) ok = false;
+        int nw[HMK_MAXL1 + 1] = {0};
+        for (int n = 1; n <= HMK_MAXL1 && ok; n++) {
+            if (!present[n]) continue;
+            for (int m = 1; m <= HMK_MAXL1 && ok; m++) {
+                if (!present[m]) continue;
+                const int ls = std::min(m, n), ll = std::max(m, n), d = ll - ls;
+                const int lanes = 2 * X_ + 1 + d;
+                nw[n] = std::max(nw[n], (lanes + lpw - 1) / lpw);
+                if (nw[n] > 4) { ok = false; break; }
+                for (int k = -X_; k <= X_ + d && ok; k++) {
+                    const int64_t cells = std::min(ls + k, ll) - std::max(k, 0);
+                    const int64_t pen = (int64_t)d * P_ + (k < 0 ? -2LL * k * P_ : 0) + (k > d ? 2LL * (k - d) * P_ : 0);
+                    const int64_t init = pen + half - (int64_t)T_ - cells * bias;
+                    const int64_t hi = init + cells * (mmax + bias);
+                    if (init < 0 || hi > top || init > top) ok = false;
+                }
+            }
         }
         if (!ok) continue;
-        fast_ = true;
-        sc_.nw = nw; sc_.lane16 = lane16; sc_.bias = (int32_t)bias; sc_.half = (int32_t)half;
-        sc_.prof_words = nw * HMK_MAXL1 * HMK_NRES;
+        sc_.lane16 = lane16; sc_.bias = (int32_t)bias; sc_.half = (int32_t)half;
+        if (min_len_ == max_len_) {
+            fast_ = true;
+            sc_.nw = nw[max_len_];
+        } else {
+            mixed_ = true;
+            sc_.nw = 0;
+            for (int n = 0; n <= HMK_MAXL1; n++) { nw_len_[n] = nw[n]; sc_.nw = std::max(sc_.nw, nw[n]); }
+        }
+        sc_.prof_words = sc_.nw * HMK_MAXL1 * HMK_NRES;
         return;
     }
 }
@@ -374,6 +408,16 @@ void Engine::upload(const hmk_greedy_in* in) {
         CK(cudaStreamSynchronize(st_));
     }
     choose_scheme(in->matrix);
+    for (auto& v : h_bucket_) v.clear();
+    if (mixed_) {
+        for (int i = 0; i < n_; i++) h_bucket_[h_off_[i + 1] - h_off_[i]].push_back(i);
+        for (int L = 1; L <= HMK_MAXL1; L++) {
+            if (h_bucket_[L].empty()) continue;
+            d_bucket_[L].reserve(h_bucket_[L].size());
+            CK(cudaMemcpyAsync(d_bucket_[L].p, h_bucket_[L].data(), sizeof(int32_t) * h_bucket_[L].size(), cudaMemcpyHostToDevice, st_));
+        }
+        CK(cudaStreamSynchronize(st_));
+    }
     fast_scalar_ = n_ > 0 && min_len_ == max_len_ && max_len_ >= 1 && max_len_ <= HMK_MAXL1 && X_ >= 0 && X_ < max_len_;
     // validate residues + pack 5 bits/residue on the device
     d_packed_.reserve(std::max(n_, 1));
@@ -389,7 +433,8 @@ void Engine::upload(const hmk_greedy_in* in) {
     const int kc = std::max(K_, 1);
     d_slot_.reserve(std::max(n_, 1)); d_rank_.reserve(std::max(n_, 1)); d_next_.reserve(std::max(n_, 1));
     d_cf_.reserve(kc); d_cs_.reserve(kc); d_cc_.reserve(kc); d_ct_.reserve(kc);
-    d_ctl_.reserve(1); d_counts_.reserve(4); d_pairctr_.reserve(2);
+    d_ctl_.reserve(1); d_counts_.reserve(4); d_pairctr_.reserve(4);
+    d_sidx_.reserve(std::max(n_, 1)); d_pcells_.reserve(std::max(K_, HMK_MAXBATCH)); d_pops_.reserve(std::max(K_, HMK_MAXBATCH));
     d_cluster_id_.reserve(std::max(n_, 1)); d_member_rank_.reserve(std::max(n_, 1));
     d_singles_.reserve(std::max(n_, 1)); d_blockcnt_.reserve((n_ + 1023) / 1024 + 1);
     uploaded_ = true;
@@ -406,17 +451,27 @@ cudaEvent_t Engine::next_event() {
     return ev_pool_[ev_used_++];
 }
 
-int Engine::qt_max() const {
+int Engine::qt_max(const HmkScheme& sc) const {
     if (opt.qt > 0) return (int)opt.qt;
-    const size_t pwb = (size_t)sc_.prof_words * 4;
+    const size_t pwb = (size_t)sc.prof_words * 4;
     const size_t per = pwb + (size_t)opt.kb * 8 + 8 + 12;
     const size_t fixed = 64 + (HMK_BULK_THREADS / 32) * HMK_QCAP * 8;
     return (int)std::min<size_t>(255, std::max<size_t>(1, (smem_optin_ - fixed) / per));
 }
 
-void Engine::launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof) {
+// scheme of a launch whose thread-side sequences all have length n
+HmkScheme Engine::scheme_for(int n) const {
+    HmkScheme sc = sc_;
+    sc.L = n;
+    if (mixed_) sc.nw = nw_len_[n];
+    sc.prof_words = sc.nw * HMK_MAXL1 * HMK_NRES;
+    return sc;
+}
+
+void Engine::launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof, const HmkScheme& sc, cudaStream_t s,
+                             uint32_t* cells, uint32_t* ops) {
     if (nq <= 0) return;
-    hmk_build_profiles<<<nq, 128, 0, st_>>>(sc_, mode, ids, nq, d_res_.p, d_off_.p, d_M_.p, prof);
+    hmk_build_profiles<<<nq, 128, 0, s>>>(sc, mode, ids, nq, d_res_.p, d_off_.p, d_M_.p, prof, cells, ops);
     CK(cudaGetLastError());
     launches_++;
 }
@@ -453,19 +508,14 @@ static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, 
     hmk_bulk_generic<MODE><<<grid, HMK_GENERIC_THREADS, smem, st>>>(g);
 }
 
-// fills in the tiling fields of `a` (nqt, qt, nstripes, chunk) and launches
-void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s, BatchBuf* bb) {
-    if (a.nq <= 0 || a.ndb <= 0) return;
-    if (!s) s = st_;
-    a.sc = sc_;
-    a.pair_counter = d_pairctr_.p;
-    a.kb = (int)opt.kb;
-    const int threads = fast_ ? HMK_BULK_THREADS : HMK_GENERIC_THREADS;
-    const int qmax = fast_ ? qt_max() : 128;
+// tiling of a bulk launch: nqt profile tiles x nstripes database stripes; the grid is an exact
+// multiple of the SM count whenever the database is large enough (one CTA per SM is resident:
+// the profile tile fills shared memory)
+void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch) const {
+    const int threads = sch ? HMK_BULK_THREADS : HMK_GENERIC_THREADS;
+    const int qmax = sch ? qt_max(*sch) : 128;
     a.nqt = (a.nq + qmax - 1) / qmax;
     a.qt = (a.nq + a.nqt - 1) / a.nqt;
-    // grid = nqt * nstripes: an exact multiple of the SM count whenever the database is large
-    // enough (one CTA per SM is resident: the profile tile fills shared memory)
     int want = (int)((sm_count_ * opt.waves + a.nqt - 1) / a.nqt);
     if (a.nqt <= sm_count_ * opt.waves && (sm_count_ * opt.waves) % a.nqt != 0) {
         // nqt does not divide waves*SMs: round the total up to the next multiple of the SM count
@@ -476,16 +526,20 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
     a.nstripes = std::max(1, std::min(want, max_stripes));
     a.chunk = (a.ndb + a.nstripes - 1) / a.nstripes;
     a.nstripes = (a.ndb + a.chunk - 1) / a.chunk;
-    if (mode == HMK_MODE_TOPK) {
-        const size_t slots = (size_t)a.nstripes * a.nq;
-        bb->tk_key.reserve(slots * a.kb); bb->tk_cnt.reserve(slots); bb->tk_ovf.reserve(slots);
-        a.tk_key = bb->tk_key.p; a.tk_cnt = bb->tk_cnt.p; a.tk_ovf = bb->tk_ovf.p;
-    }
+}
+
+// launches a planned bulk pass.  `sch` non-NULL: packed SWAR kernel with that scheme (a.prof holds
+// matching profiles); NULL: generic scalar kernel (prof_ids / prof_is_query name the profile side).
+void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const int32_t* prof_ids, int prof_is_query,
+                            cudaStream_t s) {
+    a.sc = sch ? *sch : sc_;
+    a.pair_counter = d_pairctr_.p;
+    a.kb = (int)opt.kb;
     const int grid = a.nqt * a.nstripes;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, s)); }
-    if (fast_) {
-        size_t smem = (((size_t)a.qt * sc_.prof_words * 4 + 15) & ~(size_t)15) + 16 +
+    if (sch) {
+        size_t smem = (((size_t)a.qt * sch->prof_words * 4 + 15) & ~(size_t)15) + 16 +
                       hmk_carve_bytes(a.qt, a.kb, HMK_BULK_THREADS, false);
         if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, s);
         else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, s);
@@ -504,8 +558,24 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
     if (opt.profile) { CK(cudaEventRecord(e1, s)); bulk_events_.push_back({e0, e1}); }
     launches_++;
     bulk_launches_++;
+}
+
+// one-launch convenience for everything that is not a (possibly multi-bucket) partner search:
+// the uniform packed kernel when the whole input has one length <= 12, else the generic kernel
+void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s, BatchBuf* bb) {
+    if (a.nq <= 0 || a.ndb <= 0) return;
+    if (!s) s = st_;
+    const HmkScheme* sch = fast_ ? &sc_ : nullptr;
+    plan_bulk(a, sch);
     if (mode == HMK_MODE_TOPK) {
-        hmk_topk_merge<<<(a.nq * 32 + 255) / 256, 256, 0, s>>>(a.nq, a.nstripes, a.kb, bb->tk_key.p, bb->tk_cnt.p,
+        const size_t slots = (size_t)a.nstripes * a.nq;
+        bb->tk_key.reserve(slots * opt.kb); bb->tk_cnt.reserve(slots); bb->tk_ovf.reserve(slots);
+        a.tk_key = bb->tk_key.p; a.tk_cnt = bb->tk_cnt.p; a.tk_ovf = bb->tk_ovf.p;
+        a.stripe_base = 0;
+    }
+    launch_planned(mode, a, sch, prof_ids, prof_is_query, s);
+    if (mode == HMK_MODE_TOPK) {
+        hmk_topk_merge<<<(a.nq * 32 + 255) / 256, 256, 0, s>>>(a.nq, a.nstripes, (int)opt.kb, bb->tk_key.p, bb->tk_cnt.p,
                                                                bb->tk_ovf.p, bb->bk_key.p, bb->bk_cnt.p, bb->bk_ovf.p);
         CK(cudaGetLastError());
         launches_++;
@@ -549,23 +619,63 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
     hmk_select_queries<<<1, 1024, 0, s>>>(d_slot_.p, n_, d_ctl_.p, start_after, nq, bb.qid.p, bb.nq_dev.p);
     CK(cudaGetLastError());
     launches_++;
-    if (fast_) {
-        hmk_build_profiles<<<nq, 128, 0, s>>>(sc_, HMK_PROF_QUERY, bb.qid.p, nq, d_res_.p, d_off_.p, d_M_.p, bb.prof.p);
-        CK(cudaGetLastError());
-        launches_++;
-    }
     HmkBulkArgs a{};
-    a.prof = bb.prof.p; a.nq = nq;
-    // this rank's stripe of the later singletons (the whole range on one GPU)
-    const int64_t span = (int64_t)n_ - db_from;
-    const int lo = db_from + (int)(span * rank_ / world_), hi = db_from + (int)(span * (rank_ + 1) / world_);
-    a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = lo; a.ndb = hi - lo;
-    a.slot = d_slot_.p; a.q_minid = bb.qid.p;
+    a.nq = nq;
+    a.packed = d_packed_.p; a.slot = d_slot_.p; a.q_minid = bb.qid.p;
     a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
-    if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, bb.qid.p, 1, s, &bb);
-    else {
-        CK(cudaMemsetAsync(bb.bk_cnt.p, 0, sizeof(int32_t) * nq, s));
-        CK(cudaMemsetAsync(bb.bk_ovf.p, 0, sizeof(int32_t) * nq, s));
+    if (!mixed_) {
+        if (fast_) launch_profiles(HMK_PROF_QUERY, bb.qid.p, nq, bb.prof.p, sc_, s);
+        a.prof = bb.prof.p;
+        // this rank's stripe of the later singletons (the whole range on one GPU)
+        const int64_t span = (int64_t)n_ - db_from;
+        const int lo = db_from + (int)(span * rank_ / world_), hi = db_from + (int)(span * (rank_ + 1) / world_);
+        a.db_ids = nullptr; a.db_begin = lo; a.ndb = hi - lo;
+        if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, bb.qid.p, 1, s, &bb);
+        else {
+            CK(cudaMemsetAsync(bb.bk_cnt.p, 0, sizeof(int32_t) * nq, s));
+            CK(cudaMemsetAsync(bb.bk_ovf.p, 0, sizeof(int32_t) * nq, s));
+        }
+    } else {
+        // mixed lengths: one packed-kernel launch per length bucket of the later singletons (profiles are
+        // built per thread-side length), all writing into one set of per-stripe lists merged once
+        struct Plan { int L; HmkBulkArgs a; HmkScheme sc; };
+        std::vector<Plan> plans;
+        int total_stripes = 0;
+        for (int L = 1; L <= HMK_MAXL1; L++) {
+            const auto& ids = h_bucket_[L];
+            if (ids.empty()) continue;
+            const int first = (int)(std::lower_bound(ids.begin(), ids.end(), db_from) - ids.begin());
+            const int64_t span = (int64_t)ids.size() - first;
+            const int lo = first + (int)(span * rank_ / world_), hi = first + (int)(span * (rank_ + 1) / world_);
+            if (hi <= lo) continue;
+            Plan p;
+            p.L = L; p.sc = scheme_for(L); p.a = a;
+            p.a.db_ids = d_bucket_[L].p + lo; p.a.db_begin = 0; p.a.ndb = hi - lo;
+            plan_bulk(p.a, &p.sc);
+            p.a.stripe_base = total_stripes;
+            total_stripes += p.a.nstripes;
+            plans.push_back(p);
+        }
+        if (plans.empty()) {
+            CK(cudaMemsetAsync(bb.bk_cnt.p, 0, sizeof(int32_t) * nq, s));
+            CK(cudaMemsetAsync(bb.bk_ovf.p, 0, sizeof(int32_t) * nq, s));
+        } else {
+            const size_t slots = (size_t)total_stripes * nq;
+            bb.tk_key.reserve(slots * kb); bb.tk_cnt.reserve(slots); bb.tk_ovf.reserve(slots);
+            for (auto& p : plans) {
+                auto& pf = bb.prof_len[p.L];
+                pf.reserve((size_t)HMK_MAXBATCH * p.sc.prof_words);
+                bb.pcells[p.L].reserve(HMK_MAXBATCH); bb.pops[p.L].reserve(HMK_MAXBATCH);
+                launch_profiles(HMK_PROF_QUERY, bb.qid.p, nq, pf.p, p.sc, s, bb.pcells[p.L].p, bb.pops[p.L].p);
+                p.a.prof = pf.p; p.a.prof_cells = bb.pcells[p.L].p; p.a.prof_ops = bb.pops[p.L].p;
+                p.a.tk_key = bb.tk_key.p; p.a.tk_cnt = bb.tk_cnt.p; p.a.tk_ovf = bb.tk_ovf.p;
+                launch_planned(HMK_MODE_TOPK, p.a, &p.sc, bb.qid.p, 1, s);
+            }
+            hmk_topk_merge<<<(nq * 32 + 255) / 256, 256, 0, s>>>(nq, total_stripes, kb, bb.tk_key.p, bb.tk_cnt.p, bb.tk_ovf.p,
+                                                                 bb.bk_key.p, bb.bk_cnt.p, bb.bk_ovf.p);
+            CK(cudaGetLastError());
+            launches_++;
+        }
     }
     if (world_ > 1) {
         // best-hit exchange: every rank contributes its stripe's top-k per query (a few KB),
@@ -632,7 +742,7 @@ int Engine::phase1() {
             launch_bulk(HMK_MODE_EMIT, a, d_qid, 1);
             HmkCheckArgs c{};
             c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
-            c.hit_t_is_query = 1; c.qids = d_qid;
+            c.hit_t_is_query = 1; c.qids = d_qid; c.sidx = nullptr;
             c.ac_cnt = d_ac_cnt_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p; c.capq = (int32_t)capq;
             c.cand_count = d_counts_.p + 1; c.cand_cap = 0; c.linked = 1;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
@@ -726,11 +836,8 @@ void Engine::phase2() {
     const int ns = compact_unassigned(d_singles_.p);
     stats.p2_queries = ns;
     if (ncl == 0 || ns == 0) { sec(-1); return; }
-    // founder profiles (member side), built once: founders are fixed during phase 2
-    if (fast_) {
-        d_fprof_.reserve((size_t)ncl * sc_.prof_words);
-        launch_profiles(HMK_PROF_MEMBER, d_cf_.p, ncl, d_fprof_.p);
-    }
+    hmk_index_of<<<(ns + 255) / 256, 256, 0, st_>>>(d_singles_.p, ns, d_sidx_.p);   // sequence id -> query index
+    launches_++;
     size_t hit_cap = d_hits_.cap ? d_hits_.cap : (size_t)opt.hit_cap;
     d_hits_.reserve(hit_cap);
     size_t cand_cap = std::max<size_t>(1 << 20, (size_t)ns / 2);
@@ -741,47 +848,78 @@ void Engine::phase2() {
     const int chunk = (int)std::max<int64_t>(1024, opt.p2_chunk);
     // this rank's share of the phase-2 queries (all of them on one GPU)
     const int my_lo = (int)((int64_t)ns * rank_ / world_), my_hi = (int)((int64_t)ns * (rank_ + 1) / world_);
-    for (int c0 = my_lo; c0 < my_hi;) {
-        const int cn = std::min(chunk, my_hi - c0);
-        sec(SEC_P2_FILTER);
-        CK(cudaMemsetAsync(d_counts_.p, 0, sizeof(unsigned int), st_));
-        HmkBulkArgs a{};
-        a.prof = d_fprof_.p; a.nq = ncl;
-        a.packed = d_packed_.p; a.db_ids = d_singles_.p + c0; a.db_begin = 0; a.ndb = cn;
-        a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
-        launch_bulk(HMK_MODE_EMIT, a, d_cf_.p, 0);
-        sec(SEC_P2_CHECK);
-        CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
-        CK(cudaStreamSynchronize(st_));
-        const size_t nh = (uint32_t)h_scalars_[0];
-        if (nh > hit_cap) {   // redo this chunk with a bigger buffer
-            hit_cap = nh * 5 / 4 + 1024;
-            d_hits_.reserve(hit_cap);
-            continue;
-        }
-        stats.p2_hits += (int64_t)nh;
-        if (nh) {
-            if (ncand + nh > cand_cap) {
-                size_t nc = std::max(cand_cap * 2, ncand + nh);
-                d_key_q_.grow_keep(nc, ncand, st_); d_key_c_.grow_keep(nc, ncand, st_); d_cand_score_.grow_keep(nc, ncand, st_);
-                cand_cap = nc;
-            }
-            HmkCheckArgs c{};
-            c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
-            c.hit_t_is_query = 0; c.qids = d_singles_.p + c0;
-            // candidate keys carry the GLOBAL query index: offset added below
-            c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
-            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
-            c.q_index_offset = c0;
-            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
-            hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
-            CK(cudaGetLastError());
-            launches_++;
-            CK(cudaMemcpyAsync(h_scalars_ + 1, d_counts_.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+
+    // founder filter + member check for one list of queries (`sch` NULL: generic kernel)
+    auto run_list = [&](const int32_t* ids, int count, const HmkScheme* sch) {
+        for (int c0 = 0; c0 < count;) {
+            const int cn = std::min(chunk, count - c0);
+            sec(SEC_P2_FILTER);
+            CK(cudaMemsetAsync(d_counts_.p, 0, sizeof(unsigned int), st_));
+            HmkBulkArgs a{};
+            a.prof = d_fprof_.p; a.nq = ncl;
+            a.packed = d_packed_.p; a.db_ids = ids + c0; a.db_begin = 0; a.ndb = cn;
+            a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
+            if (sch && mixed_) { a.prof_cells = d_pcells_.p; a.prof_ops = d_pops_.p; }
+            plan_bulk(a, sch);
+            launch_planned(HMK_MODE_EMIT, a, sch, d_cf_.p, 0, st_);
+            sec(SEC_P2_CHECK);
+            CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
             CK(cudaStreamSynchronize(st_));
-            ncand = (uint32_t)h_scalars_[1];
+            const size_t nh = (uint32_t)h_scalars_[0];
+            if (nh > hit_cap) {   // redo this chunk with a bigger buffer
+                hit_cap = nh * 5 / 4 + 1024;
+                d_hits_.reserve(hit_cap);
+                continue;
+            }
+            stats.p2_hits += (int64_t)nh;
+            if (nh) {
+                if (ncand + nh > cand_cap) {
+                    size_t nc = std::max(cand_cap * 2, ncand + nh);
+                    d_key_q_.grow_keep(nc, ncand, st_); d_key_c_.grow_keep(nc, ncand, st_); d_cand_score_.grow_keep(nc, ncand, st_);
+                    cand_cap = nc;
+                }
+                HmkCheckArgs c{};
+                c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
+                c.hit_t_is_query = 0; c.qids = nullptr; c.sidx = d_sidx_.p;
+                c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
+                c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
+                c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
+                hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
+                CK(cudaGetLastError());
+                launches_++;
+                CK(cudaMemcpyAsync(h_scalars_ + 1, d_counts_.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+                CK(cudaStreamSynchronize(st_));
+                ncand = (uint32_t)h_scalars_[1];
+            }
+            c0 += cn;
         }
-        c0 += cn;
+    };
+
+    if (!mixed_) {
+        // founder profiles (member side), built once: founders are fixed during phase 2
+        if (fast_) {
+            d_fprof_.reserve((size_t)ncl * sc_.prof_words);
+            launch_profiles(HMK_PROF_MEMBER, d_cf_.p, ncl, d_fprof_.p, sc_, st_);
+        }
+        run_list(d_singles_.p + my_lo, my_hi - my_lo, fast_ ? &sc_ : nullptr);
+    } else if (my_hi > my_lo) {
+        // mixed lengths: split this rank's queries by length; per length, founder profiles for that
+        // thread-side length and one packed-kernel pass
+        const int my_n = my_hi - my_lo;
+        d_sb_ids_.reserve((size_t)(HMK_MAXL1 + 1) * my_n); d_sb_cnt_.reserve(HMK_MAXL1 + 1);
+        CK(cudaMemsetAsync(d_sb_cnt_.p, 0, sizeof(int32_t) * (HMK_MAXL1 + 1), st_));
+        hmk_bucket_by_length<<<(my_n + 255) / 256, 256, 0, st_>>>(d_singles_.p + my_lo, my_n, d_off_.p, my_n, d_sb_ids_.p, d_sb_cnt_.p);
+        launches_++;
+        int32_t cnt[HMK_MAXL1 + 1];
+        CK(cudaMemcpyAsync(cnt, d_sb_cnt_.p, sizeof(cnt), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        for (int L = 1; L <= HMK_MAXL1; L++) {
+            if (cnt[L] <= 0) continue;
+            const HmkScheme sch = scheme_for(L);
+            d_fprof_.reserve((size_t)ncl * sch.prof_words);
+            launch_profiles(HMK_PROF_MEMBER, d_cf_.p, ncl, d_fprof_.p, sch, st_, d_pcells_.p, d_pops_.p);
+            run_list(d_sb_ids_.p + (size_t)L * my_n, cnt[L], &sch);
+        }
     }
     if (world_ > 1) {
         // candidate exchange: all-gather the per-rank candidate lists (padded to the longest; the
@@ -918,8 +1056,8 @@ int Engine::run() {
     for (double& v : section_ms) v = 0;
     ran_ = false;
     if (bad_residue_) return HMK_ERR_BAD_RESIDUE;
-    stats.fast_path = fast_ ? 1 : 0;
-    stats.lane_bits = fast_ ? (sc_.lane16 ? 16 : 8) : 32;
+    stats.fast_path = fast_ ? 1 : (mixed_ ? 2 : 0);     // 2: packed kernel per length bucket (mixed lengths)
+    stats.lane_bits = (fast_ || mixed_) ? (sc_.lane16 ? 16 : 8) : 32;
     CK(cudaEventRecord(ev_a_, st_));
     if (n_) {
         hmk_fill_i32<<<sm_count_ * 2, 256, 0, st_>>>(d_slot_.p, -1, (size_t)n_);
@@ -931,7 +1069,7 @@ int Engine::run() {
     c0.cur = 0; c0.ncl = 0; c0.unproc_alive = n_; c0.status = HMK_P1_CONTINUE; c0.npe_step = -1;
     *h_ctl_ = c0;
     CK(cudaMemcpyAsync(d_ctl_.p, h_ctl_, sizeof(HmkCtl), cudaMemcpyHostToDevice, st_));
-    CK(cudaMemsetAsync(d_pairctr_.p, 0, 2 * sizeof(unsigned long long), st_));
+    CK(cudaMemsetAsync(d_pairctr_.p, 0, 4 * sizeof(unsigned long long), st_));
     // DataException "Shift too big" (ShiftedScorer.java:59-62): thrown by the first pair score
     // touching a sequence not longer than maxShift; step 0 of phase 1 scores every sequence.
     if (K_ > 0 && n_ >= 2 && X_ >= min_len_) return HMK_ERR_SHIFT_TOO_BIG;
@@ -948,7 +1086,7 @@ int Engine::run() {
     }
     CK(cudaEventRecord(ev_c_, st_));
     fetch_ctl();
-    unsigned long long pc[2] = {0, 0};
+    unsigned long long pc[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(pc, d_pairctr_.p, sizeof(pc), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
     float ms1 = 0, ms2 = 0;
@@ -975,6 +1113,9 @@ int Engine::run() {
     if (min_len_ == max_len_) {
         stats.bulk_cells = stats.bulk_pairs * hmk_pair_cells(max_len_, max_len_, X_);
         stats.bulk_ops = stats.bulk_cells + stats.bulk_pairs * (2 * (int64_t)X_ + 1);
+    } else if (mixed_) {   // counted by the packed-kernel launches (the small generic launches are not included)
+        stats.bulk_cells = (int64_t)pc[1];
+        stats.bulk_ops = (int64_t)pc[2];
     }
     stats.bulk_launches = bulk_launches_; stats.total_launches = launches_;
     stats.p1_steps = h_ctl_->steps; stats.p1_joins = h_ctl_->joins; stats.p1_new_clusters = h_ctl_->creates;
@@ -1017,7 +1158,7 @@ void Engine::score_block(const int32_t* first, int32_t nf, const int32_t* second
     for (int s0 = 0; s0 < ns; s0 += chunk) {
         const int sn = std::min(chunk, ns - s0);
         CK(cudaMemcpyAsync(d_second.p, second + s0, sizeof(int32_t) * sn, cudaMemcpyHostToDevice, st_));
-        if (fast_) launch_profiles(HMK_PROF_QUERY, d_second.p, sn, d_prof.p);
+        if (fast_) launch_profiles(HMK_PROF_QUERY, d_second.p, sn, d_prof.p, sc_, st_);
         HmkBulkArgs a{};
         a.prof = d_prof.p; a.nq = sn;
         a.packed = d_packed_.p; a.db_ids = d_first.p; a.db_begin = 0; a.ndb = nf;

@@ -43,39 +43,58 @@ struct HmkScheme {
 };
 
 // ---------------------------------------------------------------- profile builder
-// prof[t][h][j][r] with j < HMK_MAXL1 (rows j >= L are zero); mode QUERY: profile sequence is the reference's seq2 (compared/query,
-// the "shorter" one for equal lengths), threads will carry seq1 (member/candidate):
-//   lane k gets M[p[j-k]][r];   mode MEMBER: profile sequence is seq1 (member), threads carry
-// seq2 (query): lane k gets M[r][p[j+k]]   (M[shorter][longer], ShiftedScorer.java:71,75,110)
+// prof[t][h][j][r] with j < HMK_MAXL1 (rows j >= n are zero), for THREAD-side sequences of length
+// n = sc.L and a profile sequence p of length m (read per profile, so batches may mix lengths).
+// Reference roles (ShiftedScorer.java:51-57): the shorter sequence is "s", the longer "l", equal
+// lengths make seq2 the shorter one; d = |n - m|; shifts k = -X .. X+d; matrix index
+// M[shorter][longer] (:71,75,110).
+//   mode QUERY : profile = seq2 (compared sequence), threads carry seq1 (member / candidate)
+//   mode MEMBER: profile = seq1 (member),            threads carry seq2 (query)
+// profile is the shorter one ("ps") iff m <= n (QUERY) resp. m < n (MEMBER):
+//   ps : thread position j is l[j]   -> lane k gets M[p[j-k]][r], valid 0 <= j-k < m
+//   !ps: thread position i is s[i]   -> lane k gets M[r][p[i+k]], valid 0 <= i+k < m
+// Lane k's constant (added at position 0): penalties + (half - T) - cells_k * bias, so that
+// lane value >= half  <=>  score_k >= T.
 __global__ void hmk_build_profiles(HmkScheme sc, int mode, const int32_t* __restrict__ ids, int nq,
                                    const uint8_t* __restrict__ res, const int32_t* __restrict__ off,
-                                   const int32_t* __restrict__ M, uint32_t* __restrict__ prof) {
+                                   const int32_t* __restrict__ M, uint32_t* __restrict__ prof,
+                                   uint32_t* __restrict__ prof_cells, uint32_t* __restrict__ prof_ops) {
     __shared__ int32_t sM[HMK_NRES * HMK_NRES];
     __shared__ uint8_t sp[HMK_MAXL1];
     const int t = blockIdx.x;
     if (t >= nq) return;
     for (int i = threadIdx.x; i < HMK_NRES * HMK_NRES; i += blockDim.x) sM[i] = M[i];
     const int32_t id = ids[t];
-    if (threadIdx.x < sc.L) sp[threadIdx.x] = res[off[id] + threadIdx.x];
+    const int m = off[id + 1] - off[id], n = sc.L;
+    if (threadIdx.x < m && threadIdx.x < HMK_MAXL1) sp[threadIdx.x] = res[off[id] + threadIdx.x];
     __syncthreads();
-    const int L = sc.L, lanes_per_word = sc.lane16 ? 2 : 4, lane_bits = sc.lane16 ? 16 : 8;
+    const bool ps = mode == HMK_PROF_QUERY ? (m <= n) : (m < n);
+    const int ls = m < n ? m : n, ll = m < n ? n : m, d = ll - ls;
+    const int lanes_per_word = sc.lane16 ? 2 : 4, lane_bits = sc.lane16 ? 16 : 8;
     uint32_t* out = prof + (size_t)t * sc.prof_words;
     for (int e = threadIdx.x; e < sc.prof_words; e += blockDim.x) {
         const int r = e % HMK_NRES, j = (e / HMK_NRES) % HMK_MAXL1, h = e / (HMK_NRES * HMK_MAXL1);
         uint32_t word = 0;
-        if (j >= L) { out[e] = 0; continue; }
+        if (j >= n) { out[e] = 0; continue; }
         for (int b = 0; b < lanes_per_word; b++) {
             const int lam = h * lanes_per_word + b;
-            if (lam > 2 * sc.X) continue;
-            const int k = lam - sc.X, ak = k < 0 ? -k : k;
+            if (lam > 2 * sc.X + d) continue;
+            const int k = lam - sc.X;
             int32_t val = 0;
-            const int pi = mode == HMK_PROF_QUERY ? j - k : j + k;
-            if (pi >= 0 && pi < L)
-                val = (mode == HMK_PROF_QUERY ? sM[sp[pi] * HMK_NRES + r] : sM[r * HMK_NRES + sp[pi]]) + sc.bias;
-            if (j == 0) val += 2 * sc.P * ak + sc.half - sc.T - (L - ak) * sc.bias;   // lane constant
+            const int pi = ps ? j - k : j + k;
+            if (pi >= 0 && pi < m) val = (ps ? sM[sp[pi] * HMK_NRES + r] : sM[r * HMK_NRES + sp[pi]]) + sc.bias;
+            if (j == 0) {
+                const int cells = (ls + k < ll ? ls + k : ll) - (k > 0 ? k : 0);
+                const int pen = d * sc.P + (k < 0 ? -2 * k * sc.P : 0) + (k > d ? 2 * (k - d) * sc.P : 0);
+                val += pen + sc.half - sc.T - cells * sc.bias;
+            }
             word |= ((uint32_t)val & ((1u << lane_bits) - 1u)) << (b * lane_bits);
         }
         out[e] = word;
+    }
+    if (threadIdx.x == 0 && prof_cells) {   // work accounting: cells and cells + shifts of one pair
+        prof_cells[t] = (uint32_t)hmk_pair_cells(m, n, sc.X);
+        prof_ops[t] = prof_cells[t] + (uint32_t)(2 * sc.X + d + 1);
     }
 }
 
@@ -121,6 +140,7 @@ struct HmkBulkArgs {
     const int32_t* db_ids;     // NULL: id = db_begin + i
     int32_t db_begin, ndb;
     int32_t nstripes, chunk;   // items per stripe
+    int32_t stripe_base;       // first slot of this launch in tk_* (several launches, e.g. one per length, share a merge)
     const int32_t* slot;       // non-NULL: skip items whose slot >= 0 (no longer singletons)
     const int32_t* q_minid;    // non-NULL: only ids > q_minid[t] qualify (initialList[index+1..])
     const int32_t* tierank;    // NULL: tierank == id
@@ -130,13 +150,15 @@ struct HmkBulkArgs {
     int32_t* tk_cnt;           // [nstripes][nq]
     int32_t* tk_ovf;           // [nstripes][nq]
     // MODE_EMIT
-    int4* hits;                // (t, i, score, 0)
+    int4* hits;                // (profile index, thread-side sequence id, score, 0)
     unsigned int* hit_count;
     unsigned int hit_cap;
     // MODE_DENSE
     int32_t* dense;            // dense[t * dense_stride + i]
     int32_t dense_stride;
-    unsigned long long* pair_counter;
+    unsigned long long* pair_counter;   // [0] pairs, [1] cells, [2] int ops (the last two only with prof_cells)
+    const uint32_t* prof_cells;         // per profile: cells of one pair against this launch's thread-side length
+    const uint32_t* prof_ops;
 };
 
 // ---------------------------------------------------------------- hit handling
@@ -211,7 +233,9 @@ __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopk
             const uint64_t v = hq.q[e];
             const unsigned int pos = base + e;
             const int32_t sc = hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32);
-            if (pos < a.hit_cap) a.hits[pos] = make_int4(q0 + (int)(v >> 48), (int32_t)(uint32_t)v, sc, 0);
+            const int32_t i = (int32_t)(uint32_t)v;
+            const int32_t id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
+            if (pos < a.hit_cap) a.hits[pos] = make_int4(q0 + (int)(v >> 48), id, sc, 0);
         }
     } else if (MODE == HMK_MODE_TOPK) {
         for (int e0 = 0; e0 < n; e0 += 32) {
@@ -294,7 +318,7 @@ __device__ __forceinline__ void hmk_topk_flush(const HmkBulkArgs& a, const HmkTo
             while (j >= 0 && k[j] < v) { k[j + 1] = k[j]; j--; }
             k[j + 1] = v;
         }
-        size_t o = (size_t)stripe * a.nq + q0 + t;
+        size_t o = (size_t)(a.stripe_base + stripe) * a.nq + q0 + t;
         for (int i = 0; i < c; i++) a.tk_key[o * a.kb + i] = k[i];
         a.tk_cnt[o] = c;
         a.tk_ovf[o] = tk.ovf[t];
@@ -423,7 +447,15 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __gri
     if (MODE != HMK_MODE_DENSE && hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
     if (a.pair_counter) {
         for (int s = 16; s > 0; s >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, s);
-        if ((threadIdx.x & 31) == 0 && scored) atomicAdd(a.pair_counter, scored);
+        if ((threadIdx.x & 31) == 0 && scored) {
+            atomicAdd(a.pair_counter, scored);
+            if (a.prof_cells) {   // mixed lengths: cells differ per profile; items of this launch share one length
+                unsigned long long tc = 0, to = 0;
+                for (int t = 0; t < qn; t++) { tc += a.prof_cells[q0 + t]; to += a.prof_ops[q0 + t]; }
+                atomicAdd(a.pair_counter + 1, scored / qn * tc);
+                atomicAdd(a.pair_counter + 2, scored / qn * to);
+            }
+        }
     }
     if (MODE == HMK_MODE_TOPK) {
         __syncthreads();
@@ -611,8 +643,9 @@ struct HmkCheckArgs {
     const int4* hits;
     const unsigned int* hit_count;
     unsigned int hit_cap;
-    int32_t hit_t_is_query;      // 1: hit.x = query index, hit.y = cluster slot; 0: the reverse
-    const int32_t* qids;         // query index -> sequence id
+    int32_t hit_t_is_query;      // 1: hit.x = query index, hit.y = founder's id; 0: hit.x = cluster slot, hit.y = query's id
+    const int32_t* qids;         // phase 1: query index -> sequence id
+    const int32_t* sidx;         // phase 2: sequence id -> index in the singles list
     // phase 1 output: per-query arrays ac_slot/ac_score[qi * capq + k], k < ac_cnt[qi]
     int32_t* ac_cnt; int32_t* ac_slot; int32_t* ac_score; int32_t capq;
     // phase 2 output: flat candidate arrays
@@ -622,7 +655,6 @@ struct HmkCheckArgs {
     unsigned int* cand_count;
     unsigned int cand_cap;
     int32_t linked;
-    int32_t q_index_offset;      // added to the query index in the flat candidate keys
     const uint64_t* packed;      // non-NULL: uniform length <= 12, use the packed scalar scorer
     int32_t L;
 };
@@ -636,8 +668,10 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
     long long npairs = 0;
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < nh; e += gridDim.x * blockDim.x) {
         const int4 h = a.hits[e];
-        const int qi = a.hit_t_is_query ? h.x : h.y, c = a.hit_t_is_query ? h.y : h.x;
-        const int32_t q = a.qids[qi];
+        // phase 1: (query index, founder's sequence id); phase 2: (founder = cluster slot, query's sequence id)
+        const int qi = a.hit_t_is_query ? h.x : a.sidx[h.y];
+        const int c = a.hit_t_is_query ? a.S.slot[h.y] : h.x;
+        const int32_t q = a.hit_t_is_query ? a.qids[qi] : h.y;
         int32_t cl = h.z;
         bool ok = true;
         for (int32_t m = a.S.next[a.S.c_founder[c]]; m >= 0; m = a.S.next[m]) {
@@ -658,7 +692,7 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         unsigned int pos = atomicAdd(a.cand_count, 1u);
         if (pos >= a.cand_cap) continue;
         {
-            const uint32_t gq = (uint32_t)(qi + a.q_index_offset);
+            const uint32_t gq = (uint32_t)qi;
             a.cand_key_q[pos] = ((unsigned long long)gq << 32) | (uint32_t)c;
             a.cand_key_c[pos] = ((unsigned long long)(uint32_t)c << 32) | gq;
             a.cand_score[pos] = cl;
@@ -1377,6 +1411,23 @@ __global__ void hmk_scatter_unassigned(const int32_t* __restrict__ slot, int n, 
     int pre = 0;
     for (int w = 0; w < wid; w++) pre += wsum[w];
     if (f) out[block_off[blockIdx.x] + pre + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+__global__ void hmk_index_of(const int32_t* __restrict__ list, int n, int32_t* __restrict__ index_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) index_of[list[i]] = i;
+}
+
+// split an id list by sequence length: out[len * stride + k], k < count[len] (order inside a bucket is arbitrary)
+__global__ void hmk_bucket_by_length(const int32_t* __restrict__ ids, int n, const int32_t* __restrict__ off, int stride,
+                                     int32_t* __restrict__ out, int32_t* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t id = ids[i];
+    const int len = off[id + 1] - off[id];
+    if (len > HMK_MAXL1) return;
+    const int k = atomicAdd(count + len, 1);
+    out[(size_t)len * stride + k] = id;
 }
 
 // first index whose key's high half is >= s, for s = 0..nseg (start[nseg] = n)

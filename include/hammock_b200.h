@@ -75,7 +75,7 @@ typedef struct {
     int32_t p1_steps, p1_joins, p1_new_clusters, p1_orphans, p1_batches, p1_restarts;
     int32_t p2_queries, p2_assigned, p2_rounds;
     int64_t p2_hits, p2_candidates;
-    int32_t fast_path;        /* 1: packed SWAR kernel, 0: generic scalar kernel                      */
+    int32_t fast_path;        /* 0: generic scalar kernel, 1: packed SWAR kernel (one length), 2: packed per length bucket */
     int32_t lane_bits;        /* 8 or 16 on the fast path                                             */
     int32_t error_step;       /* phase-1 step of HMK_STATUS_NULL_CLUSTER in the last run, else -1     */
     int32_t pad_;
