@@ -214,10 +214,11 @@ private:
     int32_t min_len_ = 0, max_len_ = 0;
     bool uploaded_ = false, ran_ = false, bad_residue_ = false;
     bool fast_ = false;
-    bool mixed_ = false;         // lengths differ but all <= 12 and every (m, n) pair fits the packed lanes
-    int nw_len_[HMK_MAXL1 + 1] = {0};
-    std::vector<int32_t> h_bucket_[HMK_MAXL1 + 1];   // ids per length, ascending
-    DevBuf<int32_t> d_bucket_[HMK_MAXL1 + 1];
+    bool mixed_ = false;         // lengths differ but every (m, n) pair fits the packed lanes
+    int words_ = 1;              // 64-bit words per packed sequence
+    int nw_len_[HMK_MAXLEN + 1] = {0};
+    std::vector<int32_t> h_bucket_[HMK_MAXLEN + 1];   // ids per length, ascending
+    DevBuf<int32_t> d_bucket_[HMK_MAXLEN + 1];
     DevBuf<int32_t> d_sidx_, d_sb_ids_, d_sb_cnt_;
     DevBuf<uint32_t> d_pcells_, d_pops_;
     bool fast_scalar_ = false;   // uniform length <= 12: packed scalar scorer usable
@@ -238,7 +239,7 @@ private:
         DevBuf<int32_t> qid, nq_dev, tk_cnt, tk_ovf, bk_cnt, bk_ovf, gk_cnt, gk_ovf;
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
         DevBuf<uint32_t> prof;
-        DevBuf<uint32_t> prof_len[HMK_MAXL1 + 1], pcells[HMK_MAXL1 + 1], pops[HMK_MAXL1 + 1];   // mixed lengths: per thread-side length
+        DevBuf<uint32_t> prof_len[HMK_MAXLEN + 1], pcells[HMK_MAXLEN + 1], pops[HMK_MAXLEN + 1];   // mixed lengths: per thread-side length
         cudaEvent_t ready = nullptr;
         bool valid = false;      // partner search for the batch starting behind `after` has been issued
         int nq = 0;
@@ -327,12 +328,14 @@ void Engine::choose_scheme(const int32_t* M) {
     sc_ = HmkScheme{};
     sc_.L = max_len_; sc_.X = X_; sc_.P = P_; sc_.T = T_;
     if (opt.force_generic) return;
-    if (n_ <= 0 || min_len_ < 1 || max_len_ > HMK_MAXL1) return;
+    if (n_ <= 0 || min_len_ < 1 || max_len_ > HMK_MAXLEN) return;
+    const bool lng = max_len_ > HMK_MAXL1;       // more than one packed word: hmk_bulk_long
+    const int nwcap = lng ? HMK_NWMAX : 4;
     if (X_ < 0 || X_ >= min_len_) return;
     int64_t mmin = M[0], mmax = M[0];
     for (int i = 0; i < HMK_NRES * HMK_NRES; i++) { mmin = std::min<int64_t>(mmin, M[i]); mmax = std::max<int64_t>(mmax, M[i]); }
     const int64_t bias = mmin < 0 ? -mmin : 0;
-    bool present[HMK_MAXL1 + 1] = {false};
+    bool present[HMK_MAXLEN + 1] = {false};
     for (int i = 0; i < n_; i++) present[h_off_[i + 1] - h_off_[i]] = true;
     // every pair of lengths (m, n) that occurs must fit the packed lanes: 2X+1+|n-m| lanes, and for each
     // shift k the lane value stays inside [0, top] with "score >= T" at the lane's top bit
@@ -340,15 +343,15 @@ void Engine::choose_scheme(const int32_t* M) {
         const int64_t half = lane16 ? 32768 : 128, top = lane16 ? 65535 : 255;
         const int lpw = lane16 ? 2 : 4;
         bool ok = true;
-        int nw[HMK_MAXL1 + 1] = {0};
-        for (int n = 1; n <= HMK_MAXL1 && ok; n++) {
+        int nw[HMK_MAXLEN + 1] = {0};
+        for (int n = 1; n <= HMK_MAXLEN && ok; n++) {
             if (!present[n]) continue;
-            for (int m = 1; m <= HMK_MAXL1 && ok; m++) {
+            for (int m = 1; m <= HMK_MAXLEN && ok; m++) {
                 if (!present[m]) continue;
                 const int ls = std::min(m, n), ll = std::max(m, n), d = ll - ls;
                 const int lanes = 2 * X_ + 1 + d;
                 nw[n] = std::max(nw[n], (lanes + lpw - 1) / lpw);
-                if (nw[n] > 4) { ok = false; break; }
+                if (nw[n] > nwcap) { ok = false; break; }
                 for (int k = -X_; k <= X_ + d && ok; k++) {
                     const int64_t cells = std::min(ls + k, ll) - std::max(k, 0);
                     const int64_t pen = (int64_t)d * P_ + (k < 0 ? -2LL * k * P_ : 0) + (k > d ? 2LL * (k - d) * P_ : 0);
@@ -360,15 +363,16 @@ void Engine::choose_scheme(const int32_t* M) {
         }
         if (!ok) continue;
         sc_.lane16 = lane16; sc_.bias = (int32_t)bias; sc_.half = (int32_t)half;
+        sc_.words = words_; sc_.long_layout = lng ? 1 : 0;
         if (min_len_ == max_len_) {
             fast_ = true;
             sc_.nw = nw[max_len_];
         } else {
             mixed_ = true;
             sc_.nw = 0;
-            for (int n = 0; n <= HMK_MAXL1; n++) { nw_len_[n] = nw[n]; sc_.nw = std::max(sc_.nw, nw[n]); }
+            for (int n = 0; n <= HMK_MAXLEN; n++) { nw_len_[n] = nw[n]; sc_.nw = std::max(sc_.nw, nw[n]); }
         }
-        sc_.prof_words = sc_.nw * HMK_MAXL1 * HMK_NRES;
+        sc_.prof_words = sc_.nw * (lng ? max_len_ : HMK_MAXL1) * HMK_NRES;
         return;
     }
 }
@@ -407,11 +411,12 @@ void Engine::upload(const hmk_greedy_in* in) {
         CK(cudaMemcpyAsync(d_id_of_rank_.p, ids.data(), sizeof(int32_t) * n_, cudaMemcpyHostToDevice, st_));
         CK(cudaStreamSynchronize(st_));
     }
+    words_ = max_len_ <= HMK_MAXLEN ? std::max(1, (max_len_ + HMK_MAXL1 - 1) / HMK_MAXL1) : 1;
     choose_scheme(in->matrix);
     for (auto& v : h_bucket_) v.clear();
     if (mixed_) {
         for (int i = 0; i < n_; i++) h_bucket_[h_off_[i + 1] - h_off_[i]].push_back(i);
-        for (int L = 1; L <= HMK_MAXL1; L++) {
+        for (int L = 1; L <= HMK_MAXLEN; L++) {
             if (h_bucket_[L].empty()) continue;
             d_bucket_[L].reserve(h_bucket_[L].size());
             CK(cudaMemcpyAsync(d_bucket_[L].p, h_bucket_[L].data(), sizeof(int32_t) * h_bucket_[L].size(), cudaMemcpyHostToDevice, st_));
@@ -420,11 +425,12 @@ void Engine::upload(const hmk_greedy_in* in) {
     }
     fast_scalar_ = n_ > 0 && min_len_ == max_len_ && max_len_ >= 1 && max_len_ <= HMK_MAXL1 && X_ >= 0 && X_ < max_len_;
     // validate residues + pack 5 bits/residue on the device
-    d_packed_.reserve(std::max(n_, 1));
+    words_ = max_len_ <= HMK_MAXLEN ? std::max(1, (max_len_ + HMK_MAXL1 - 1) / HMK_MAXL1) : 1;
+    d_packed_.reserve((size_t)std::max(n_, 1) * words_);
     d_flags_.reserve(8);
     CK(cudaMemsetAsync(d_flags_.p, 0, 8 * sizeof(int32_t), st_));
     if (n_) {
-        hmk_pack_sequences<<<(n_ + 255) / 256, 256, 0, st_>>>(n_, d_res_.p, d_off_.p, d_packed_.p, d_flags_.p);
+        hmk_pack_sequences<<<(n_ + 255) / 256, 256, 0, st_>>>(n_, words_, d_res_.p, d_off_.p, d_packed_.p, d_flags_.p);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(h_scalars_, d_flags_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
@@ -464,7 +470,7 @@ HmkScheme Engine::scheme_for(int n) const {
     HmkScheme sc = sc_;
     sc.L = n;
     if (mixed_) sc.nw = nw_len_[n];
-    sc.prof_words = sc.nw * HMK_MAXL1 * HMK_NRES;
+    sc.prof_words = sc.nw * (sc.long_layout ? n : HMK_MAXL1) * HMK_NRES;
     return sc;
 }
 
@@ -489,7 +495,18 @@ static void launch_fast_inst(const HmkBulkArgs& a, int grid, size_t smem, cudaSt
 }
 
 template <int MODE>
+static void launch_long_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    static size_t configured_smem = 0;
+    if (smem > configured_smem) {
+        CK(cudaFuncSetAttribute(hmk_bulk_long<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_smem = smem;
+    }
+    hmk_bulk_long<MODE><<<grid, HMK_LONG_THREADS, smem, st>>>(a);
+}
+
+template <int MODE>
 static void launch_fast_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    if (a.sc.long_layout) { launch_long_mode<MODE>(a, grid, smem, st); return; }
     switch (a.sc.nw) {
         case 1: launch_fast_inst<1, MODE>(a, grid, smem, st); break;
         case 2: launch_fast_inst<2, MODE>(a, grid, smem, st); break;
@@ -512,7 +529,7 @@ static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, 
 // multiple of the SM count whenever the database is large enough (one CTA per SM is resident:
 // the profile tile fills shared memory)
 void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch) const {
-    const int threads = sch ? HMK_BULK_THREADS : HMK_GENERIC_THREADS;
+    const int threads = sch ? (sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS) : HMK_GENERIC_THREADS;
     const int qmax = sch ? qt_max(*sch) : 128;
     a.nqt = (a.nq + qmax - 1) / qmax;
     a.qt = (a.nq + a.nqt - 1) / a.nqt;
@@ -540,7 +557,7 @@ void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const
     if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, s)); }
     if (sch) {
         size_t smem = (((size_t)a.qt * sch->prof_words * 4 + 15) & ~(size_t)15) + 16 +
-                      hmk_carve_bytes(a.qt, a.kb, HMK_BULK_THREADS, false);
+                      hmk_carve_bytes(a.qt, a.kb, sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS, false);
         if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, s);
         else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, s);
         else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, s);
@@ -641,7 +658,7 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         struct Plan { int L; HmkBulkArgs a; HmkScheme sc; };
         std::vector<Plan> plans;
         int total_stripes = 0;
-        for (int L = 1; L <= HMK_MAXL1; L++) {
+        for (int L = 1; L <= HMK_MAXLEN; L++) {
             const auto& ids = h_bucket_[L];
             if (ids.empty()) continue;
             const int first = (int)(std::lower_bound(ids.begin(), ids.end(), db_from) - ids.begin());
@@ -906,14 +923,14 @@ void Engine::phase2() {
         // mixed lengths: split this rank's queries by length; per length, founder profiles for that
         // thread-side length and one packed-kernel pass
         const int my_n = my_hi - my_lo;
-        d_sb_ids_.reserve((size_t)(HMK_MAXL1 + 1) * my_n); d_sb_cnt_.reserve(HMK_MAXL1 + 1);
-        CK(cudaMemsetAsync(d_sb_cnt_.p, 0, sizeof(int32_t) * (HMK_MAXL1 + 1), st_));
+        d_sb_ids_.reserve((size_t)(HMK_MAXLEN + 1) * my_n); d_sb_cnt_.reserve(HMK_MAXLEN + 1);
+        CK(cudaMemsetAsync(d_sb_cnt_.p, 0, sizeof(int32_t) * (HMK_MAXLEN + 1), st_));
         hmk_bucket_by_length<<<(my_n + 255) / 256, 256, 0, st_>>>(d_singles_.p + my_lo, my_n, d_off_.p, my_n, d_sb_ids_.p, d_sb_cnt_.p);
         launches_++;
-        int32_t cnt[HMK_MAXL1 + 1];
+        int32_t cnt[HMK_MAXLEN + 1];
         CK(cudaMemcpyAsync(cnt, d_sb_cnt_.p, sizeof(cnt), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
-        for (int L = 1; L <= HMK_MAXL1; L++) {
+        for (int L = 1; L <= HMK_MAXLEN; L++) {
             if (cnt[L] <= 0) continue;
             const HmkScheme sch = scheme_for(L);
             d_fprof_.reserve((size_t)ncl * sch.prof_words);

@@ -21,6 +21,9 @@
 #include "hmk_resolve.h"
 
 #define HMK_MAXL1 12           // residues per 64-bit packed word
+#define HMK_MAXLEN 36          // longest sequence the packed kernels take (three words)
+#define HMK_NWMAX 10           // most 32-bit words per profile entry (long kernel)
+#define HMK_LONG_THREADS 512
 #ifndef HMK_BULK_THREADS
 #define HMK_BULK_THREADS 768
 #endif
@@ -39,7 +42,9 @@ struct HmkScheme {
     int32_t lane16;   // 0: four u8 lanes per word, 1: two s16 lanes per word
     int32_t bias;     // added to every valid cell so entries are >= 0
     int32_t half;     // 128 or 32768: lane value >= half  <=>  score >= T
-    int32_t prof_words;  // nw * HMK_MAXL1 * 24 (fixed row stride so LDS offsets are immediates)
+    int32_t prof_words;  // one word: nw * HMK_MAXL1 * 24 (fixed row stride so LDS offsets are immediates); long: nw * L * 24
+    int32_t words;       // 64-bit words per packed sequence (1..3)
+    int32_t long_layout; // 0: prof[t][h][j][r] for hmk_bulk_fast, 1: prof[t][j][h][r] for hmk_bulk_long
 };
 
 // ---------------------------------------------------------------- profile builder
@@ -60,20 +65,22 @@ __global__ void hmk_build_profiles(HmkScheme sc, int mode, const int32_t* __rest
                                    const int32_t* __restrict__ M, uint32_t* __restrict__ prof,
                                    uint32_t* __restrict__ prof_cells, uint32_t* __restrict__ prof_ops) {
     __shared__ int32_t sM[HMK_NRES * HMK_NRES];
-    __shared__ uint8_t sp[HMK_MAXL1];
+    __shared__ uint8_t sp[HMK_MAXLEN];
     const int t = blockIdx.x;
     if (t >= nq) return;
     for (int i = threadIdx.x; i < HMK_NRES * HMK_NRES; i += blockDim.x) sM[i] = M[i];
     const int32_t id = ids[t];
     const int m = off[id + 1] - off[id], n = sc.L;
-    if (threadIdx.x < m && threadIdx.x < HMK_MAXL1) sp[threadIdx.x] = res[off[id] + threadIdx.x];
+    if (threadIdx.x < m && threadIdx.x < HMK_MAXLEN) sp[threadIdx.x] = res[off[id] + threadIdx.x];
     __syncthreads();
     const bool ps = mode == HMK_PROF_QUERY ? (m <= n) : (m < n);
     const int ls = m < n ? m : n, ll = m < n ? n : m, d = ll - ls;
     const int lanes_per_word = sc.lane16 ? 2 : 4, lane_bits = sc.lane16 ? 16 : 8;
     uint32_t* out = prof + (size_t)t * sc.prof_words;
     for (int e = threadIdx.x; e < sc.prof_words; e += blockDim.x) {
-        const int r = e % HMK_NRES, j = (e / HMK_NRES) % HMK_MAXL1, h = e / (HMK_NRES * HMK_MAXL1);
+        const int r = e % HMK_NRES;
+        const int j = sc.long_layout ? e / (HMK_NRES * sc.nw) : (e / HMK_NRES) % HMK_MAXL1;
+        const int h = sc.long_layout ? (e / HMK_NRES) % sc.nw : e / (HMK_NRES * HMK_MAXL1);
         uint32_t word = 0;
         if (j >= n) { out[e] = 0; continue; }
         for (int b = 0; b < lanes_per_word; b++) {
@@ -450,6 +457,115 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __gri
         if ((threadIdx.x & 31) == 0 && scored) {
             atomicAdd(a.pair_counter, scored);
             if (a.prof_cells) {   // mixed lengths: cells differ per profile; items of this launch share one length
+                unsigned long long tc = 0, to = 0;
+                for (int t = 0; t < qn; t++) { tc += a.prof_cells[q0 + t]; to += a.prof_ops[q0 + t]; }
+                atomicAdd(a.pair_counter + 1, scored / qn * tc);
+                atomicAdd(a.pair_counter + 2, scored / qn * to);
+            }
+        }
+    }
+    if (MODE == HMK_MODE_TOPK) {
+        __syncthreads();
+        hmk_topk_flush(a, tk, q0, qn, stripe);
+    }
+}
+
+// ---------------------------------------------------------------- long bulk kernel
+// Same scheme for sequences of 13..36 residues (two or three packed words) and up to HMK_NWMAX words
+// per profile entry (s16 lanes: up to 20 shift diagonals).  Layout prof[t][j][h][r]: all words of one
+// position are 96 B apart, so they are immediates off one per-position pointer; L and nw are runtime
+// (fully unrolled, predicated).  One query at a time (the NW independent accumulators give the ILP).
+template <int MODE>
+__global__ void __launch_bounds__(HMK_LONG_THREADS, 1) hmk_bulk_long(const __grid_constant__ HmkBulkArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int qtile = blockIdx.x % a.nqt, stripe = blockIdx.x / a.nqt;
+    const int q0 = qtile * a.qt;
+    const int qn = min(a.qt, a.nq - q0);
+    if (qn <= 0) return;
+    const int L = a.sc.L, nw = a.sc.nw, W = a.sc.words;
+    const uint32_t PWB = (uint32_t)a.sc.prof_words * 4u;
+    size_t o = ((size_t)a.qt * PWB + 15) & ~(size_t)15;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + o);
+    o += 16;
+    HmkTopkSmem tk;
+    HmkHitQueue hq;
+    hmk_carve(smem_raw + o, a.qt, a.kb, false, tk, hq);
+    if (threadIdx.x == 0) hmk_mbar_init(bar, 1);
+    if (MODE == HMK_MODE_TOPK) hmk_topk_init(tk, qn, a.kb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = (uint32_t)qn * PWB;
+        hmk_mbar_expect_tx(bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.prof) + (size_t)q0 * PWB;
+        uint32_t done = 0;
+        while (done < total) {
+            uint32_t n = min(total - done, 32768u);
+            hmk_bulk_g2s(smem_raw + done, src + done, n, bar);
+            done += n;
+        }
+    }
+    hmk_mbar_wait(bar, 0);
+
+    const int i_begin = stripe * a.chunk;
+    const int i_end = min(a.ndb, i_begin + a.chunk);
+    unsigned long long scored = 0;
+    const uint32_t topmask = a.sc.lane16 ? 0x80008000u : 0x80808080u;
+    const int32_t dec = a.sc.T - a.sc.half;
+    const uint32_t jstride = (uint32_t)nw * HMK_ROWB;
+
+    for (int ib = i_begin + (threadIdx.x & ~31); ib < i_end; ib += blockDim.x) {
+        const int i = ib + (threadIdx.x & 31);
+        bool valid = i < i_end;
+        const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
+        if (valid && a.slot && a.slot[id] >= 0) valid = false;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        uint64_t w[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (valid && k < W) w[k] = a.packed[(size_t)id * W + k];
+        const unsigned char* rowp[HMK_MAXLEN];
+#pragma unroll
+        for (int j = 0; j < HMK_MAXLEN; j++)
+            rowp[j] = smem_raw + j * jstride + (uint32_t)((w[j / HMK_MAXL1] >> (5 * (j % HMK_MAXL1))) & 31u) * 4u;
+        if (valid) scored += qn;
+        for (int t = 0; t < qn; t++) {
+            uint32_t acc[HMK_NWMAX];
+#pragma unroll
+            for (int h = 0; h < HMK_NWMAX; h++) acc[h] = 0;
+#pragma unroll
+            for (int j = 0; j < HMK_MAXLEN; j++) {
+                if (j < L) {
+#pragma unroll
+                    for (int h = 0; h < HMK_NWMAX; h++)
+                        if (h < nw) acc[h] += *reinterpret_cast<const uint32_t*>(rowp[j] + h * HMK_ROWB);
+                    rowp[j] += PWB;
+                }
+            }
+            uint32_t any = 0, m2 = 0, m4 = 0;
+#pragma unroll
+            for (int h = 0; h < HMK_NWMAX; h++)
+                if (h < nw) { any |= acc[h]; m2 = __vmaxu2(m2, acc[h]); m4 = __vmaxu4(m4, acc[h]); }
+            int32_t best;
+            if (a.sc.lane16) { const uint32_t lo = m2 & 0xffffu, hi = m2 >> 16; best = (int32_t)(lo > hi ? lo : hi); }
+            else {
+                uint32_t x = m4 & 0xffu, y = (m4 >> 8) & 0xffu, z = (m4 >> 16) & 0xffu, v = m4 >> 24;
+                x = x > y ? x : y; z = z > v ? z : v;
+                best = (int32_t)(x > z ? x : z);
+            }
+            if (MODE == HMK_MODE_DENSE) {
+                if (valid) a.dense[(size_t)(q0 + t) * a.dense_stride + i] = best + dec;
+            } else {
+                const bool hit = valid && (any & topmask) != 0;
+                hmk_queue_push<MODE>(a, tk, q0, hq, hit, t, hit ? best + dec : 0, i);
+            }
+        }
+    }
+    if (MODE != HMK_MODE_DENSE && hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
+    if (a.pair_counter) {
+        for (int s = 16; s > 0; s >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, s);
+        if ((threadIdx.x & 31) == 0 && scored) {
+            atomicAdd(a.pair_counter, scored);
+            if (a.prof_cells) {
                 unsigned long long tc = 0, to = 0;
                 for (int t = 0; t < qn; t++) { tc += a.prof_cells[q0 + t]; to += a.prof_ops[q0 + t]; }
                 atomicAdd(a.pair_counter + 1, scored / qn * tc);
@@ -1363,18 +1479,20 @@ __global__ void hmk_fill_i32(int32_t* p, int32_t v, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-__global__ void hmk_pack_sequences(int n, const uint8_t* __restrict__ res, const int32_t* __restrict__ off,
+// 5 bits per residue, 12 residues per 64-bit word, `words` words per sequence (residue j lives in word
+// j / 12 at bits [5 (j % 12), +5)); also validates the residue codes
+__global__ void hmk_pack_sequences(int n, int words, const uint8_t* __restrict__ res, const int32_t* __restrict__ off,
                                    uint64_t* __restrict__ packed, int32_t* __restrict__ bad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int len = off[i + 1] - off[i];
-    uint64_t w = 0;
+    uint64_t w[3] = {0, 0, 0};
     for (int j = 0; j < len; j++) {
         uint32_t r = res[off[i] + j];
         if (r >= HMK_NRES) { atomicExch(bad, 1); r = 0; }
-        if (j < HMK_MAXL1) w |= (uint64_t)r << (5 * j);
+        if (j < HMK_MAXL1 * words) w[j / HMK_MAXL1] |= (uint64_t)r << (5 * (j % HMK_MAXL1));
     }
-    packed[i] = w;
+    for (int k = 0; k < words; k++) packed[(size_t)i * words + k] = w[k];
 }
 
 // flags -> exclusive positions, three-step scan (per-block counts, single-block scan, scatter)
@@ -1425,7 +1543,7 @@ __global__ void hmk_bucket_by_length(const int32_t* __restrict__ ids, int n, con
     if (i >= n) return;
     const int32_t id = ids[i];
     const int len = off[id + 1] - off[id];
-    if (len > HMK_MAXL1) return;
+    if (len > HMK_MAXLEN) return;
     const int k = atomicAdd(count + len, 1);
     out[(size_t)len * stride + k] = id;
 }

@@ -13,8 +13,9 @@ mats = np.load(os.path.join(ROOT, "tests", "golden", "matrices.npz"))
 NT = os.cpu_count() or 1
 cases = [("S100k_len7-12", 100000, 7, 12, "blosum62", 0, True)]
 for L in (7, 9, 12, 16, 20, 25, 30):
-    cases.append((f"sweep_len{L}", 50000, L, L, "blosum62", 0, L <= 12))
-cases.append(("sweep_len7-30", 50000, 7, 30, "blosum62", 0, False))
+    cases.append((f"sweep_len{L}", 50000, L, L, "blosum62", 0, True))
+cases.append(("sweep_len7-30", 50000, 7, 30, "blosum62", 0, True))
+cases.append(("sweep_len13-18", 50000, 13, 18, "blosum62", 0, True))
 for m in ("blosum30", "blosum45", "blosum80", "blosum100", "pam250", "mcla71"):
     cases.append((f"sweep_{m}", 50000, 12, 12, m, 0, True))
 cases.append(("sweep_blosum62_P-1", 50000, 12, 12, "blosum62", -1, True))

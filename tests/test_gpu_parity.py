@@ -200,14 +200,17 @@ SYNTH_CASES = [
     # n, min_len, max_len, matrix, P, K override, abundance shuffle, options
     (4000, 12, 12, "blosum62", 0, None, False, {}),
     (4000, 12, 12, "blosum62", -1, None, False, {"batch": 32}),
-    (3000, 7, 12, "blosum62", 0, None, False, {}),                 # mixed lengths -> generic kernel
+    (3000, 7, 12, "blosum62", 0, None, False, {}),                 # mixed lengths -> packed kernel per length bucket
     (3000, 7, 12, "blosum62", -2, None, False, {"batch": 16, "kb": 2}),
     (3000, 9, 9, "pam250", 0, None, False, {}),
     (3000, 12, 12, "blosum30", 0, None, False, {}),
     (2500, 12, 12, "blosum100", 0, None, False, {}),               # wide range: 16-bit lanes
     (3000, 12, 12, "blosum62", 0, 1000, False, {}),                # K large: phase 1 runs to exhaustion
     (3000, 12, 12, "blosum62", 0, None, True, {}),                 # abundance not sorted -> tie-rank path
-    (1500, 16, 16, "blosum62", 0, None, False, {}),                # longer than one packed word -> generic
+    (1500, 16, 16, "blosum62", 0, None, False, {}),                # two packed words -> long packed kernel (s16 lanes)
+    (1500, 30, 30, "blosum62", -1, None, False, {}),               # three packed words, 17 diagonals
+    (2000, 13, 18, "blosum45", 0, None, False, {"batch": 40}),     # mixed lengths on the long kernel
+    (1500, 20, 20, "blosum62", 0, None, False, {"force_generic": 1}),
     (2000, 7, 30, "blosum50", 0, None, False, {}),
 ]
 
