@@ -8,6 +8,8 @@ from .host import (ALPHABET, Cluster, CudaError, DataException, FileFormatExcept
                    GreedyResult, HammockException, LimitedGreedySequenceClusterer, NullClusterError, ShiftedScorer,
                    UniqueSequence, check_max_shift, get_max_shift, greedy_cluster_arrays, initial_clusters_limit,
                    load_scoring_matrix, load_unique_sequences_from_fasta, load_unique_sequences_from_table,
-                   pack_sequences, rebuild_clusters, run_greedy_clustering, set_greedy_threshold, sort_sequences)
+                   pack_sequences, rebuild_clusters, run_greedy_clustering, set_greedy_threshold, sort_sequences,
+                   get_sorted_labels, java_hashmap_order, save_cluster_sequences_to_csv,
+                   save_cluster_sequences_to_csv_ordered, save_clusters_to_csv, save_input_statistics)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -48,6 +48,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_SRC = os.path.join(HERE, "host_cpp", "hammock_greedy.cpp")
+HOST_HDR = os.path.join(HERE, "host_cpp", "hammock_host.hpp")
+HOST_BIN = os.path.join(HERE, "hammock_greedy")
+
+
+def build_host(force: bool = False) -> str:
+    """The native `greedy`-mode driver (C++ host side above the C ABI); links libhammock_b200.so."""
+    build(force=False)
+    if not force and os.path.exists(HOST_BIN) and all(
+            os.path.getmtime(HOST_BIN) >= os.path.getmtime(f) for f in (HOST_SRC, HOST_HDR, LIB)):
+        return HOST_BIN
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, HOST_SRC, "-L", HERE, "-lhammock_b200",
+                           "-Wl,-rpath,$ORIGIN"])
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print(LIB)
+    print(build_host(force="--force" in sys.argv))

@@ -377,6 +377,109 @@ def initial_clusters_limit(sequences) -> int:                  # Hammock.java:39
     return _java_round(len(sequences) * 0.025)
 
 
+# ---------------------------------------------------------------- labels + result files
+def _java_string_hash(s: str) -> int:
+    h = 0
+    for ch in s:                          # String.hashCode (labels are ASCII here)
+        h = (31 * h + ord(ch)) & 0xFFFFFFFF
+    return h
+
+
+def java_hashmap_order(keys: Sequence[str]) -> List[str]:
+    """Iteration order of a java.util.HashMap<String, ?> (Java 8+: tail insertion, order-preserving resize,
+    bins assumed not to treeify) that received `keys` in this order."""
+    cap = 16
+    while len(keys) > cap * 3 // 4:
+        cap *= 2
+    bins: List[List[str]] = [[] for _ in range(cap)]
+    for k in keys:
+        h = _java_string_hash(k)
+        h ^= h >> 16
+        bins[h & (cap - 1)].append(k)
+    return [k for b in bins for k in b]
+
+
+def get_sorted_labels(sequences: Sequence[UniqueSequence]) -> List[str]:
+    """Hammock.getSortedLabels (Hammock.java:1586-1605): TreeMap with ValueComparator (FileIOManager.java:1464-1480,
+    never returns 0) filled from a HashMap -> count descending, equal counts in reverse HashMap iteration order."""
+    cnt: Dict[str, int] = {}
+    for s in sequences:
+        for k, v in s.labels_map.items():
+            cnt[k] = _i32(cnt.get(k, 0) + v)
+    out: List[str] = []
+    for k in java_hashmap_order(list(cnt.keys())):
+        pos = 0
+        while pos < len(out) and cnt[out[pos]] > cnt[k]:
+            pos += 1
+        out.insert(pos, k)
+    return out
+
+
+def _clusters_largest_first(clusters: Sequence[Cluster]) -> List[Cluster]:
+    """Collections.sort(list, reverseOrder()) with Cluster.compareTo (Cluster.java:197-204): size desc, id desc"""
+    return sorted(clusters, key=lambda c: (c.size(), c.get_id()), reverse=True)
+
+
+def _row(cluster_id, s: UniqueSequence, alignment: str, labels) -> str:
+    return "\t".join([str(cluster_id), s.get_sequence_string(), alignment, str(s.size())] +
+                     [str(s.labels_map.get(lab, 0)) for lab in labels]) + "\n"
+
+
+def save_cluster_sequences_to_csv(clusters: Sequence[Cluster], path: str, labels: Sequence[str]) -> None:
+    """FileIOManager.saveClusterSequencesToCsv (FileIOManager.java:398-404, 594-638).  The alignment column is the
+    sequence for one-member clusters and "NA" for multi-member clusters (the reference fills it from the Clustal-Omega
+    MSA it builds after the greedy stage, Hammock.java:414-426 -- outside this path; `cluster` mode accepts NA)."""
+    with open(path, "w") as w:
+        w.write("\t".join(["cluster_id", "sequence", "alignment", "sum"] + list(labels)) + "\n")
+        for c in _clusters_largest_first(clusters):
+            members = sorted(c.get_sequences(), key=lambda s: (s.size(), s.get_sequence_string()), reverse=True)
+            for s in members:
+                w.write(_row(c.get_id(), s, s.get_sequence_string() if len(members) == 1 else "NA", labels))
+
+
+def save_cluster_sequences_to_csv_ordered(clusters: Sequence[Cluster], path: str, labels: Sequence[str],
+                                          ordered_sequences: Sequence[UniqueSequence]) -> None:
+    """FileIOManager.saveClusterSequencesToCsvOrdered (FileIOManager.java:371-374)"""
+    of = {}
+    for c in clusters:
+        for s in c.get_sequences():
+            of[s.get_sequence_string()] = c
+    with open(path, "w") as w:
+        w.write("\t".join(["cluster_id", "sequence", "alignment", "sum"] + list(labels)) + "\n")
+        for s in ordered_sequences:
+            c = of.get(s.get_sequence_string())
+            if c is None:
+                w.write(_row("NA", s, "NA", labels))
+            else:
+                w.write(_row(c.get_id(), s, s.get_sequence_string() if c.get_unique_size() == 1 else "NA", labels))
+
+
+def save_clusters_to_csv(clusters: Sequence[Cluster], path: str, labels: Sequence[str]) -> None:
+    """FileIOManager.SaveClustersToCsv (FileIOManager.java:649-676): main_sequence = most abundant member, ties
+    alphabetically first."""
+    with open(path, "w") as w:
+        w.write("\t".join(["cluster_id", "main_sequence", "sum"] + list(labels)) + "\n")
+        for c in _clusters_largest_first(clusters):
+            seqs = c.get_sequences()
+            top = max(s.size() for s in seqs)
+            main = min(s.get_sequence_string() for s in seqs if s.size() == top)
+            sums = []
+            for lab in labels:
+                t = 0
+                for s in seqs:
+                    t = _i32(t + s.labels_map.get(lab, 0))
+                sums.append(str(t))
+            w.write("\t".join([str(c.get_id()), main, str(c.size())] + sums) + "\n")
+
+
+def save_input_statistics(sequences: Sequence[UniqueSequence], labels: Sequence[str], path: str) -> None:
+    """FileIOManager.saveInputStatistics (FileIOManager.java:709-729)"""
+    with open(path, "w") as w:
+        w.write("".join("\t" + lab for lab in labels) + "\n")
+        w.write("total_count" + "".join("\t" + str(_i32(sum(s.labels_map.get(lab, 0) for s in sequences))) for lab in labels) + "\n")
+        w.write("unique_count" + "".join("\t" + str(sum(1 for s in sequences if lab in s.labels_map)) for lab in labels))
+
+
 # ---------------------------------------------------------------- packing + C ABI
 def shard_range(n: int, world: int, rank: int):
     """Contiguous share [lo, hi) of n work items for `rank` of `world` (same split as the library's

@@ -313,3 +313,49 @@ def test_s1m_properties(blosum62):
     G2 = ctx.download()
     assert (G2.cluster_id == G.cluster_id).all() and (G2.member_rank == G.member_rank).all()
     ctx.close()
+
+
+def test_cpp_host_driver_end_to_end(tmp_path, golden_dir, blosum62):
+    """hammock_greedy (C++ host side + C ABI): fasta in, the reference's result files out; compared with the
+    Python mirror's writers on the same clustering and with the MUSI golden assignment."""
+    import subprocess
+    from hammock_b200 import build as hb_build
+    exe = hb_build.build_host()
+    z = np.load(os.path.join(golden_dir, "musi.npz"))
+    strs = synth.to_strings(z["residues"], z["offsets"])
+    rng = np.random.default_rng(4)
+    labs = ["rep1", "rep2", "ctrl"]
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for k, i in enumerate(rng.permutation(len(strs))):
+            f.write(f">s{k}|{int(z['abundance'][i])}|{labs[k % 3]}\n{strs[i]}\n")
+    mp = tmp_path / "m.txt"
+    with open(mp, "w") as f:
+        f.write("# test copy of BLOSUM62\n   " + "  ".join(hb.ALPHABET) + "\n")
+        for i in range(24):
+            f.write(hb.ALPHABET[i] + " " + " ".join(f"{int(v):2d}" for v in blosum62[i]) + "\n")
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([exe, "greedy", "-i", str(fa), "-d", str(out), "-m", str(mp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # same pipeline through the Python mirror
+    seqs = hb.load_unique_sequences_from_fasta(str(fa))
+    labels = hb.get_sorted_labels(seqs)
+    ordered = hb.sort_sequences(seqs, "size", labels)
+    clusters = hb.LimitedGreedySequenceClusterer(hb.ShiftedScorer(hb.load_scoring_matrix(str(mp)), 0, hb.get_max_shift(seqs)),
+                                                 hb.set_greedy_threshold(seqs), hb.initial_clusters_limit(seqs)).cluster(ordered)
+    ref = tmp_path / "ref"
+    ref.mkdir()
+    hb.save_cluster_sequences_to_csv(clusters, str(ref / "initial_clusters_sequences.tsv"), labels)
+    hb.save_cluster_sequences_to_csv_ordered(clusters, str(ref / "initial_clusters_sequences_original_order.tsv"), labels, seqs)
+    hb.save_clusters_to_csv(clusters, str(ref / "initial_clusters.tsv"), labels)
+    hb.save_input_statistics(seqs, labels, str(ref / "input_statistics.tsv"))
+    for fn in ("initial_clusters_sequences.tsv", "initial_clusters_sequences_original_order.tsv", "initial_clusters.tsv",
+               "input_statistics.tsv"):
+        assert (out / fn).read_text() == (ref / fn).read_text(), fn
+    # all abundances are 1 in MUSI and the clustering order is (abundance, string) -> same order as the golden
+    got = {}
+    for line in (out / "initial_clusters_sequences.tsv").read_text().splitlines()[1:]:
+        cid, s = line.split("\t")[:2]
+        got[s] = int(cid)
+    assert [got[s] for s in strs] == z["cluster_id"].tolist()
