@@ -1,0 +1,86 @@
+"""Randomised differential test (GPU vs oracle): small inputs, random parameters -- thresholds around and far
+from the automatic value, shifts up to the limit, penalties of both signs, tiny / huge cluster limits, every
+bundled matrix, uniform / mixed / long lengths, sorted and unsorted abundances, tiny batches and candidate
+lists (restarts, grows, look-ahead aborts).  Every status code and every assignment must agree."""
+import os
+
+import numpy as np
+import pytest
+
+import hammock_b200 as hb
+from hammock_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(rng, mats, names):
+    kind = rng.integers(0, 6)
+    if kind == 0:
+        lo = hi = int(rng.integers(5, 13))
+    elif kind == 1:
+        lo = int(rng.integers(4, 10)); hi = int(rng.integers(lo + 1, 13))
+    elif kind == 2:
+        lo = hi = int(rng.integers(13, 31))
+    elif kind == 3:
+        lo = int(rng.integers(13, 20)); hi = lo + int(rng.integers(1, 6))
+    elif kind == 4:
+        lo = int(rng.integers(5, 12)); hi = int(rng.integers(14, 40))
+    else:
+        lo = hi = 12
+    n = int(rng.integers(2, 500))
+    d = synth.generate(n, lo, hi, seed=int(rng.integers(1, 1 << 30)), top_abundance=int(rng.choice([1, 3, 50, 100000])))
+    if rng.random() < 0.25:
+        d["abundance"] = np.ascontiguousarray(rng.permutation(d["abundance"]))
+    T0, X0, K0 = synth.default_params(d["lengths"])
+    T = int(T0 + rng.choice([0, 0, -3, 4, -12, 15, 40, -60]))
+    X = int(rng.choice([X0, X0, 0, 1, lo - 1, lo, X0 + 1]))
+    P = int(rng.choice([0, 0, 0, -1, -2, -5, 1]))
+    K = int(rng.choice([K0, K0, 0, 1, 2, n // 3, n, 2 * n]))
+    m = names[int(rng.integers(0, len(names)))]
+    opts = {}
+    if rng.random() < 0.5:
+        opts = {"batch": int(rng.choice([1, 2, 5, 17, 64])), "kb": int(rng.choice([1, 2, 8])), "capq": int(rng.choice([1, 4, 256])),
+                "p2_window": int(rng.choice([1, 7, 64, 65536])), "lookahead": int(rng.integers(0, 2))}
+    return d, mats[m], T, max(X, 0), P, K, opts, (n, lo, hi, m)
+
+
+def test_fuzz_against_oracle(golden_dir):
+    z = np.load(os.path.join(golden_dir, "matrices.npz"))
+    mats = {k: z[k] for k in z.files}
+    names = sorted(mats)
+    asym = mats["blosum62"].copy()
+    asym[np.triu_indices(24, 1)] -= 1          # orientation M[shorter][longer] matters
+    mats["asym"] = asym
+    names.append("asym")
+    big = mats["blosum62"] * 700               # does not fit 8/16-bit lanes: generic kernel, int32 sums
+    mats["big"] = big
+    names.append("big")
+    rng = np.random.default_rng(20260101)
+    seen = {"status": set(), "path": set()}
+    for it in range(220):
+        d, M, T, X, P, K, opts, tag = _case(rng, mats, names)
+        if tag[3] == "big":
+            T *= 700
+        R = O.greedy_cluster(d["residues"], d["offsets"], d["abundance"], M, T, X, P, K, nthreads=1)
+        ctx = hb.GreedyContext(0, **opts)
+        try:
+            ctx.upload(d["residues"], d["offsets"], d["abundance"], M, T, X, P, K)
+            rc, _ = ctx.run_status()
+            st = ctx.stats()
+            what = f"iter {it} {tag} T={T} X={X} P={P} K={K} opts={opts} path={st['fast_path']}"
+            assert rc == R.status, what
+            if rc == 2:
+                assert st["error_step"] == R.counters["npe_step"], what
+            if rc == 0:
+                G = ctx.download()
+                assert (G.cluster_id == R.cluster_id).all(), what
+                assert (G.member_rank == R.member_rank).all(), what
+                assert len(G.result_order) == len(R.result_order) and (G.result_order == R.result_order).all(), what
+                assert G.n_multi == R.n_multi, what
+                assert st["p1_steps"] == R.counters["p1_steps"] and st["p2_assigned"] == R.counters["p2_assigned"], what
+            seen["status"].add(rc)
+            seen["path"].add(st["fast_path"])
+        finally:
+            ctx.close()
+    assert seen["status"] >= {0, 1, 2} and seen["path"] == {0, 1, 2}, seen
