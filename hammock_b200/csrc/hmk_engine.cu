@@ -123,6 +123,7 @@ enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_R
 struct Options {
     int64_t batch = 0;          // phase-1 queries per batch (0 = three profile tiles)
     int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
+    int64_t filter = 1;         // 1: filter + verify kernel where it applies (u8 lanes, two words, one length <= 12)
     int64_t lookahead = 1;      // 1: prepare the next batch's partner search while the current batch resolves
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
     int64_t kb = 8;             // partner candidates kept per query
@@ -240,6 +241,10 @@ private:
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
         DevBuf<uint32_t> prof;
         DevBuf<uint32_t> prof_len[HMK_MAXLEN + 1], pcells[HMK_MAXLEN + 1], pops[HMK_MAXLEN + 1];   // mixed lengths: per thread-side length
+        // state-independent inputs of the resolver: intra-batch scores (+ bit mask), partner candidate ids and
+        // their scores against every batch query
+        DevBuf<int32_t> ib, pcand, pd;
+        DevBuf<uint32_t> ibm;
         cudaEvent_t ready = nullptr;
         bool valid = false;      // partner search for the batch starting behind `after` has been issued
         int nq = 0;
@@ -248,10 +253,9 @@ private:
     cudaStream_t st2_ = nullptr;
     void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s);
     // ---- phase-1 scratch
-    DevBuf<int32_t> d_qid_, d_nq_, d_ib_,
+    DevBuf<int32_t> d_qid_, d_nq_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_, d_dirty_b_;
-    DevBuf<uint32_t> d_ibm_;
-    DevBuf<int32_t> d_pcand_, d_pd_;
+    int plan_sms_ = 0;                // SMs a bulk launch may count on (one less while the resolver holds an SM)
     int batch_id_ = 0;
     DevBuf<uint32_t> d_prof_;
     DevBuf<int4> d_hits_;
@@ -364,15 +368,23 @@ void Engine::choose_scheme(const int32_t* M) {
         if (!ok) continue;
         sc_.lane16 = lane16; sc_.bias = (int32_t)bias; sc_.half = (int32_t)half;
         sc_.words = words_; sc_.long_layout = lng ? 1 : 0;
+        sc_.filter = 0;
         if (min_len_ == max_len_) {
             fast_ = true;
             sc_.nw = nw[max_len_];
+            if (opt.filter && !lane16 && !lng && sc_.nw == 2) {
+                // the filter bytes (max of two neighbouring lanes, summed) must stay below 256
+                int64_t worst = 0;
+                for (int k = -X_; k <= X_; k++)   // filter lanes count every position (padding = score 0)
+                    worst = std::max<int64_t>(worst, 2LL * P_ * (k < 0 ? -k : k) + half - (int64_t)T_ - max_len_ * bias);
+                if (worst + (int64_t)max_len_ * (mmax + bias) <= 255) sc_.filter = 1;
+            }
         } else {
             mixed_ = true;
             sc_.nw = 0;
             for (int n = 0; n <= HMK_MAXLEN; n++) { nw_len_[n] = nw[n]; sc_.nw = std::max(sc_.nw, nw[n]); }
         }
-        sc_.prof_words = sc_.nw * (lng ? max_len_ : HMK_MAXL1) * HMK_NRES;
+        sc_.prof_words = sc_.filter ? HMK_FPW : sc_.nw * (lng ? max_len_ : HMK_MAXL1) * HMK_NRES;
         return;
     }
 }
@@ -461,7 +473,7 @@ int Engine::qt_max(const HmkScheme& sc) const {
     if (opt.qt > 0) return (int)opt.qt;
     const size_t pwb = (size_t)sc.prof_words * 4;
     const size_t per = pwb + (size_t)opt.kb * 8 + 8 + 12;
-    const size_t fixed = 64 + (HMK_BULK_THREADS / 32) * HMK_QCAP * 8;
+    const size_t fixed = 64 + (HMK_BULK_THREADS / 32) * HMK_QCAP * 8 + (sc.filter ? 16 + (HMK_BULK_THREADS / 32) * HMK_CQCAP * 12 : 0);
     return (int)std::min<size_t>(255, std::max<size_t>(1, (smem_optin_ - fixed) / per));
 }
 
@@ -470,7 +482,7 @@ HmkScheme Engine::scheme_for(int n) const {
     HmkScheme sc = sc_;
     sc.L = n;
     if (mixed_) sc.nw = nw_len_[n];
-    sc.prof_words = sc.nw * (sc.long_layout ? n : HMK_MAXL1) * HMK_NRES;
+    sc.prof_words = sc.filter ? HMK_FPW : sc.nw * (sc.long_layout ? n : HMK_MAXL1) * HMK_NRES;
     return sc;
 }
 
@@ -505,8 +517,30 @@ static void launch_long_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaSt
 }
 
 template <int MODE>
+static void launch_filter_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    static size_t configured_smem = 0;
+    if (MODE == HMK_MODE_DENSE) {      // every score is wanted: exact kernel on the filter-layout profiles
+        if (smem > configured_smem) {
+            CK(cudaFuncSetAttribute(hmk_bulk_fast<2, HMK_MODE_DENSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured_smem = smem;
+        }
+        hmk_bulk_fast<2, HMK_MODE_DENSE, true><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
+    } else {
+        constexpr int M2 = MODE == HMK_MODE_DENSE ? HMK_MODE_EMIT : MODE;
+        if (smem > configured_smem) {
+            CK(cudaFuncSetAttribute(hmk_bulk_filter<M2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(hmk_bulk_filter<M2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured_smem = smem;
+        }
+        if (a.sc.L == 12) hmk_bulk_filter<M2, 12><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
+        else hmk_bulk_filter<M2, 0><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
+    }
+}
+
+template <int MODE>
 static void launch_fast_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
     if (a.sc.long_layout) { launch_long_mode<MODE>(a, grid, smem, st); return; }
+    if (a.sc.filter) { launch_filter_mode<MODE>(a, grid, smem, st); return; }
     switch (a.sc.nw) {
         case 1: launch_fast_inst<1, MODE>(a, grid, smem, st); break;
         case 2: launch_fast_inst<2, MODE>(a, grid, smem, st); break;
@@ -531,17 +565,29 @@ static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, 
 void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch) const {
     const int threads = sch ? (sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS) : HMK_GENERIC_THREADS;
     const int qmax = sch ? qt_max(*sch) : 128;
+    const int sms = plan_sms_ > 0 ? plan_sms_ : sm_count_;
     a.nqt = (a.nq + qmax - 1) / qmax;
     a.qt = (a.nq + a.nqt - 1) / a.nqt;
-    int want = (int)((sm_count_ * opt.waves + a.nqt - 1) / a.nqt);
-    if (a.nqt <= sm_count_ * opt.waves && (sm_count_ * opt.waves) % a.nqt != 0) {
+    int want = (int)((sms * opt.waves + a.nqt - 1) / a.nqt);
+    if (a.nqt <= sms * opt.waves && (sms * opt.waves) % a.nqt != 0) {
         // nqt does not divide waves*SMs: round the total up to the next multiple of the SM count
-        int total = (int)((((int64_t)want * a.nqt + sm_count_ - 1) / sm_count_) * sm_count_);
+        int total = (int)((((int64_t)want * a.nqt + sms - 1) / sms) * sms);
         want = std::max(1, total / a.nqt);
     }
     int max_stripes = (a.ndb + threads - 1) / threads;
+    if (a.nqt > sms * opt.waves) {
+        // more profile tiles than resident CTAs: take the stripe count (<= 8, stripes of >= 16 K items) that
+        // fills the last wave best
+        double best = 0;
+        for (int s = 1; s <= 8 && (s == 1 || a.ndb / s >= 16384); s++) {
+            const int64_t total = (int64_t)a.nqt * s;
+            const double eff = (double)total / (double)(((total + sms - 1) / sms) * sms);
+            if (eff > best + 0.01) { best = eff; want = s; }
+        }
+    }
     a.nstripes = std::max(1, std::min(want, max_stripes));
     a.chunk = (a.ndb + a.nstripes - 1) / a.nstripes;
+    if (sch && sch->filter) a.chunk = std::min(a.chunk, (1 << 22) - 1);   // candidate entries hold 22 bits of stripe offset
     a.nstripes = (a.ndb + a.chunk - 1) / a.chunk;
 }
 
@@ -558,6 +604,7 @@ void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const
     if (sch) {
         size_t smem = (((size_t)a.qt * sch->prof_words * 4 + 15) & ~(size_t)15) + 16 +
                       hmk_carve_bytes(a.qt, a.kb, sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS, false);
+        if (sch->filter) smem += 16 + (size_t)(HMK_BULK_THREADS / 32) * HMK_CQCAP * 12;   // candidate queues
         if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, s);
         else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, s);
         else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, s);
@@ -708,6 +755,33 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         CK(cudaGetLastError());
         launches_++;
     }
+    // intra-batch scores S(member = q_b2, query = q_b); row strides padded to 16 bytes for the TMA row prefetch
+    const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * kb + 3) & ~3, nw = (nq + 31) / 32;
+    bb.ib.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH + 4)); bb.ibm.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH / 32));
+    bb.pcand.reserve((size_t)nq * kb); bb.pd.reserve((size_t)nq * (pd_stride + 4));
+    {
+        HmkBulkArgs d{};
+        d.prof = bb.prof.p; d.nq = nq;
+        d.packed = d_packed_.p; d.db_ids = bb.qid.p; d.db_begin = 0; d.ndb = nq;
+        d.dense = bb.ib.p; d.dense_stride = ib_stride;
+        launch_bulk(HMK_MODE_DENSE, d, bb.qid.p, 1, s);
+    }
+    hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, s>>>(nq, nw, T_, bb.ib.p, ib_stride, bb.ibm.p);
+    launches_++;
+    // S(partner candidate, query) for every candidate of the batch: clusters born inside the
+    // batch have one of these as their second member
+    {
+        const int npc = nq * kb;
+        hmk_partner_ids<<<(npc + 127) / 128, 128, 0, s>>>(nq, kb, bb.bk_key.p, bb.bk_cnt.p,
+                                                          identity_rank_ ? nullptr : d_id_of_rank_.p, bb.qid.p, bb.pcand.p);
+        launches_++;
+        HmkBulkArgs d{};
+        d.prof = bb.prof.p; d.nq = nq;
+        d.packed = d_packed_.p; d.db_ids = bb.pcand.p; d.db_begin = 0; d.ndb = npc;
+        d.dense = bb.pd.p; d.dense_stride = pd_stride;
+        launch_bulk(HMK_MODE_DENSE, d, bb.qid.p, 1, s);
+    }
+    CK(cudaGetLastError());
     CK(cudaEventRecord(bb.ready, s));
     bb.valid = true;
     bb.nq = nq;
@@ -715,14 +789,10 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
 
 int Engine::phase1() {
     int B = (int)opt.batch;
-    if (B <= 0) B = fast_ ? 3 * qt_max() : 192;
+    if (B <= 0) B = fast_ ? (sc_.filter ? 5 : 3) * qt_max() : 192;   // measured optimum on the 1 M workload
     B = std::max(1, std::min(B, HMK_MAXBATCH));
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
-    const int nwmax = (B + 31) / 32;
-    d_ib_.reserve((size_t)B * (B + 4));
-    d_ibm_.reserve((size_t)B * nwmax);
-    d_pcand_.reserve((size_t)B * opt.kb); d_pd_.reserve((size_t)B * (B * opt.kb + 4));
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
     batch_id_ = 0;
     size_t hit_cap = (size_t)opt.hit_cap;
@@ -738,13 +808,11 @@ int Engine::phase1() {
         if (!cb.valid) stage_partner_search(cb, std::min(B, h_ctl_->unproc_alive), cur, nullptr, st_);   // not prepared ahead
         else CK(cudaStreamWaitEvent(st_, cb.ready, 0));
         const int nq = cb.nq;
-        // look ahead: the next batch's partner search runs on the side stream while this batch is
-        // resolved (it only needs this batch's last query id; whatever this batch consumes in the
-        // meantime is filtered by the resolver's consumed set)
-        if (opt.lookahead && !nb.valid && nq == B && h_ctl_->unproc_alive >= nq + 3 * B) {
-            CK(cudaStreamWaitEvent(st2_, cb.ready, 0));
-            stage_partner_search(nb, B, cur, cb.qid.p + (nq - 1), st2_);
-        }
+        // look ahead: the next batch's partner search (and everything else that does not depend on the
+        // clustering state) runs on the side stream while this batch is resolved; it is issued right
+        // behind the resolver so that the resolver's CTA is placed first.  It only needs this batch's last
+        // query id; whatever this batch consumes in the meantime is filtered by the resolver's consumed set
+        const bool ahead = opt.lookahead && !nb.valid && nq == B && h_ctl_->unproc_alive >= nq + 3 * B;
         const int32_t* d_qid = cb.qid.p;
         const uint32_t* d_prof = cb.prof.p;
         // A: clusters whose founder scores >= T, then complete linkage over their members
@@ -767,39 +835,15 @@ int Engine::phase1() {
             CK(cudaGetLastError());
             launches_++;
         }
-        // intra-batch scores S(member = q_b2, query = q_b); row strides padded to 16 bytes for the TMA row prefetch
         const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * (int)opt.kb + 3) & ~3;
-        sec(SEC_P1_INTRA);
-        {
-            HmkBulkArgs a{};
-            a.prof = d_prof; a.nq = nq;
-            a.packed = d_packed_.p; a.db_ids = d_qid; a.db_begin = 0; a.ndb = nq;
-            a.dense = d_ib_.p; a.dense_stride = ib_stride;
-            launch_bulk(HMK_MODE_DENSE, a, d_qid, 1);
-        }
         const int nw = (nq + 31) / 32;
-        hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, st_>>>(nq, nw, T_, d_ib_.p, ib_stride, d_ibm_.p);
-        launches_++;
-        // S(partner candidate, query) for every candidate of the batch: clusters born inside the
-        // batch have one of these as their second member
-        {
-            const int npc = nq * (int)opt.kb;
-            hmk_partner_ids<<<(npc + 127) / 128, 128, 0, st_>>>(nq, (int)opt.kb, cb.bk_key.p, cb.bk_cnt.p,
-                                                                 identity_rank_ ? nullptr : d_id_of_rank_.p, d_qid, d_pcand_.p);
-            launches_++;
-            HmkBulkArgs a{};
-            a.prof = d_prof; a.nq = nq;
-            a.packed = d_packed_.p; a.db_ids = d_pcand_.p; a.db_begin = 0; a.ndb = npc;
-            a.dense = d_pd_.p; a.dense_stride = pd_stride;
-            launch_bulk(HMK_MODE_DENSE, a, d_qid, 1);
-        }
         HmkP1Batch pb{};
         pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid; pb.kb = (int)opt.kb;
         pb.bk_key = cb.bk_key.p; pb.bk_cnt = cb.bk_cnt.p; pb.bk_ovf = cb.bk_ovf.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
-        pb.ib = d_ib_.p; pb.ib_stride = ib_stride; pb.ibm = d_ibm_.p; pb.nw = nw;
-        pb.pcand = d_pcand_.p;
-        pb.pd = d_pd_.p; pb.pd_stride = pd_stride;
+        pb.ib = cb.ib.p; pb.ib_stride = ib_stride; pb.ibm = cb.ibm.p; pb.nw = nw;
+        pb.pcand = cb.pcand.p;
+        pb.pd = cb.pd.p; pb.pd_stride = pd_stride;
         // the resolver must not run on truncated hit lists: checked on the host first
         CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
@@ -825,6 +869,12 @@ int Engine::phase1() {
         CK(cudaGetLastError());
         launches_++;
         stats.p1_batches++;
+        if (ahead) {
+            sec(SEC_P1_INTRA);   // host time of issuing the look-ahead
+            plan_sms_ = sm_count_ - 1;
+            stage_partner_search(nb, B, cur, cb.qid.p + (nq - 1), st2_);
+            plan_sms_ = 0;
+        }
         sec(-1);
         fetch_ctl();
         cb.valid = false;
@@ -1375,6 +1425,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
     else if (s == "qt") o.qt = value;
     else if (s == "capq") o.capq = value;
     else if (s == "lookahead") o.lookahead = value;
+    else if (s == "filter") o.filter = value;
     else if (s == "kb") o.kb = value;
     else if (s == "waves") o.waves = value;
     else if (s == "p2_chunk") o.p2_chunk = value;

@@ -24,6 +24,8 @@
 #define HMK_MAXLEN 36          // longest sequence the packed kernels take (three words)
 #define HMK_NWMAX 10           // most 32-bit words per profile entry (long kernel)
 #define HMK_LONG_THREADS 512
+#define HMK_FPW 868            // words per profile with the filter sub-table: 3 x 288 + 4 (the +16 B skews the tables over the banks)
+#define HMK_CQCAP 64           // filter kernel: candidate-queue entries per warp
 #ifndef HMK_BULK_THREADS
 #define HMK_BULK_THREADS 768
 #endif
@@ -45,6 +47,7 @@ struct HmkScheme {
     int32_t prof_words;  // one word: nw * HMK_MAXL1 * 24 (fixed row stride so LDS offsets are immediates); long: nw * L * 24
     int32_t words;       // 64-bit words per packed sequence (1..3)
     int32_t long_layout; // 0: prof[t][h][j][r] for hmk_bulk_fast, 1: prof[t][j][h][r] for hmk_bulk_long
+    int32_t filter;      // 1: u8 lanes, nw == 2, and a third sub-table with pair-of-diagonals upper bounds (HMK_FPW words per profile)
 };
 
 // ---------------------------------------------------------------- profile builder
@@ -82,10 +85,10 @@ __global__ void hmk_build_profiles(HmkScheme sc, int mode, const int32_t* __rest
         const int j = sc.long_layout ? e / (HMK_NRES * sc.nw) : (e / HMK_NRES) % HMK_MAXL1;
         const int h = sc.long_layout ? (e / HMK_NRES) % sc.nw : e / (HMK_NRES * HMK_MAXL1);
         uint32_t word = 0;
-        if (j >= n) { out[e] = 0; continue; }
-        for (int b = 0; b < lanes_per_word; b++) {
-            const int lam = h * lanes_per_word + b;
-            if (lam > 2 * sc.X + d) continue;
+        if (j >= n || h > sc.nw || (h == sc.nw && !sc.filter)) { out[e] = 0; continue; }
+        // value of lane `lam` at (j, r): biased cell + (at position 0) the lane constant
+        auto lane_val = [&](int lam) -> int32_t {
+            if (lam > 2 * sc.X + d) return 0;
             const int k = lam - sc.X;
             int32_t val = 0;
             const int pi = ps ? j - k : j + k;
@@ -95,7 +98,31 @@ __global__ void hmk_build_profiles(HmkScheme sc, int mode, const int32_t* __rest
                 const int pen = d * sc.P + (k < 0 ? -2 * k * sc.P : 0) + (k > d ? 2 * (k - d) * sc.P : 0);
                 val += pen + sc.half - sc.T - cells * sc.bias;
             }
-            word |= ((uint32_t)val & ((1u << lane_bits) - 1u)) << (b * lane_bits);
+            return val;
+        };
+        if (h < sc.nw) {
+            for (int b = 0; b < lanes_per_word; b++)
+                word |= ((uint32_t)lane_val(h * lanes_per_word + b) & ((1u << lane_bits) - 1u)) << (b * lane_bits);
+        } else {
+            // filter sub-table (u8): byte g bounds the lanes of group g from above (max per position, so the
+            // sum bounds every lane's sum): "no filter byte reaches 128" proves "no diagonal reaches T".
+            // Positions outside a diagonal count as score 0 here (value `bias`, the lane constant is
+            // reduced to match) -- with 0 there, the maximum would pick up the neighbour's real cell.
+            // One length only (d == 0).  Group g = lanes 2g, 2g+1: bytes 0,1 bound exact word 0, bytes 2,3 word 1.
+            const int nl = 2 * sc.X + 1;
+            for (int g = 0; g < 4; g++) {
+                const int l0 = 2 * g, l1 = l0 + 1 < nl ? l0 + 1 : nl - 1;
+                int32_t best = 0;
+                for (int lam = l0; lam <= l1; lam++) {
+                    const int k = lam - sc.X;
+                    const int pi = ps ? j - k : j + k;
+                    int32_t val = sc.bias;
+                    if (pi >= 0 && pi < m) val += ps ? sM[sp[pi] * HMK_NRES + r] : sM[r * HMK_NRES + sp[pi]];
+                    if (j == 0) val += 2 * sc.P * (k < 0 ? -k : k) + sc.half - sc.T - n * sc.bias;
+                    best = val > best ? val : best;
+                }
+                word |= ((uint32_t)best & 0xffu) << (8 * g);
+            }
         }
         out[e] = word;
     }
@@ -355,10 +382,10 @@ __host__ __device__ inline size_t hmk_carve_bytes(int qt, int kb, int threads, b
 // ---------------------------------------------------------------- fast bulk kernel
 #define HMK_ROWB (HMK_NRES * 4)                    // bytes of one (h, j) row: 24 residues x u32
 
-template <int NW, int MODE>
+template <int NW, int MODE, bool FSTRIDE = false>
 __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __grid_constant__ HmkBulkArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr uint32_t PWB = NW * HMK_MAXL1 * HMK_ROWB;   // bytes per profile (compile time)
+    constexpr uint32_t PWB = FSTRIDE ? HMK_FPW * 4 : NW * HMK_MAXL1 * HMK_ROWB;   // bytes per profile (compile time)
     const int qtile = blockIdx.x % a.nqt, stripe = blockIdx.x / a.nqt;
     const int q0 = qtile * a.qt;
     const int qn = min(a.qt, a.nq - q0);
@@ -463,6 +490,160 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __gri
                 atomicAdd(a.pair_counter + 2, scored / qn * to);
             }
         }
+    }
+    if (MODE == HMK_MODE_TOPK) {
+        __syncthreads();
+        hmk_topk_flush(a, tk, q0, qn, stripe);
+    }
+}
+
+// ---------------------------------------------------------------- filter + verify bulk kernel
+// The exact kernel needs 24 shared-memory look-ups per pair and is bound by that pipe.  Here every pair
+// first takes 12 look-ups in a FILTER table whose four u8 lanes bound PAIRS of neighbouring diagonals from
+// above (max of the two exact entries per position); only pairs where some bound reaches the threshold
+// (about 7 % for random 12-mers at T = 20, against 0.3 % real hits) are queued per warp and re-scored
+// exactly, 32 candidates at a time, one per lane.  No false negatives (sum of maxima >= each sum), exact
+// scores for everything that is reported.  u8 lanes, two exact words, lengths <= 12.
+// LT: compile-time length (0 = use sc.L; then the twelve look-ups are predicated, which costs issue slots)
+template <int MODE, int LT>
+__global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __grid_constant__ HmkBulkArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t PWB = HMK_FPW * 4;
+    constexpr uint32_t SUB = HMK_MAXL1 * HMK_ROWB;   // bytes of one sub-table
+    const int qtile = blockIdx.x % a.nqt, stripe = blockIdx.x / a.nqt;
+    const int q0 = qtile * a.qt;
+    const int qn = min(a.qt, a.nq - q0);
+    if (qn <= 0) return;
+    const int L = LT ? LT : a.sc.L;
+    size_t o = ((size_t)a.qt * PWB + 15) & ~(size_t)15;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + o);
+    o += 16;
+    HmkTopkSmem tk;
+    HmkHitQueue hq;
+    hmk_carve(smem_raw + o, a.qt, a.kb, false, tk, hq);
+    o += hmk_carve_bytes(a.qt, a.kb, HMK_BULK_THREADS, false);
+    // candidate queue of this warp: packed word of the database item + entry word (see verify)
+    uint64_t* cqw = reinterpret_cast<uint64_t*>(smem_raw + ((o + 15) & ~(size_t)15)) + (threadIdx.x >> 5) * HMK_CQCAP;
+    uint32_t* cq = reinterpret_cast<uint32_t*>(smem_raw + ((o + 15) & ~(size_t)15) + (size_t)(HMK_BULK_THREADS / 32) * HMK_CQCAP * 8) +
+                   (threadIdx.x >> 5) * HMK_CQCAP;
+    int ccnt = 0;   // warp-uniform
+
+    if (threadIdx.x == 0) hmk_mbar_init(bar, 1);
+    if (MODE == HMK_MODE_TOPK) hmk_topk_init(tk, qn, a.kb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = (uint32_t)qn * PWB;
+        hmk_mbar_expect_tx(bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.prof) + (size_t)q0 * PWB;
+        uint32_t done = 0;
+        while (done < total) {
+            uint32_t n = min(total - done, 32768u);
+            hmk_bulk_g2s(smem_raw + done, src + done, n, bar);
+            done += n;
+        }
+    }
+    hmk_mbar_wait(bar, 0);
+
+    const int i_begin = stripe * a.chunk;
+    const int i_end = min(a.ndb, i_begin + a.chunk);
+    unsigned long long scored = 0;
+    const int32_t dec = a.sc.T - a.sc.half;
+    const unsigned char* sbase = smem_raw;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
+
+    // exact re-scoring of up to 32 queued candidates, one per lane.  entry: bits 24..31 = t, bit 7 / bit 23 =
+    // "a filter byte of exact word 0 / word 1 passed", the other 22 bits = offset in the stripe.  Only the
+    // exact word(s) whose filter bytes passed are summed (both: rare, handled in a divergent tail)
+    auto verify = [&]() {
+        const int n = ccnt < 32 ? ccnt : 32, base = ccnt - n;
+        const bool have = lane < n;
+        const uint32_t ent = have ? cq[base + lane] : 0u;
+        const int t = (int)(ent >> 24);
+        const uint32_t halves = ((ent >> 7) & 1u) | ((ent >> 22) & 2u);
+        const int32_t i = i_begin + (int32_t)((ent & 0x7fu) | ((ent & 0x7fff00u) >> 1));
+        const uint64_t w = have ? cqw[base + lane] : 0ull;
+        const unsigned char* pb = sbase + (uint32_t)t * PWB + ((halves & 1u) ? 0u : SUB);
+        uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+        for (int j = 0; j < HMK_MAXL1; j++)
+            if (j < L) acc0 += *reinterpret_cast<const uint32_t*>(pb + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u);
+        if (halves == 3u) {
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++)
+                if (j < L) acc1 += *reinterpret_cast<const uint32_t*>(pb + SUB + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u);
+        }
+        __syncwarp();
+        const bool hit = have && ((acc0 | acc1) & 0x80808080u) != 0;
+        ccnt = base;
+        const uint32_t mx = __vmaxu4(acc0, acc1);
+        const uint32_t m2 = __vmaxu4(mx, mx >> 16);
+        const uint32_t m1 = (m2 & 0xffu) > ((m2 >> 8) & 0xffu) ? (m2 & 0xffu) : ((m2 >> 8) & 0xffu);
+        hmk_queue_push<MODE>(a, tk, q0, hq, hit, t, hit ? (int32_t)m1 + dec : 0, i);
+    };
+
+    for (int ib = i_begin + (threadIdx.x & ~31); ib < i_end; ib += blockDim.x) {
+        const int i = ib + lane;
+        bool valid = i < i_end;
+        const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
+        if (valid && a.slot && a.slot[id] >= 0) valid = false;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const uint64_t w = valid ? a.packed[id] : 0ull;
+        const unsigned char* rowp[HMK_MAXL1];   // &filter[0][j][residue_j]
+#pragma unroll
+        for (int j = 0; j < HMK_MAXL1; j++)
+            rowp[j] = sbase + 2 * SUB + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u;
+        if (!valid) {   // point at the zero words that end profile 0: the bound stays 0, nothing is queued
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++) rowp[j] = sbase + 3 * SUB;
+        }
+        if (valid) scored += qn;
+        const uint32_t ilocal = (uint32_t)(i - i_begin);
+        uint32_t tI = (ilocal & 0x7fu) | ((ilocal >> 7) << 8);
+
+        auto bound = [&](const int tu) -> uint32_t {
+            uint32_t f = 0;
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++)
+                if (j < L) f += *reinterpret_cast<const uint32_t*>(rowp[j] + tu * PWB);
+            return f;
+        };
+        auto enqueue = [&](const uint32_t tu, const uint32_t f) {
+            const uint32_t top = f & 0x80808080u;
+            const unsigned m = __ballot_sync(0xffffffffu, top != 0);
+            if (m) {
+                if (top) {
+                    const int slot = ccnt + __popc(m & ltmask);
+                    cq[slot] = (tI + (tu << 24)) | ((top | (top >> 8)) & 0x00800080u);
+                    cqw[slot] = w;
+                }
+                ccnt += __popc(m);
+                __syncwarp();
+                if (ccnt >= 32) verify();
+            }
+        };
+
+        int t = 0;
+        for (; t + 4 <= qn; t += 4) {
+            const uint32_t f0 = bound(0), f1 = bound(1), f2 = bound(2), f3 = bound(3);
+            enqueue(0, f0); enqueue(1, f1); enqueue(2, f2); enqueue(3, f3);
+            tI += 4u << 24;
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += 4 * PWB;
+        }
+        for (; t < qn; t++) {
+            const uint32_t f0 = bound(0);
+            enqueue(0, f0);
+            tI += 1u << 24;
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += PWB;
+        }
+    }
+    while (ccnt > 0) verify();
+    if (hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
+    if (a.pair_counter) {
+        for (int s = 16; s > 0; s >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, s);
+        if ((threadIdx.x & 31) == 0 && scored) atomicAdd(a.pair_counter, scored);
     }
     if (MODE == HMK_MODE_TOPK) {
         __syncthreads();
