@@ -123,6 +123,7 @@ enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_R
 struct Options {
     int64_t batch = 0;          // phase-1 queries per batch (0 = three profile tiles)
     int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
+    int64_t reuse = 1;          // 1: phase 2 takes its founder hits from the phase-1 partner searches (symmetric matrices)
     int64_t filter = 1;         // 1: filter + verify kernel where it applies (u8 lanes, two words, one length <= 12)
     int64_t lookahead = 1;      // 1: prepare the next batch's partner search while the current batch resolves
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
@@ -248,6 +249,7 @@ private:
         cudaEvent_t ready = nullptr;
         bool valid = false;      // partner search for the batch starting behind `after` has been issued
         int nq = 0;
+        int batch_id = 0;
     };
     BatchBuf bb_[2];
     cudaStream_t st2_ = nullptr;
@@ -255,6 +257,12 @@ private:
     // ---- phase-1 scratch
     DevBuf<int32_t> d_qid_, d_nq_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_, d_dirty_b_;
+    // phase-1 partner-search hits kept for phase 2 (opt.reuse): buffer, 64-bit counters [0] appended, [1] valid
+    DevBuf<int4> d_xhits_;
+    DevBuf<unsigned long long> d_xcount_;
+    DevBuf<int32_t> d_qbatch_;
+    size_t xhit_want_ = 0;            // entries the last run would have needed
+    bool sym_ = false, reuse_ = false;
     int plan_sms_ = 0;                // SMs a bulk launch may count on (one less while the resolver holds an SM)
     int batch_id_ = 0;
     DevBuf<uint32_t> d_prof_;
@@ -286,6 +294,7 @@ private:
         S.id_of_rank = identity_rank_ ? nullptr : d_id_of_rank_.p;
         S.slot = d_slot_.p; S.rank = d_rank_.p; S.next = d_next_.p;
         S.c_founder = d_cf_.p; S.c_size = d_cs_.p; S.c_count = d_cc_.p; S.c_tail = d_ct_.p;
+        S.qbatch = reuse_ ? d_qbatch_.p : nullptr;
         S.ctl = d_ctl_.p;
         return S;
     }
@@ -407,6 +416,11 @@ void Engine::upload(const hmk_greedy_in* in) {
     CK(cudaMemcpyAsync(d_off_.p, h_off_.data(), sizeof(int32_t) * (n_ + 1), cudaMemcpyHostToDevice, st_));
     if (n_) CK(cudaMemcpyAsync(d_ab_.p, in->abundance, sizeof(int32_t) * n_, cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_M_.p, in->matrix, sizeof(int32_t) * HMK_NRES * HMK_NRES, cudaMemcpyHostToDevice, st_));
+    sym_ = true;   // S(a, b) == S(b, a) for every pair iff the matrix is symmetric (equal lengths transpose it)
+    for (int i = 0; i < HMK_NRES && sym_; i++)
+        for (int j = 0; j < i; j++)
+            if (in->matrix[i * HMK_NRES + j] != in->matrix[j * HMK_NRES + i]) { sym_ = false; break; }
+    xhit_want_ = 0;
     // tie-break rank of the partner search: (abundance desc, id asc); identity when the
     // input is abundance-sorted (order "size", UniqueSequence.java:180)
     identity_rank_ = true;
@@ -687,6 +701,10 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
     a.nq = nq;
     a.packed = d_packed_.p; a.slot = d_slot_.p; a.q_minid = bb.qid.p;
     a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
+    bb.batch_id = ++batch_id_;
+    if (reuse_) {
+        a.xhits = d_xhits_.p; a.xhit_count = d_xcount_.p; a.xhit_cap = d_xhits_.cap; a.xbatch = bb.batch_id;
+    }
     if (!mixed_) {
         if (fast_) launch_profiles(HMK_PROF_QUERY, bb.qid.p, nq, bb.prof.p, sc_, s);
         a.prof = bb.prof.p;
@@ -795,6 +813,16 @@ int Engine::phase1() {
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
     batch_id_ = 0;
+    reuse_ = opt.reuse && sym_ && K_ > 0 && n_ > 1;
+    if (reuse_) {
+        // room for every partner-search hit: the last run's need if known, else ~96 per sequence; a run that
+        // overflows falls back to the separate founder pass in phase 2 and remembers the size it needed
+        size_t want = xhit_want_ ? xhit_want_ + xhit_want_ / 8 : std::max<size_t>((size_t)1 << 20, (size_t)n_ * 96);
+        want = std::min<size_t>(want, (size_t)1 << 30);
+        d_xhits_.reserve(want); d_xcount_.reserve(2); d_qbatch_.reserve(n_);
+        CK(cudaMemsetAsync(d_xcount_.p, 0, 2 * sizeof(unsigned long long), st_));
+        CK(cudaMemsetAsync(d_qbatch_.p, 0xff, sizeof(int32_t) * n_, st_));
+    }
     size_t hit_cap = (size_t)opt.hit_cap;
     d_hits_.reserve(hit_cap);
     bb_[0].valid = bb_[1].valid = false;
@@ -838,7 +866,7 @@ int Engine::phase1() {
         const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * (int)opt.kb + 3) & ~3;
         const int nw = (nq + 31) / 32;
         HmkP1Batch pb{};
-        pb.nq = nq; pb.batch_id = ++batch_id_; pb.qid = d_qid; pb.kb = (int)opt.kb;
+        pb.nq = nq; pb.batch_id = cb.batch_id; pb.qid = d_qid; pb.kb = (int)opt.kb;
         pb.bk_key = cb.bk_key.p; pb.bk_cnt = cb.bk_cnt.p; pb.bk_ovf = cb.bk_ovf.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
         pb.ib = cb.ib.p; pb.ib_stride = ib_stride; pb.ibm = cb.ibm.p; pb.nw = nw;
@@ -962,7 +990,56 @@ void Engine::phase2() {
         }
     };
 
-    if (!mixed_) {
+    // opt.reuse: every (founder, single) pair scoring >= T was already seen by a phase-1 partner search --
+    // the founder was a query of some batch and the single a later singleton of that scan (or the other way
+    // round for a phase-1 orphan), and S is symmetric.  The member check filters the kept hits down to those
+    // pairs (and to scans of batches that were not re-done) instead of scoring founders x singles again.
+    bool reused = false;
+    if (reuse_) {
+        CK(cudaMemcpyAsync(h_scalars_ + 10, d_xcount_.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        unsigned long long nx;
+        memcpy(&nx, h_scalars_ + 10, sizeof(nx));
+        xhit_want_ = (size_t)nx;
+        reused = nx <= d_xhits_.cap;      // else: some hits were dropped -> separate founder pass below
+        if (world_ > 1) {                 // every rank must take the same path
+            d_gcount_.reserve(world_ + 1);
+            int32_t mine = reused ? 1 : 0;
+            CK(cudaMemcpyAsync(d_gcount_.p + world_, &mine, sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            allgather(d_gcount_.p + world_, d_gcount_.p, sizeof(int32_t), st_);
+            std::vector<int32_t> all(world_);
+            CK(cudaMemcpyAsync(all.data(), d_gcount_.p, sizeof(int32_t) * world_, cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            for (int r = 0; r < world_; r++) reused = reused && all[r] != 0;
+        }
+    }
+    if (reused) {
+        sec(SEC_P2_CHECK);
+        for (;;) {
+            CK(cudaMemsetAsync(d_counts_.p + 1, 0, sizeof(unsigned int), st_));
+            CK(cudaMemsetAsync(d_xcount_.p + 1, 0, sizeof(unsigned long long), st_));
+            HmkCheckArgs c{};
+            c.S = state(); c.hits = d_xhits_.p; c.hit_t_is_query = 2; c.xhit_count = d_xcount_.p; c.hit_valid = d_xcount_.p + 1;
+            c.qids = nullptr; c.sidx = d_sidx_.p;
+            c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
+            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
+            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
+            hmk_member_check<<<sm_count_ * 8, 256, 0, st_>>>(c);
+            CK(cudaGetLastError());
+            launches_++;
+            CK(cudaMemcpyAsync(h_scalars_ + 1, d_counts_.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
+            CK(cudaMemcpyAsync(h_scalars_ + 10, d_xcount_.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            ncand = (uint32_t)h_scalars_[1];
+            if (ncand <= cand_cap) break;
+            const size_t nc = ncand + ncand / 16;      // candidates beyond the capacity were only counted: redo
+            d_key_q_.reserve(nc); d_key_c_.reserve(nc); d_cand_score_.reserve(nc);
+            cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
+        }
+        unsigned long long nv;
+        memcpy(&nv, h_scalars_ + 10, sizeof(nv));
+        stats.p2_hits = (int64_t)nv;
+    } else if (!mixed_) {
         // founder profiles (member side), built once: founders are fixed during phase 2
         if (fast_) {
             d_fprof_.reserve((size_t)ncl * sc_.prof_words);
@@ -1426,6 +1503,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
     else if (s == "capq") o.capq = value;
     else if (s == "lookahead") o.lookahead = value;
     else if (s == "filter") o.filter = value;
+    else if (s == "reuse") o.reuse = value;
     else if (s == "kb") o.kb = value;
     else if (s == "waves") o.waves = value;
     else if (s == "p2_chunk") o.p2_chunk = value;

@@ -183,6 +183,11 @@ struct HmkBulkArgs {
     uint64_t* tk_key;          // [nstripes][nq][kb] descending
     int32_t* tk_cnt;           // [nstripes][nq]
     int32_t* tk_ovf;           // [nstripes][nq]
+    // MODE_TOPK, optional: every qualifying hit is also appended here for phase 2 (see Engine::phase2)
+    int4* xhits;               // (profile-side sequence id, thread-side sequence id, score, xbatch)
+    unsigned long long* xhit_count;
+    unsigned long long xhit_cap;
+    int32_t xbatch;
     // MODE_EMIT
     int4* hits;                // (profile index, thread-side sequence id, score, 0)
     unsigned int* hit_count;
@@ -276,21 +281,36 @@ __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopk
             const int e = e0 + lane;
             bool pending = false;
             int tl = 0;
+            int32_t id = 0, sc = 0;
             uint64_t key = 0;
             if (e < n) {
                 const uint64_t v = hq.q[e];
                 tl = (int)(v >> 48);
                 const int32_t i = (int32_t)(uint32_t)v;
-                const int32_t id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
+                id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
+                sc = hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32);
                 pending = !(a.q_minid && id <= a.q_minid[q0 + tl]);   // initialList[index+1 ..] only
-                if (pending) {
-                    const uint32_t rk = a.tierank ? (uint32_t)a.tierank[id] : (uint32_t)id;
-                    key = hmk_key_make(hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32), rk);
-                    // cheap reject without the lock (minkey only grows once the list is full)
-                    if (*(volatile int*)(tk.cnt + tl) >= a.kb && key <= *(volatile uint64_t*)(tk.minkey + tl)) {
-                        tk.ovf[tl] = 1;
-                        pending = false;
+            }
+            if (a.xhits) {   // keep every qualifying hit for phase 2
+                const unsigned xm = __ballot_sync(0xffffffffu, pending);
+                if (xm) {
+                    unsigned long long xb = 0;
+                    const int leader = __ffs(xm) - 1;
+                    if (lane == leader) xb = atomicAdd(a.xhit_count, (unsigned long long)__popc(xm));
+                    xb = __shfl_sync(0xffffffffu, xb, leader);
+                    if (pending) {
+                        const unsigned long long pos = xb + __popc(xm & ((1u << lane) - 1u));
+                        if (pos < a.xhit_cap) a.xhits[pos] = make_int4(a.q_minid[q0 + tl], id, sc, a.xbatch);
                     }
+                }
+            }
+            if (pending) {
+                const uint32_t rk = a.tierank ? (uint32_t)a.tierank[id] : (uint32_t)id;
+                key = hmk_key_make(sc, rk);
+                // cheap reject without the lock (minkey only grows once the list is full)
+                if (*(volatile int*)(tk.cnt + tl) >= a.kb && key <= *(volatile uint64_t*)(tk.minkey + tl)) {
+                    tk.ovf[tl] = 1;
+                    pending = false;
                 }
             }
             unsigned m;
@@ -941,6 +961,9 @@ struct HmkCheckArgs {
     const unsigned int* hit_count;
     unsigned int hit_cap;
     int32_t hit_t_is_query;      // 1: hit.x = query index, hit.y = founder's id; 0: hit.x = cluster slot, hit.y = query's id
+                                 // 2: phase-1 partner-search hits (xhits): (profile-side id, thread-side id, score, batch)
+    const unsigned long long* xhit_count;   // mode 2: number of entries in hits
+    unsigned long long* hit_valid;          // mode 2: counts the hits that are (founder, single) pairs of valid batches
     const int32_t* qids;         // phase 1: query index -> sequence id
     const int32_t* sidx;         // phase 2: sequence id -> index in the singles list
     // phase 1 output: per-query arrays ac_slot/ac_score[qi * capq + k], k < ac_cnt[qi]
@@ -961,14 +984,28 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
     hmk_load_matrix_smem(sM, a.S.M);
     HmkScalar sc;
     sc.packed = a.packed; sc.sM = sM; sc.L = a.L;
-    const unsigned int nh = min(*a.hit_count, a.hit_cap);
-    long long npairs = 0;
-    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < nh; e += gridDim.x * blockDim.x) {
+    const size_t nh = a.hit_t_is_query == 2 ? (size_t)*a.xhit_count : (size_t)min(*a.hit_count, a.hit_cap);
+    long long npairs = 0, nvalid = 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nh; e += (size_t)gridDim.x * blockDim.x) {
         const int4 h = a.hits[e];
-        // phase 1: (query index, founder's sequence id); phase 2: (founder = cluster slot, query's sequence id)
-        const int qi = a.hit_t_is_query ? h.x : a.sidx[h.y];
-        const int c = a.hit_t_is_query ? a.S.slot[h.y] : h.x;
-        const int32_t q = a.hit_t_is_query ? a.qids[qi] : h.y;
+        int qi, c;
+        int32_t q;
+        if (a.hit_t_is_query == 2) {
+            // S is symmetric here (checked by the host), so the partner-search score of (x, y) is the founder
+            // score of either role assignment; the batch tag drops scans of batches that were re-done
+            if (a.S.qbatch[h.x] != h.w) continue;
+            const int32_t sx = a.S.slot[h.x], sy = a.S.slot[h.y];
+            if (sx >= 0 && sy < 0 && a.S.c_founder[sx] == h.x) { c = sx; q = h.y; }
+            else if (sy >= 0 && sx < 0 && a.S.c_founder[sy] == h.y) { c = sy; q = h.x; }
+            else continue;
+            qi = a.sidx[q];
+            nvalid++;
+        } else {
+            // phase 1: (query index, founder's sequence id); phase 2: (founder = cluster slot, query's sequence id)
+            qi = a.hit_t_is_query ? h.x : a.sidx[h.y];
+            c = a.hit_t_is_query ? a.S.slot[h.y] : h.x;
+            q = a.hit_t_is_query ? a.qids[qi] : h.y;
+        }
         int32_t cl = h.z;
         bool ok = true;
         for (int32_t m = a.S.next[a.S.c_founder[c]]; m >= 0; m = a.S.next[m]) {
@@ -997,6 +1034,10 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
     }
     for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
     if ((threadIdx.x & 31) == 0 && npairs) atomicAdd((unsigned long long*)&a.S.ctl->scalar_pairs, (unsigned long long)npairs);
+    if (a.hit_t_is_query == 2) {
+        for (int s = 16; s > 0; s >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, s);
+        if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd(a.hit_valid, (unsigned long long)nvalid);
+    }
 }
 
 // ---------------------------------------------------------------- phase-1 resolver
@@ -1473,6 +1514,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         steps++;
         unproc--;
         cur = q + 1;
+        if (lane == 0 && S.qbatch) S.qbatch[q] = B.batch_id;
         __syncwarp();
         HMK_TICK(5);   // decision + apply
     }

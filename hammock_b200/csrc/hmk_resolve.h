@@ -30,6 +30,7 @@ struct HmkState {
     int32_t* c_size;    // [K]  abundance-weighted Cluster.size()
     int32_t* c_count;   // [K]  getUniqueSize()
     int32_t* c_tail;    // [K]
+    int32_t* qbatch;    // [n]  id of the phase-1 batch in which the sequence was resolved as a query (-1: never); may be NULL
     HmkCtl* ctl;
 };
 

@@ -42,7 +42,17 @@ def _case(rng, mats, names):
     if rng.random() < 0.5:
         opts = {"batch": int(rng.choice([1, 2, 5, 17, 64])), "kb": int(rng.choice([1, 2, 8])), "capq": int(rng.choice([1, 4, 256])),
                 "p2_window": int(rng.choice([1, 7, 64, 65536])), "lookahead": int(rng.integers(0, 2))}
-    return d, mats[m], T, max(X, 0), P, K, opts, (n, lo, hi, m)
+    if rng.random() < 0.4:      # the older code paths stay covered: exact packed kernel, separate phase-2 founder pass
+        opts = dict(opts, filter=int(rng.integers(0, 2)), reuse=int(rng.integers(0, 2)))
+    M = mats[m]
+    if rng.random() < 0.12:     # asymmetric matrix: S(a, b) != S(b, a) for equal lengths, phase-2 hit reuse must switch off
+        M = M.copy()
+        for _ in range(int(rng.integers(1, 6))):
+            i, j = (int(v) for v in rng.integers(0, 20, size=2))
+            if i != j:
+                M[i, j] += int(rng.integers(1, 4))
+        m = m + "+asym"
+    return d, M, T, max(X, 0), P, K, opts, (n, lo, hi, m)
 
 
 def test_fuzz_against_oracle(golden_dir):

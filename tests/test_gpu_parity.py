@@ -183,7 +183,7 @@ def test_musi_reference_interface(golden_dir, blosum62):
         assert c.size() == int(z["abundance"][mem].sum())
 
 
-@pytest.mark.parametrize("opts", [{}, {"batch": 48, "kb": 2}])
+@pytest.mark.parametrize("opts", [{}, {"batch": 48, "kb": 2}, {"reuse": 0}])
 def test_antibodies_golden_gpu(golden_dir, blosum62, opts):
     z = np.load(os.path.join(golden_dir, "antibodies.npz"))
     T, X, P, K = (int(v) for v in z["params"])
@@ -193,7 +193,8 @@ def test_antibodies_golden_gpu(golden_dir, blosum62, opts):
     assert len(bad) == 0, (bad[:10], G.cluster_id[bad[:10]], z["cluster_id"][bad[:10]])
     assert (G.member_rank == z["member_rank"]).all() and (G.result_order == z["result_order"]).all()
     assert (st["p1_steps"], st["p1_joins"], st["p1_new_clusters"]) == (1923, 72, 1851)
-    assert st["bulk_pairs"] + st["scalar_pairs"] >= 140546010 + 130649021   # >= the reference's early-exit count
+    if opts.get("reuse") == 0:   # every founder x single pair is scored again in phase 2
+        assert st["bulk_pairs"] + st["scalar_pairs"] >= 140546010 + 130649021   # >= the reference's early-exit count
 
 
 SYNTH_CASES = [
@@ -212,6 +213,11 @@ SYNTH_CASES = [
     (2000, 13, 18, "blosum45", 0, None, False, {"batch": 40}),     # mixed lengths on the long kernel
     (1500, 20, 20, "blosum62", 0, None, False, {"force_generic": 1}),
     (2000, 7, 30, "blosum50", 0, None, False, {}),
+    (4000, 12, 12, "blosum62", 0, None, False, {"filter": 0}),             # exact packed kernel instead of filter + verify
+    (4000, 12, 12, "blosum62", 0, None, False, {"reuse": 0}),              # separate founder pass in phase 2
+    (3000, 7, 12, "blosum62", 0, None, False, {"reuse": 0, "batch": 24}),
+    (3000, 10, 10, "blosum62", -1, None, False, {"batch": 8, "kb": 1}),     # truncated partner lists -> restarts, hits of re-done batches
+    (3000, 11, 11, "blosum62", 0, 200, True, {"batch": 20, "kb": 2}),
 ]
 
 
