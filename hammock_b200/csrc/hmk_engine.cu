@@ -240,6 +240,7 @@ private:
     struct BatchBuf {
         DevBuf<int32_t> qid, nq_dev, tk_cnt, tk_ovf, bk_cnt, bk_ovf, gk_cnt, gk_ovf;
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
+        DevBuf<unsigned long long> gmin;   // per query: published lower bound of the kb-th best key (prunes top-k insertions)
         DevBuf<uint32_t> prof;
         DevBuf<uint32_t> prof_len[HMK_MAXLEN + 1], pcells[HMK_MAXLEN + 1], pops[HMK_MAXLEN + 1];   // mixed lengths: per thread-side length
         // state-independent inputs of the resolver: intra-batch scores (+ bit mask), partner candidate ids and
@@ -702,6 +703,9 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
     a.packed = d_packed_.p; a.slot = d_slot_.p; a.q_minid = bb.qid.p;
     a.tierank = identity_rank_ ? nullptr : d_tierank_.p;
     bb.batch_id = ++batch_id_;
+    bb.gmin.reserve(HMK_MAXBATCH);
+    CK(cudaMemsetAsync(bb.gmin.p, 0, sizeof(unsigned long long) * nq, s));
+    a.tk_gmin = bb.gmin.p;
     if (reuse_) {
         a.xhits = d_xhits_.p; a.xhit_count = d_xcount_.p; a.xhit_cap = d_xhits_.cap; a.xbatch = bb.batch_id;
     }

@@ -183,6 +183,8 @@ struct HmkBulkArgs {
     uint64_t* tk_key;          // [nstripes][nq][kb] descending
     int32_t* tk_cnt;           // [nstripes][nq]
     int32_t* tk_ovf;           // [nstripes][nq]
+    unsigned long long* tk_gmin;   // optional [nq], zeroed: lower bound of the kb-th best key over ALL stripes (published by
+                                   // every CTA whose list is full) -- hits below it cannot reach the merged list
     // MODE_TOPK, optional: every qualifying hit is also appended here for phase 2 (see Engine::phase2)
     int4* xhits;               // (profile-side sequence id, thread-side sequence id, score, xbatch)
     unsigned long long* xhit_count;
@@ -226,7 +228,7 @@ __device__ __forceinline__ uint64_t hmk_hit_pack(int tl, int32_t score, int32_t 
 
 // executed by ONE lane of a warp at a time (the others wait at a ballot), so the spin only
 // ever contends with other warps
-__device__ __forceinline__ void hmk_topk_insert_locked(const HmkTopkSmem& s, int t, int kb, uint64_t key) {
+__device__ __forceinline__ void hmk_topk_insert_locked(const HmkTopkSmem& s, int t, int kb, uint64_t key, unsigned long long* gmin) {
     volatile uint64_t* keys = s.key + (size_t)t * kb;
     volatile uint64_t* mink = s.minkey + t;
     volatile int* cnt = s.cnt + t;
@@ -240,6 +242,7 @@ __device__ __forceinline__ void hmk_topk_insert_locked(const HmkTopkSmem& s, int
             uint64_t m = keys[0];
             for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; m = v < m ? v : m; }
             *mink = m;
+            if (gmin) atomicMax(gmin, (unsigned long long)m);
         }
         *cnt = c;
     } else {
@@ -252,6 +255,7 @@ __device__ __forceinline__ void hmk_topk_insert_locked(const HmkTopkSmem& s, int
             m = keys[0];
             for (int i = 1; i < kb; i++) { uint64_t v = keys[i]; m = v < m ? v : m; }
             *mink = m;
+            if (gmin) atomicMax(gmin, (unsigned long long)m);
         }
     }
     __threadfence_block();
@@ -307,8 +311,10 @@ __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopk
             if (pending) {
                 const uint32_t rk = a.tierank ? (uint32_t)a.tierank[id] : (uint32_t)id;
                 key = hmk_key_make(sc, rk);
-                // cheap reject without the lock (minkey only grows once the list is full)
-                if (*(volatile int*)(tk.cnt + tl) >= a.kb && key <= *(volatile uint64_t*)(tk.minkey + tl)) {
+                // cheap reject without the lock (minkey only grows once the list is full; tk_gmin is some
+                // stripe's kb-th best key, so at least kb better hits exist)
+                if ((a.tk_gmin && key < __ldcg(a.tk_gmin + q0 + tl)) ||
+                    (*(volatile int*)(tk.cnt + tl) >= a.kb && key <= *(volatile uint64_t*)(tk.minkey + tl))) {
                     tk.ovf[tl] = 1;
                     pending = false;
                 }
@@ -316,7 +322,7 @@ __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopk
             unsigned m;
             while ((m = __ballot_sync(0xffffffffu, pending)) != 0) {
                 if (lane == __ffs(m) - 1) {
-                    hmk_topk_insert_locked(tk, tl, a.kb, key);
+                    hmk_topk_insert_locked(tk, tl, a.kb, key, a.tk_gmin ? a.tk_gmin + q0 + tl : nullptr);
                     pending = false;
                 }
             }
