@@ -272,17 +272,22 @@ def main():
         ops_per_s = alone["bulk_ops"] / bulk_s
         ncu_traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_bulk_fast_full.json")) as f:
-                for l in json.load(f)["launches"]:
-                    if "<2, 0>" in l["Kernel Name"]:
-                        # units in that file: read in Mbyte, write in byte
-                        ncu_traffic = {"bytes_per_launch": float(l["dram__bytes_read.sum"]) * 1e6 + float(l["dram__bytes_write.sum"]),
-                                       "algorithmic_bytes_per_launch": 12 * n,   # 8 B packed word + 4 B slot flag per database item
-                                       "source": "profiles/r01_ncu_bulk_fast_full.json (ncu --set full, partner-search launch)"}
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_bulk_filter_full.json")) as f:
+                prof = json.load(f)
+            for l in prof["launches"]:
+                if "hmk_bulk_filter<0" in l["Kernel Name"].replace("(int)", ""):
+                    def _b(key):   # ncu picks a unit per column
+                        u = prof["units"][key]
+                        return float(l[key]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                    ncu_traffic = {"bytes_per_launch": _b("dram__bytes_read.sum") + _b("dram__bytes_write.sum"),
+                                   # 8 B packed word + 4 B singleton flag per database item, 16 B per kept hit (0.26 % of pairs)
+                                   "algorithmic_bytes_per_launch": 12 * n + 16 * 0.0026 * n * stats["p1_steps"] / max(stats["p1_batches"], 1),
+                                   "source": "profiles/r01_ncu_bulk_filter_full.json (ncu --set full, one partner-search launch)"}
+                    break
         except Exception:
             pass
         peak = peaks["int32_iadd3_per_s"]
-        lds_bytes = alone["bulk_pairs"] * 12 * 2 * 4          # L positions x NW words x 4 B per pair
+        lds_bytes = alone["bulk_pairs"] * 12 * 4              # filter pass: L positions x one u32 word per pair (verify look-ups not counted)
         line = {
             "metric": METRIC, "value": n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -294,9 +299,13 @@ def main():
                     "d2h_bytes_per_step": int(out.cluster_id.nbytes + out.member_rank.nbytes + out.result_order.nbytes)},
             "gpu_launches": int(stats["total_launches"]) * args.steps,
             "roofline": {
-                "kernel": "hmk_bulk_fast<2,*> (packed gapless scorer, partner search + founder filter)",
+                "kernel": "hmk_bulk_filter<*,12> (packed gapless scorer, filter + exact verify: partner search and cluster search; "
+                          "the small dense tables use hmk_bulk_fast<2,2>)",
                 "bound": "int_alu", "unit": "Gop/s (int32)",
                 "achieved": ops_per_s / 1e9, "peak": peak / 1e9, "frac": ops_per_s / peak,
+                "note": "achieved = algorithmic int ops (79 per pair: 72 cell adds + 7 shift maxima) / launch time. It exceeds the "
+                        "scalar-ALU peak because one u32 add carries 4 u8 diagonals and the filter pass bounds 2 diagonals per "
+                        "lane; the pipe that binds the kernel is shared memory, see binding_pipe",
                 "peak_source": "measured live: dependent-free IADD3 stream (hmk_measure_peaks); "
                                f"IADD3+IMAD dual-pipe stream reaches {peaks['int32_mix_per_s'] / 1e9:.0f} Gop/s",
                 "measured": "kernels timed alone: two extra steps with the phase-1 look-ahead switched off, CUDA events "

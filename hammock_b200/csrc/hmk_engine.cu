@@ -811,7 +811,7 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
 
 int Engine::phase1() {
     int B = (int)opt.batch;
-    if (B <= 0) B = fast_ ? (sc_.filter ? 5 : 3) * qt_max() : 192;   // measured optimum on the 1 M workload
+    if (B <= 0) B = fast_ ? (sc_.filter ? 8 : 3) * qt_max() : 192;   // measured optimum on the 1 M workload
     B = std::max(1, std::min(B, HMK_MAXBATCH));
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
@@ -943,6 +943,10 @@ void Engine::phase2() {
     d_key_q_.reserve(cand_cap); d_key_c_.reserve(cand_cap); d_cand_score_.reserve(cand_cap);
     cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
     size_t ncand = 0;
+    // candidate keys: two tight fields; 2^bits > count, so the all-ones padding keys of the multi-GPU exchange
+    // stay above every real key
+    auto bits_for = [](int x) { int b = 1; while ((1ll << b) <= (long long)x) b++; return b; };
+    const int cbits = bits_for(ncl), qbits = bits_for(ns);
     CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
     const int chunk = (int)std::max<int64_t>(1024, opt.p2_chunk);
     // this rank's share of the phase-2 queries (all of them on one GPU)
@@ -981,7 +985,7 @@ void Engine::phase2() {
                 c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
                 c.hit_t_is_query = 0; c.qids = nullptr; c.sidx = d_sidx_.p;
                 c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
-                c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
+                c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits; c.qbits = qbits;
                 c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
                 hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
                 CK(cudaGetLastError());
@@ -1026,7 +1030,7 @@ void Engine::phase2() {
             c.S = state(); c.hits = d_xhits_.p; c.hit_t_is_query = 2; c.xhit_count = d_xcount_.p; c.hit_valid = d_xcount_.p + 1;
             c.qids = nullptr; c.sidx = d_sidx_.p;
             c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
-            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0;
+            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits; c.qbits = qbits;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
             hmk_member_check<<<sm_count_ * 8, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
@@ -1114,19 +1118,19 @@ void Engine::phase2() {
     const int nc = (int)ncand;
     const int ncp = (int)ncand_padded_;   // >= nc: padded entries carry key ~0 and sort to the end
     // group by query (ascending cluster inside a query) and by cluster (ascending query inside a cluster)
-    sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, 64);
+    sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, cbits + qbits);
     d_cq_c_.reserve(nc); d_cc_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2);
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, d_cq_c_.p);
-    hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, d_qstart_.p);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p);
+    hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, cbits, d_qstart_.p);
     {
         size_t bytes = 0;
         d_key_tmp_.reserve(ncp);
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, 64, st_));
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, cbits + qbits, st_));
         d_cub_.reserve(bytes);
-        CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, 64, st_));
+        CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, cbits + qbits, st_));
     }
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, d_cc_q_.p);
-    hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, d_cstart_.p);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, qbits, d_cc_q_.p);
+    hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, qbits, d_cstart_.p);
     CK(cudaGetLastError());
     launches_ += 8;
     d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_wlo_.reserve(ncl); d_tent_.reserve(nc);

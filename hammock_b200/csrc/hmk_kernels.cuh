@@ -619,10 +619,6 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
 #pragma unroll
         for (int j = 0; j < HMK_MAXL1; j++)
             rowp[j] = sbase + 2 * SUB + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u;
-        if (!valid) {   // point at the zero words that end profile 0: the bound stays 0, nothing is queued
-#pragma unroll
-            for (int j = 0; j < HMK_MAXL1; j++) rowp[j] = sbase + 3 * SUB;
-        }
         if (valid) scored += qn;
         const uint32_t ilocal = (uint32_t)(i - i_begin);
         uint32_t tI = (ilocal & 0x7fu) | ((ilocal >> 7) << 8);
@@ -635,7 +631,8 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
             return f;
         };
         auto enqueue = [&](const uint32_t tu, const uint32_t f) {
-            const uint32_t top = f & 0x80808080u;
+            // lanes without an item look up residue 0 (same row as everybody else: no bank conflict) and are masked here
+            const uint32_t top = valid ? f & 0x80808080u : 0u;
             const unsigned m = __ballot_sync(0xffffffffu, top != 0);
             if (m) {
                 if (top) {
@@ -975,8 +972,9 @@ struct HmkCheckArgs {
     // phase 1 output: per-query arrays ac_slot/ac_score[qi * capq + k], k < ac_cnt[qi]
     int32_t* ac_cnt; int32_t* ac_slot; int32_t* ac_score; int32_t capq;
     // phase 2 output: flat candidate arrays
-    unsigned long long* cand_key_q;   // (query index << 32) | slot
-    unsigned long long* cand_key_c;   // (slot << 32) | query index
+    unsigned long long* cand_key_q;   // (query index << cbits) | slot      -- fields packed tight: the radix sorts only
+    unsigned long long* cand_key_c;   // (slot << qbits) | query index         touch cbits + qbits bits
+    int32_t cbits, qbits;
     int32_t* cand_score;
     unsigned int* cand_count;
     unsigned int cand_cap;
@@ -1033,8 +1031,8 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         if (pos >= a.cand_cap) continue;
         {
             const uint32_t gq = (uint32_t)qi;
-            a.cand_key_q[pos] = ((unsigned long long)gq << 32) | (uint32_t)c;
-            a.cand_key_c[pos] = ((unsigned long long)(uint32_t)c << 32) | gq;
+            a.cand_key_q[pos] = ((unsigned long long)gq << a.cbits) | (uint32_t)c;
+            a.cand_key_c[pos] = ((unsigned long long)(uint32_t)c << a.qbits) | gq;
             a.cand_score[pos] = cl;
         }
     }
@@ -1777,20 +1775,20 @@ __global__ void hmk_bucket_by_length(const int32_t* __restrict__ ids, int n, con
     out[(size_t)len * stride + k] = id;
 }
 
-// first index whose key's high half is >= s, for s = 0..nseg (start[nseg] = n)
-__global__ void hmk_segment_starts(const unsigned long long* __restrict__ keys, int n, int nseg, int32_t* __restrict__ start) {
+// first index whose key's high field (bits >= shift) is >= s, for s = 0..nseg (start[nseg] = n)
+__global__ void hmk_segment_starts(const unsigned long long* __restrict__ keys, int n, int nseg, int shift, int32_t* __restrict__ start) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > nseg) return;
     int lo = 0, hi = n;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if ((int64_t)(keys[mid] >> 32) < (int64_t)s) lo = mid + 1; else hi = mid;
+        if ((int64_t)(keys[mid] >> shift) < (int64_t)s) lo = mid + 1; else hi = mid;
     }
     start[s] = lo;
 }
-__global__ void hmk_split_keys_lo(const unsigned long long* __restrict__ keys, int n, int32_t* __restrict__ lo) {
+__global__ void hmk_split_keys_lo(const unsigned long long* __restrict__ keys, int n, int shift, int32_t* __restrict__ lo) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) lo[i] = (int32_t)(uint32_t)keys[i];
+    if (i < n) lo[i] = (int32_t)(uint32_t)(keys[i] & ((1ull << shift) - 1ull));
 }
 
 __global__ void hmk_finalize(int n, const int32_t* __restrict__ slot, const int32_t* __restrict__ rank,
