@@ -27,6 +27,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include "../../include/hammock_b200.h"
 #include "hmk_kernels.cuh"
@@ -246,7 +247,7 @@ private:
         // state-independent inputs of the resolver: intra-batch scores (+ bit mask), partner candidate ids and
         // their scores against every batch query
         DevBuf<int32_t> ib, pcand, pd;
-        DevBuf<uint32_t> ibm;
+        DevBuf<uint32_t> ibm, ibm2;
         cudaEvent_t ready = nullptr;
         bool valid = false;      // partner search for the batch starting behind `after` has been issued
         int nq = 0;
@@ -327,6 +328,20 @@ public:
 private:
     void fetch_ctl() {
         CK(cudaMemcpyAsync(h_ctl_, d_ctl_.p, sizeof(HmkCtl), cudaMemcpyDeviceToHost, st_));
+        if (getenv("HMK_DEBUG_HANG")) {      // debugging aid: report where the device is stuck instead of waiting forever
+            for (int i = 0; i < 5000 && cudaStreamQuery(st_) == cudaErrorNotReady; i++) usleep(1000);
+            if (cudaStreamQuery(st_) == cudaErrorNotReady) {
+                cudaStream_t s3;
+                cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking);
+                cudaMemcpyAsync(h_ctl_, d_ctl_.p, sizeof(HmkCtl), cudaMemcpyDeviceToHost, s3);
+                cudaStreamSynchronize(s3);
+                fprintf(stderr, "HANG: side stream %s; ctl cur %d ncl %d unproc %d steps %d dbg %lld %lld %lld %lld\n",
+                        cudaStreamQuery(st2_) == cudaErrorNotReady ? "busy" : "idle", h_ctl_->cur, h_ctl_->ncl, h_ctl_->unproc_alive,
+                        h_ctl_->steps, (long long)h_ctl_->dbg[0], (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3]);
+                fflush(stderr);
+                _exit(3);
+            }
+        }
         CK(cudaStreamSynchronize(st_));
     }
     int phase1();
@@ -779,7 +794,7 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
     }
     // intra-batch scores S(member = q_b2, query = q_b); row strides padded to 16 bytes for the TMA row prefetch
     const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * kb + 3) & ~3, nw = (nq + 31) / 32;
-    bb.ib.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH + 4)); bb.ibm.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH / 32));
+    bb.ib.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH + 4)); bb.ibm.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH / 32)); bb.ibm2.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH / 32));
     bb.pcand.reserve((size_t)nq * kb); bb.pd.reserve((size_t)nq * (pd_stride + 4));
     {
         HmkBulkArgs d{};
@@ -788,7 +803,7 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         d.dense = bb.ib.p; d.dense_stride = ib_stride;
         launch_bulk(HMK_MODE_DENSE, d, bb.qid.p, 1, s);
     }
-    hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, s>>>(nq, nw, T_, bb.ib.p, ib_stride, bb.ibm.p);
+    hmk_ib_mask<<<(nq * nw + 127) / 128, 128, 0, s>>>(nq, nw, T_, bb.ib.p, ib_stride, bb.ibm.p, kb, bb.bk_key.p, bb.bk_cnt.p, bb.ibm2.p);
     launches_++;
     // S(partner candidate, query) for every candidate of the batch: clusters born inside the
     // batch have one of these as their second member
@@ -813,6 +828,14 @@ int Engine::phase1() {
     int B = (int)opt.batch;
     if (B <= 0) B = fast_ ? (sc_.filter ? 8 : 3) * qt_max() : 192;   // measured optimum on the 1 M workload
     B = std::max(1, std::min(B, HMK_MAXBATCH));
+    opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
+    {   // the resolver keeps the whole batch's bookkeeping in shared memory
+        const size_t avail = smem_optin_ - 3 * HMK_HASH_SIZE * 4 - 1024;
+        auto need = [&](int b) {
+            return hmk_resolve_fixed_bytes(b, (b + 31) / 32, (int)opt.kb, (b + 3) & ~3, (b * (int)opt.kb + 3) & ~3) + 64;
+        };
+        while (B > 32 && need(B) > avail) B -= 32;
+    }
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
@@ -873,7 +896,7 @@ int Engine::phase1() {
         pb.nq = nq; pb.batch_id = cb.batch_id; pb.qid = d_qid; pb.kb = (int)opt.kb;
         pb.bk_key = cb.bk_key.p; pb.bk_cnt = cb.bk_cnt.p; pb.bk_ovf = cb.bk_ovf.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
-        pb.ib = cb.ib.p; pb.ib_stride = ib_stride; pb.ibm = cb.ibm.p; pb.nw = nw;
+        pb.ib = cb.ib.p; pb.ib_stride = ib_stride; pb.ibm = cb.ibm.p; pb.ibm2 = cb.ibm2.p; pb.nw = nw;
         pb.pcand = cb.pcand.p;
         pb.pd = cb.pd.p; pb.pd_stride = pd_stride;
         // the resolver must not run on truncated hit lists: checked on the host first
@@ -911,6 +934,9 @@ int Engine::phase1() {
         fetch_ctl();
         cb.valid = false;
         const int st = h_ctl_->status;
+        if (getenv("HMK_DEBUG_BATCH"))
+            fprintf(stderr, "batch %d nq %d: cur %d ncl %d unproc %d status %d steps %d ahead %d\n", cb.batch_id, nq, h_ctl_->cur, h_ctl_->ncl,
+                    h_ctl_->unproc_alive, st, h_ctl_->steps, (int)ahead);
         if (st != HMK_P1_CONTINUE && nb.valid) {     // the look-ahead batch does not follow this one after all
             CK(cudaStreamSynchronize(st2_));
             nb.valid = false;
@@ -1260,8 +1286,11 @@ int Engine::run() {
     stats.bulk_pairs = (int64_t)pc[0];
     stats.scalar_pairs = h_ctl_->scalar_pairs;
     if (getenv("HMK_DEBUG_TIMING"))
-        fprintf(stderr, "resolver cycles: staging %lld rowwait %lld bpart %lld static %lld eval %lld apply %lld loop-top %lld\n", (long long)h_ctl_->dbg[0],
-                (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3], (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5], (long long)h_ctl_->dbg[7]);
+        fprintf(stderr, "resolver: %lld windows applied %lld lanes, %lld sequential steps\n", (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5],
+                (long long)h_ctl_->dbg[6]);
+    if (getenv("HMK_DEBUG_TIMING"))
+        fprintf(stderr, "resolver cycles: staging %lld window(rest) %lld bpart %lld static %lld eval %lld apply %lld window(pick) %lld window(bounds) %lld\n", (long long)h_ctl_->dbg[0],
+                (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3], (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5], (long long)h_ctl_->dbg[7], (long long)h_ctl_->dbg[6]);
     if (min_len_ == max_len_) {
         stats.bulk_cells = stats.bulk_pairs * hmk_pair_cells(max_len_, max_len_, X_);
         stats.bulk_ops = stats.bulk_cells + stats.bulk_pairs * (2 * (int64_t)X_ + 1);

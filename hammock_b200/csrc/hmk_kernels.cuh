@@ -1071,6 +1071,7 @@ struct HmkP1Batch {
     const int32_t* ib;        // ib[b*ib_stride + b2] = S(member = qid[b2], query = qid[b])
     int32_t ib_stride;
     const uint32_t* ibm;      // [nq][nw]
+    const uint32_t* ibm2;     // [nq][nw] subset of ibm: founders that could beat query b's own pair (see hmk_ib_mask)
     int32_t nw;
     const int32_t* pcand;     // [nq][kb] sequence ids of the partner candidates (bk_key decoded)
     const int32_t* pd;        // pd[b*pd_stride + b2*kb + j] = S(member = j-th partner candidate of b2, query = qid[b])
@@ -1092,16 +1093,28 @@ __global__ void hmk_partner_ids(int nq, int kb, const uint64_t* __restrict__ bk_
     out[i] = id;
 }
 
-__global__ void hmk_ib_mask(int nq, int nw, int32_t T, const int32_t* __restrict__ ib, int stride, uint32_t* __restrict__ ibm) {
+// ibm [b][w]: earlier batch queries b2 with S(q_b2, q_b) >= T;
+// ibm2[b][w]: those with S(q_b2, q_b) >= the LOWEST score in query b's partner list -- whichever partner b ends up
+// with scores at least that, so a cluster founded by a b2 outside ibm2 can never beat b's own pair (its
+// complete-linkage score is at most the founder's score)
+__global__ void hmk_ib_mask(int nq, int nw, int32_t T, const int32_t* __restrict__ ib, int stride, uint32_t* __restrict__ ibm,
+                            int kb, const uint64_t* __restrict__ bk_key, const int32_t* __restrict__ bk_cnt, uint32_t* __restrict__ ibm2) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nq * nw) return;
     const int b = idx / nw, w = idx % nw;
-    uint32_t m = 0;
+    const int cnt = bk_cnt[b];
+    const int32_t thr = cnt > 0 ? hmk_key_score(bk_key[(size_t)b * kb + cnt - 1]) : HMK_JMAX;
+    uint32_t m = 0, m2 = 0;
     for (int k = 0; k < 32; k++) {
         const int b2 = w * 32 + k;
-        if (b2 < b && ib[(size_t)b * stride + b2] >= T) m |= 1u << k;
+        if (b2 < b) {
+            const int32_t s = ib[(size_t)b * stride + b2];
+            if (s >= T) m |= 1u << k;
+            if (s >= T && s >= thr) m2 |= 1u << k;
+        }
     }
     ibm[idx] = m;
+    ibm2[idx] = m2;
 }
 
 // warp arg-max under the reference's key (score desc, size desc, id asc) with three hardware
@@ -1126,18 +1139,23 @@ __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
 #else
 #define HMK_TICK(i) do {} while (0)
 #endif
+#ifdef HMK_RESOLVE_TRACE
+#define HMK_TRACE(slot, v) do { if (lane == 0) *(volatile long long*)&ctl->dbg[slot] = (long long)(v); } while (0)
+#else
+#define HMK_TRACE(slot, v) do {} while (0)
+#endif
 #define HMK_HASH_SIZE 2048          // >= 2 * HMK_MAXBATCH, power of two
 
 // shared-memory bytes of the resolver for a batch of nq queries, before the candidate cache
 __host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb, int ib_stride, int pd_stride) {
-    size_t o = (size_t)(ib_stride + pd_stride) * 4 * 2;   // double-buffered rows of ib and pd (first: 16-byte aligned)
+    size_t o = (size_t)(ib_stride + pd_stride) * 4;       // one row of ib and of pd (first: 16-byte aligned)
     o += (size_t)nq * 4 * 5;                 // qid, qab, bk_cnt, bk_ovf, ac_raw
     o += (size_t)(nq + 1) * 4;               // ac_off
-    o += (size_t)nq * nw * 4 * 2;            // ibm, t_mask
+    o += (size_t)nq * nw * 4 * 3;            // ibm, ibm2, t_mask
     o += (size_t)nq * 4 * 10;                // t_fb, t_size, t_fid, t_count, t_tail, t_nmem, t_first, f_slot, f_pick, f_tidx
     o += (size_t)nq * kb * 4 * 3;            // bk_id, bk_score, bk_ab
     o += (size_t)nq * 4 * 3;                 // per-step list of touched candidates (tc_c, tc_cl, tc_row)
-    o += (size_t)nq * 16 + (size_t)nw * 4 + 16;   // best untouched static candidate per query, dirty mask
+    o += (size_t)nq * 16 + ((size_t)nw * 4 + 16) * 2;   // best untouched static candidate per query, dirty mask, founder mask
     return o;
 }
 #define HMK_RESOLVE_CAND_BYTES 16            // cached candidate: slot, score, size, founder id
@@ -1156,8 +1174,8 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     extern __shared__ __align__(128) unsigned char rs_raw[];
     const int nq = B.nq, nw = B.nw, kb = B.kb;
     unsigned char* p = rs_raw;
-    int32_t* s_ibrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.ib_stride * 4 * 2;   // [2][ib_stride]: scores of the step's query
-    int32_t* s_pdrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.pd_stride * 4 * 2;   //   vs batch queries / partner candidates
+    int32_t* s_ibrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.ib_stride * 4;   // scores of the step's query vs the batch queries
+    int32_t* s_pdrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.pd_stride * 4;   //   ... and vs all partner candidates
     int32_t* s_qid = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
     int32_t* s_qab = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
     int32_t* s_bkcnt = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
@@ -1165,6 +1183,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     int32_t* s_acraw = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
     int32_t* s_acoff = reinterpret_cast<int32_t*>(p);   p += (size_t)(nq + 1) * 4;
     uint32_t* s_ibm = reinterpret_cast<uint32_t*>(p);   p += (size_t)nq * nw * 4;
+    uint32_t* s_ibm2 = reinterpret_cast<uint32_t*>(p);  p += (size_t)nq * nw * 4;
     uint32_t* t_mask = reinterpret_cast<uint32_t*>(p);  p += (size_t)nq * nw * 4;   // [row][nw] batch queries added to the cluster
     int32_t* t_fb = reinterpret_cast<int32_t*>(p);      p += (size_t)nq * 4;   // founder's batch index, -1 = pre-batch cluster
     int32_t* t_size = reinterpret_cast<int32_t*>(p);    p += (size_t)nq * 4;   // running Cluster.size()
@@ -1185,9 +1204,11 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     p = rs_raw + ((size_t)(p - rs_raw + 15) & ~(size_t)15);
     int4* s_best = reinterpret_cast<int4*>(p);           p += (size_t)nq * 16;   // per query: best static candidate (score, size, fid, slot)
     uint32_t* s_dirty = reinterpret_cast<uint32_t*>(p);  p += (((size_t)nw * 4 + 15) & ~(size_t)15);   // queries whose static list saw a change
+    uint32_t* s_fmask = reinterpret_cast<uint32_t*>(p);  p += (((size_t)nw * 4 + 15) & ~(size_t)15);   // batch queries that founded a cluster in this batch
     int4* s_cand = reinterpret_cast<int4*>(p);           // cache: (slot, score, size, fid)
     __shared__ int32_t h_cons[HMK_HASH_SIZE];            // set: sequence ids consumed as partners in this batch
     __shared__ int32_t h_tkey[HMK_HASH_SIZE], h_trow[HMK_HASH_SIZE];   // map: cluster slot -> row
+    __shared__ int32_t s_wb[32];                         // window scratch: partner taken by each lane
     __shared__ int s_ncached;                            // queries [0, s_ncached) have their candidates cached
     __shared__ __align__(8) uint64_t row_bar[2];         // TMA completion barriers of the two row buffers
 
@@ -1196,7 +1217,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         const int32_t q = B.qid[i];
         s_qid[i] = q; s_qab[i] = S.ab[q]; s_bkcnt[i] = B.bk_cnt[i]; s_bkovf[i] = B.bk_ovf[i]; s_acraw[i] = B.ac_cnt[i];
     }
-    for (int i = threadIdx.x; i < nq * nw; i += blockDim.x) s_ibm[i] = B.ibm[i];
+    for (int i = threadIdx.x; i < nq * nw; i += blockDim.x) { s_ibm[i] = B.ibm[i]; s_ibm2[i] = B.ibm2[i]; }
     for (int i = threadIdx.x; i < nq * kb; i += blockDim.x) {
         const int32_t id = B.pcand[i];
         s_bkid[i] = id; s_bksc[i] = hmk_key_score(B.bk_key[i]); s_bkab[i] = S.ab[id];
@@ -1240,14 +1261,23 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         }
     }
     __syncthreads();
-    {   // in parallel: each cached query's best static candidate, valid as long as none of them changes
+    {   // in parallel: each query's best pre-batch candidate.  For cached queries it stays THE best as long as none
+        // of their candidates changes (dirty bits); for every query its score stays an upper bound of what a
+        // pre-batch cluster can offer, because complete-linkage scores only fall when members are added.
         const int wl = threadIdx.x & 31;
-        for (int i = threadIdx.x; i < nw; i += blockDim.x) s_dirty[i] = 0;
-        for (int b = threadIdx.x >> 5; b < ncached; b += blockDim.x >> 5) {
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) { s_dirty[i] = 0; s_fmask[i] = 0; }
+        for (int b = threadIdx.x >> 5; b < nq; b += blockDim.x >> 5) {
             HmkBestCluster bb;
             bb.score = HMK_JMIN; bb.size = 0; bb.fid = 0; bb.slot = -1;
             const int cnt = min(s_acraw[b], B.capq);
-            for (int e = wl; e < cnt; e += 32) { const int4 v = s_cand[s_acoff[b] + e]; hmk_consider(bb, v.y, v.z, v.w, v.x); }
+            if (b < ncached) {
+                for (int e = wl; e < cnt; e += 32) { const int4 v = s_cand[s_acoff[b] + e]; hmk_consider(bb, v.y, v.z, v.w, v.x); }
+            } else {
+                for (int e = wl; e < cnt; e += 32) {
+                    const int32_t c = B.ac_slot[(size_t)b * B.capq + e];
+                    hmk_consider(bb, B.ac_score[(size_t)b * B.capq + e], S.c_size[c], S.c_founder[c], c);
+                }
+            }
             hmk_best_reduce(bb);
             if (wl == 0) s_best[b] = make_int4(bb.score, bb.size, bb.fid, bb.slot);
         }
@@ -1265,7 +1295,6 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     int32_t steps = ctl->steps, joins = ctl->joins, creates = ctl->creates, orphans = ctl->orphans;
     int32_t status = HMK_P1_CONTINUE, npe_step = -1, cur = ctl->cur;
     int32_t tn = 0;                 // rows of the touched table
-    uint32_t fmask = 0;             // this lane's word of the founder mask
 
     auto consumed = [&](int32_t id) -> bool {
         uint32_t h = hmk_hash((uint32_t)id);
@@ -1291,8 +1320,8 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     auto eval_touched = [&](int row, int b, int32_t& cl) -> bool {
         const uint32_t* tm = t_mask + row * nw;
         const uint32_t* hm = s_ibm + b * nw;
-        const int32_t* ibr = s_ibrow + (b & 1) * B.ib_stride;
-        const int32_t* pdr = s_pdrow + (b & 1) * B.pd_stride;
+        const int32_t* ibr = s_ibrow;
+        const int32_t* pdr = s_pdrow;
         const int32_t fb = t_fb[row];
         if (t_nmem[row] == 1) {     // the usual case: one batch query (+ its partner if the cluster was born here)
             const int b2 = t_first[row];
@@ -1326,32 +1355,176 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         cl = mn;
         return true;
     };
-    // rows b of ib / pd are fetched one step ahead by the TMA bulk-copy engine
+    // rows b of ib / pd (scores of query b against the batch queries / all partner candidates) are fetched by the
+    // TMA bulk-copy engine when a step takes the sequential path
     const uint32_t row_bytes = (uint32_t)(B.ib_stride + B.pd_stride) * 4;
-    auto prefetch_rows = [&](int b) {
-        uint64_t* bar = &row_bar[b & 1];
-        hmk_mbar_expect_tx(bar, row_bytes);
-        hmk_bulk_g2s(s_ibrow + (b & 1) * B.ib_stride, B.ib + (size_t)b * B.ib_stride, (uint32_t)B.ib_stride * 4, bar);
-        hmk_bulk_g2s(s_pdrow + (b & 1) * B.pd_stride, B.pd + (size_t)b * B.pd_stride, (uint32_t)B.pd_stride * 4, bar);
+    uint32_t row_uses = 0;          // completed phases of row_bar[0]
+    auto fetch_rows = [&](int b) {
+#ifdef HMK_NO_TMA_ROWS
+        for (int i = lane; i < B.ib_stride; i += 32) s_ibrow[i] = B.ib[(size_t)b * B.ib_stride + i];
+        for (int i = lane; i < B.pd_stride; i += 32) s_pdrow[i] = B.pd[(size_t)b * B.pd_stride + i];
+        __syncwarp();
+        return;
+#endif
+        if (lane == 0) {
+            hmk_mbar_expect_tx(&row_bar[0], row_bytes);
+            hmk_bulk_g2s(s_ibrow, B.ib + (size_t)b * B.ib_stride, (uint32_t)B.ib_stride * 4, &row_bar[0]);
+            hmk_bulk_g2s(s_pdrow, B.pd + (size_t)b * B.pd_stride, (uint32_t)B.pd_stride * 4, &row_bar[0]);
+        }
     };
-    if (lane == 0) {
-        hmk_mbar_init(&row_bar[0], 1);
-        hmk_mbar_init(&row_bar[1], 1);
-        prefetch_rows(0);
-    }
+#ifdef HMK_NO_TMA_ROWS
+    auto wait_rows = [&]() { row_uses++; };
+#else
+    auto wait_rows = [&]() { hmk_mbar_wait(&row_bar[0], row_uses & 1u); row_uses++; };
+#endif
+    if (lane == 0) hmk_mbar_init(&row_bar[0], 1);
     __syncwarp();
 
-    for (int b = 0; b < nq; b++) {
+    // ------------------------------------------------------------------------------------------------
+    // Most steps are "q founds a new cluster with its best still-alive partner" and do not interact with
+    // their neighbours.  A WINDOW of up to 32 consecutive batch queries is therefore evaluated with one
+    // query per lane against the state at the window start; a lane is only trusted if
+    //   * it is a plain case: consumed query (skipped), new pair, or orphan -- joins, truncated lists, ... take
+    //     the sequential path below,
+    //   * no cluster it could join can reach its partner's score: the best pre-batch cluster's score at batch
+    //     start (later members only lower it) and the FOUNDER score S(founder, q) of every cluster born in
+    //     this batch (complete linkage <= founder score) are all below the partner score -- this includes
+    //     the pairs created by earlier lanes of the window,
+    //   * no earlier lane of the window takes its partner or the query itself, and K is not reached.
+    // The longest prefix of trusted lanes is applied in parallel (cluster ids = creation order), the first
+    // untrusted step runs sequentially, and the next window starts behind it.  Same decisions, same order.
+    // ------------------------------------------------------------------------------------------------
+    int b = 0, penalty = 0;
+    int n_win = 0, n_win_steps = 0, n_seq = 0;      // statistics: windows tried, lanes they applied, sequential steps
+    while (b < nq) {
+        HMK_TRACE(0, b); HMK_TRACE(1, 1);
+#ifdef HMK_NO_WINDOW
+        penalty = 1;
+#endif
+        if (penalty == 0 && ncl > 0 && ncl < S.K && unproc > 96) {
+            const int W = min(32, nq - b);
+            const int bi = b + lane;
+            const bool in = lane < W;
+            const int32_t q = in ? s_qid[bi] : -1;
+            // 0 = skip (already consumed), 1 = new pair, 2 = orphan, 3 = sequential path
+            int kind = 3;
+            int32_t bid = -1, bscore = HMK_JMIN;
+            int bpick = 0;
+            if (in) {
+                if (consumed(q)) kind = 0;
+                else if (s_acraw[bi] <= B.capq) {
+                    const int bcnt = s_bkcnt[bi];
+                    int pick = -1;
+                    for (int j = 0; j < bcnt; j++)
+                        if (pick < 0 && !consumed(s_bkid[bi * kb + j])) pick = j;
+                    if (!(pick < 0 && s_bkovf[bi])) {
+                        // best pre-batch candidate at batch start: its score bounds every pre-batch cluster's
+                        // current score from above (members only lower a complete-linkage score)
+                        const int4 sb = s_best[bi];      // (score, size, fid, slot)
+                        if (pick >= 0) {
+                            bpick = pick; bid = s_bkid[bi * kb + pick]; bscore = s_bksc[bi * kb + pick];
+                            if (!(sb.w >= 0 && sb.x >= bscore)) kind = 1;
+                        } else if (sb.w < 0) kind = 2;
+                    }
+                }
+            }
+            __syncwarp();
+            HMK_TICK(7);   // window: partner pick
+            HMK_TRACE(1, 2);
+            // clusters born in this batch (before the window, or by earlier lanes of it) whose founder scores >= T
+            const unsigned cm0 = __ballot_sync(FULL, kind == 1);
+            const unsigned lt = (1u << lane) - 1u;
+            {
+                const int w0 = b >> 5, sh = b & 31;
+                const unsigned mine = cm0 & lt;
+                // a new pair only has to fear founders scoring at least its lowest listed partner (ibm2);
+                // an orphan joins whatever valid cluster there is (ibm)
+                const uint32_t* hmrow = kind == 1 ? s_ibm2 + bi * nw : s_ibm + bi * nw;
+                uint32_t any = 0;
+                if (kind == 1 || kind == 2) {
+                    for (int w = 0; w < nw; w++) {
+                        uint32_t m = s_fmask[w];
+                        m |= w == w0 ? mine << sh : 0u;
+                        m |= (w == w0 + 1 && sh) ? mine >> (32 - sh) : 0u;
+                        any |= m & hmrow[w];
+                    }
+                }
+                if (any) kind = 3;
+            }
+            __syncwarp();
+            HMK_TICK(6);   // window: founder bounds
+            HMK_TRACE(1, 3);
+            // partners / queries taken by earlier lanes of the window
+            bool bad = in && kind == 3;
+            {
+                s_wb[lane] = kind == 1 ? bid : -1;
+                __syncwarp();
+                bool taken = false;
+#pragma unroll
+                for (int j = 0; j < 32; j++) taken |= (j < lane) & (s_wb[j] == q);
+                const unsigned same = __match_any_sync(FULL, kind == 1 ? bid : -2 - lane);
+                bad |= in && kind != 0 && (taken || (same & lt) != 0);
+                __syncwarp();
+            }
+            if (in && ncl + __popc(cm0 & lt) >= S.K) bad = true;          // :90, checked before anything else of a step
+            const unsigned badm = __ballot_sync(FULL, bad || !in);
+            const int Pn = badm ? __ffs(badm) - 1 : 32;      // lanes [0, Pn) are applied
+            HMK_TRACE(1, 4); HMK_TRACE(2, Pn);
+            n_win++; n_win_steps += Pn;
+            HMK_TICK(2);
+            if (Pn > 0) {
+                const bool act = lane < Pn;
+                const unsigned cm = __ballot_sync(FULL, act && kind == 1);
+                const unsigned om = __ballot_sync(FULL, act && kind == 2);
+                if (act && kind == 1) {
+                    const int r = __popc(cm & lt);
+                    const int32_t c = ncl + r;
+                    const int row = tn + r;
+                    for (int w = 0; w < nw; w++) t_mask[row * nw + w] = 0;
+                    t_mask[row * nw + (bi >> 5)] = 1u << (bi & 31);
+                    uint32_t h = hmk_hash((uint32_t)c);
+                    while (atomicCAS(&h_tkey[h], -1, c) != -1) h = (h + 1) & (HMK_HASH_SIZE - 1);
+                    h_trow[h] = row;
+                    const int32_t sz = hmk_wadd(s_qab[bi], s_bkab[bi * kb + bpick]);
+                    t_nmem[row] = 1; t_first[row] = bi; t_fb[row] = bi; t_fid[row] = q;
+                    t_count[row] = 2; t_tail[row] = bid; t_size[row] = sz;
+                    f_slot[bi] = c; f_pick[bi] = bpick; f_tidx[bi] = row;
+                    S.c_founder[c] = q; S.c_tail[c] = bid; S.c_count[c] = 2; S.c_size[c] = sz;
+                    S.next[q] = bid; S.next[bid] = -1;
+                    S.slot[q] = c; S.rank[q] = 0; S.slot[bid] = c; S.rank[bid] = 1;
+                    h = hmk_hash((uint32_t)bid);
+                    while (atomicCAS(&h_cons[h], -1, bid) != -1) h = (h + 1) & (HMK_HASH_SIZE - 1);
+                }
+                if (act && kind != 0 && S.qbatch) S.qbatch[q] = B.batch_id;
+                {   // founder mask: window bit i is batch query b + i
+                    const int w0 = b >> 5, sh = b & 31;
+                    if (lane == w0) s_fmask[lane] |= cm << sh;
+                    else if (lane == w0 + 1 && sh) s_fmask[lane] |= cm >> (32 - sh);
+                }
+                const int nC = __popc(cm), nO = __popc(om);
+                ncl += nC; tn += nC; creates += nC; orphans += nO;
+                steps += nC + nO; unproc -= 2 * nC + nO;
+                const unsigned done = cm | om;
+                if (done) cur = __shfl_sync(FULL, q, 31 - __clz(done)) + 1;
+                __syncwarp();
+                b += Pn;
+            }
+            penalty = Pn >= 4 ? 0 : 4;      // crowded stretch: a few sequential steps before the next attempt
+            HMK_TICK(1);   // window
+            if (Pn == W) continue;
+        } else if (penalty > 0) penalty--;
+
+        // ---- one step in reference order
+        HMK_TRACE(1, 5);
+        n_seq++;
         const int32_t q = s_qid[b];
-        HMK_TICK(7);
-        hmk_mbar_wait(&row_bar[b & 1], (uint32_t)(b >> 1) & 1u);     // rows of this step have landed
-        if (lane == 0 && b + 1 < nq) prefetch_rows(b + 1);            // the other buffer was released by step b-1
-        HMK_TICK(1);   // row wait + prefetch issue
         if (ncl >= S.K) { status = HMK_P1_DONE; cur = q; break; }                   // :90
-        if (consumed(q)) continue;   // taken as a partner earlier in this batch (:101,110)
+        if (consumed(q)) { b++; continue; }   // taken as a partner earlier in this batch (:101,110)
         const int32_t acnt = s_acraw[b];
         if (acnt > B.capq) { status = HMK_P1_GROW; cur = q; break; }   // candidate arrays too small: host grows them
         const int32_t bcnt = s_bkcnt[b];
+        fetch_rows(b);
+        uint32_t fmask = lane < nw ? s_fmask[lane] : 0u;   // this lane's word of the founder mask
 
         // ---- B: nearest among initialList[index+1 ..]                               (:93)
         int bkind = 0;   // 0 = Java null, 1 = found, 2 = (null cluster, MIN_VALUE) object
@@ -1366,9 +1539,13 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 bscore = s_bksc[b * kb + bpick];
                 bkind = 1;
             } else if (s_bkovf[b]) {
+                wait_rows();
                 status = HMK_P1_RESTART; cur = q; break;    // list truncated: rescore from q
             }
         }
+        HMK_TRACE(1, 6);
+        wait_rows();
+        HMK_TRACE(1, 7);
 
         HMK_TICK(2);   // consumed check + B part
         // ---- A: nearest among actualClusters (complete linkage)                      (:92)
@@ -1406,6 +1583,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 }
                 nt += __popc(tmk);
             }
+            HMK_TRACE(1, 71); HMK_TRACE(3, nt);
             HMK_TICK(3);   // static candidates
             // clusters born in this batch whose founder scores >= T
             {
@@ -1427,6 +1605,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                     nt += total;
                 }
             }
+            HMK_TRACE(1, 72); HMK_TRACE(3, nt);
             if (nt) {
                 __syncwarp();
                 for (int i0 = 0; i0 < nt; i0 += 32) {
@@ -1439,6 +1618,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 }
                 __syncwarp();
             }
+            HMK_TRACE(1, 73);
             if (clean && nt == 0) {      // only lane 0 holds a candidate: broadcast instead of reducing
                 best.score = __shfl_sync(FULL, best.score, 0); best.size = __shfl_sync(FULL, best.size, 0);
                 best.fid = __shfl_sync(FULL, best.fid, 0); best.slot = __shfl_sync(FULL, best.slot, 0);
@@ -1446,6 +1626,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             if (best.slot >= 0) akind = 1;
         }
 
+        HMK_TRACE(1, 8);
         HMK_TICK(4);   // founders + touched evaluation + reduce
         // ---- decision                                                               (:94-114)
         const int32_t ascore = akind == 1 ? best.score : HMK_JMIN;
@@ -1492,7 +1673,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             }
             __syncwarp();
             if (lane == (b >> 5)) t_mask[row * nw + lane] |= 1u << (b & 31);
-            if (create && lane == (b >> 5)) fmask |= 1u << (b & 31);
+            if (create && lane == (b >> 5)) s_fmask[lane] |= 1u << (b & 31);
             if (lane == 0) {
                 t_nmem[row] += 1;
                 if (join) {                                               // insertAll({q})   (:97,104)
@@ -1521,12 +1702,14 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         if (lane == 0 && S.qbatch) S.qbatch[q] = B.batch_id;
         __syncwarp();
         HMK_TICK(5);   // decision + apply
+        b++;
     }
     if (status == HMK_P1_CONTINUE && (ncl >= S.K || unproc <= 0)) status = HMK_P1_DONE;
 #ifdef HMK_RESOLVE_TIMING
     if (lane == 0) for (int i = 0; i < 8; i++) ctl->dbg[i] += dbg[i];
 #endif
     if (lane == 0) {
+        ctl->dbg[4] += n_win; ctl->dbg[5] += n_win_steps; ctl->dbg[6] += n_seq;
         ctl->cur = cur; ctl->ncl = ncl; ctl->unproc_alive = unproc; ctl->status = status;
         if (npe_step >= 0) ctl->npe_step = npe_step;
         ctl->steps = steps; ctl->joins = joins; ctl->creates = creates; ctl->orphans = orphans;
