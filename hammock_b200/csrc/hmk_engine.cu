@@ -272,8 +272,8 @@ private:
     DevBuf<unsigned int> d_counts_;   // [0] hit_count, [1] cand_count
     DevBuf<unsigned long long> d_pairctr_;
     // ---- phase-2 scratch
-    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cc_q_, d_qstart_, d_cstart_,
-        d_a0_, d_a1_, d_dyn_, d_dyn_n_, d_flags_, d_base_cl_, d_wlo_, d_tent_, d_tent_n_;
+    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cq_q_, d_cc_q_, d_qstart_, d_cstart_,
+        d_a0_, d_a1_, d_dyn_, d_dyn_n_, d_flags_, d_base_cl_, d_wlo_, d_tent_, d_tent_s_, d_tent_n_;
     DevBuf<unsigned long long> d_key_q_, d_key_c_, d_key_tmp_;
     DevBuf<unsigned char> d_cub_;
     DevBuf<uint32_t> d_fprof_;
@@ -1145,8 +1145,8 @@ void Engine::phase2() {
     const int ncp = (int)ncand_padded_;   // >= nc: padded entries carry key ~0 and sort to the end
     // group by query (ascending cluster inside a query) and by cluster (ascending query inside a cluster)
     sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, cbits + qbits);
-    d_cq_c_.reserve(nc); d_cc_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2);
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p);
+    d_cq_c_.reserve(nc); d_cq_q_.reserve(nc); d_cc_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p, d_cq_q_.p);
     hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, cbits, d_qstart_.p);
     {
         size_t bytes = 0;
@@ -1155,20 +1155,20 @@ void Engine::phase2() {
         d_cub_.reserve(bytes);
         CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, cbits + qbits, st_));
     }
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, qbits, d_cc_q_.p);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, qbits, d_cc_q_.p, nullptr);
     hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, qbits, d_cstart_.p);
     CK(cudaGetLastError());
     launches_ += 8;
-    d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_wlo_.reserve(ncl); d_tent_.reserve(nc);
+    d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_wlo_.reserve(ncl); d_tent_.reserve(nc); d_tent_s_.reserve(nc);
     d_tent_n_.reserve(ncl); d_a0_.reserve(ns); d_a1_.reserve(ns); d_dirty_a_.reserve(ncl); d_dirty_b_.reserve(ncl);
     CK(cudaMemsetAsync(d_dyn_n_.p, 0, sizeof(int32_t) * ncl, st_));
     CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * ns, st_));
     CK(cudaMemsetAsync(d_a1_.p, 0xff, sizeof(int32_t) * ns, st_));
     HmkP2 P{};
     P.S = state(); P.packed = fast_scalar_ ? d_packed_.p : nullptr; P.L = max_len_;
-    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_s = d_cand_score_.p;
+    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_q = d_cq_q_.p; P.cq_s = d_cand_score_.p;
     P.cstart = d_cstart_.p; P.cc_q = d_cc_q_.p; P.dyn = d_dyn_.p; P.dyn_n = d_dyn_n_.p;
-    P.base_cl = d_base_cl_.p; P.wlo = d_wlo_.p; P.tent = d_tent_.p; P.tent_n = d_tent_n_.p;
+    P.base_cl = d_base_cl_.p; P.wlo = d_wlo_.p; P.tent = d_tent_.p; P.tent_s = d_tent_s_.p; P.tent_n = d_tent_n_.p;
     P.changed = d_flags_.p + 1;
     int32_t* cur = d_a0_.p;
     int32_t* nxt = d_a1_.p;
@@ -1196,7 +1196,7 @@ void Engine::phase2() {
             CK(cudaMemsetAsync(d_tent_n_.p, 0, sizeof(int32_t) * ncl, st_));
             CK(cudaMemsetAsync(d_flags_.p + 1, 0, sizeof(int32_t), st_));
             hmk_p2_build_tent<<<(qb - qa + 255) / 256, 256, 0, st_>>>(P);
-            hmk_p2_sort_tent<<<cgrid, 256, 0, st_>>>(P);
+            hmk_p2_sort_tent<<<(ncl * 32 + 255) / 256, 256, 0, st_>>>(P);
             hmk_p2_decide<<<qgrid, 256, 0, st_>>>(P);
             CK(cudaGetLastError());
             launches_ += 3;

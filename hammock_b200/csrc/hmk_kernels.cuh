@@ -1735,13 +1735,15 @@ struct HmkP2 {
     const int32_t* qstart;    // [ns+1] into cq_*
     const int32_t* cq_c;      // candidate cluster slot (ascending inside a query)
     const int32_t* cq_s;      // complete-linkage min over the phase-1 members
+    const int32_t* cq_q;      // query index of the pair (the key's other field)
     const int32_t* cstart;    // [ncl+1] into cc_q / dyn / tent
     const int32_t* cc_q;      // query index (into singles), ascending inside a cluster
     int32_t* dyn;             // final phase-2 members (sequence ids): dyn[cstart[c] + t]
     int32_t* dyn_n;           // [ncl]
     int32_t* base_cl;         // per pair: min over phase-1 and final phase-2 members, JMIN = invalid
     int32_t* wlo;             // [ncl] first cc_q position of the current window
-    int32_t* tent;            // tentative in-window joiners (query indices): tent[wlo[c] + t]
+    int32_t* tent;            // tentative in-window joiners (query indices) in arrival order: tent[wlo[c] + t]
+    int32_t* tent_s;          // ... in query order (hmk_p2_sort_tent)
     int32_t* tent_n;          // [ncl]
     const int32_t* a_cur;     // [ns] tentative assignment of this iteration (-1 = none)
     int32_t* a_new;
@@ -1760,10 +1762,7 @@ __global__ void hmk_p2_base(const HmkP2 P) {
     const int e0 = P.qstart[P.qa], e1 = P.qstart[P.qb];
     long long npairs = 0;
     for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
-        // query of pair e: binary search in qstart
-        int lo = P.qa, hi = P.qb - 1;
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.qstart[mid] <= e) lo = mid; else hi = mid - 1; }
-        const int32_t q = P.singles[lo];
+        const int32_t q = P.singles[P.cq_q[e]];
         const int32_t c = P.cq_c[e];
         int32_t cl = P.cq_s[e];
         const int32_t* dm = P.dyn + P.cstart[c];
@@ -1797,16 +1796,20 @@ __global__ void hmk_p2_build_tent(const HmkP2 P) {
     P.tent[P.wlo[c] + pos] = qi;
 }
 
+// one warp per cluster: rank sort of its tentative joiners (distinct query indices) into tent_s.  A popular
+// cluster can collect hundreds of joiners per window; a one-thread insertion sort made it the tail of every iteration
 __global__ void hmk_p2_sort_tent(const HmkP2 P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= P.ncl) return;
     const int n = P.tent_n[c];
-    int32_t* t = P.tent + P.wlo[c];
-    for (int i = 1; i < n; i++) {
-        int32_t v = t[i];
-        int j = i - 1;
-        while (j >= 0 && t[j] > v) { t[j + 1] = t[j]; j--; }
-        t[j + 1] = v;
+    const int32_t* t = P.tent + P.wlo[c];
+    int32_t* o = P.tent_s + P.wlo[c];
+    for (int i = lane; i < n; i += 32) {
+        const int32_t v = t[i];
+        int r = 0;
+        for (int j = 0; j < n; j++) r += t[j] < v;
+        o[r] = v;
     }
 }
 
@@ -1815,20 +1818,24 @@ __global__ void hmk_p2_sort_tent(const HmkP2 P) {
 // before it in the previous iteration (dirty_cur[c] < qi).
 __global__ void hmk_p2_decide(const HmkP2 P) {
     __shared__ int32_t sM[HMK_NRES * HMK_NRES];
-    hmk_load_matrix_smem(sM, P.S.M);
-    HmkScalar sc;
-    sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
     const int lane = threadIdx.x & 31;
     const int qi = P.qa + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (qi >= P.qb) return;
-    const int e0 = P.qstart[qi], e1 = P.qstart[qi + 1];
-    const int32_t old = P.a_cur[qi];
+    const bool inw = qi < P.qb;
+    int e0 = 0, e1 = 0;
+    int32_t old = -1;
     bool dirty = false;
-    for (int e = e0 + lane; e < e1; e += 32) dirty |= P.dirty_cur[P.cq_c[e]] < qi;
-    if (!__any_sync(0xffffffffu, dirty)) {
-        if (lane == 0) P.a_new[qi] = old;
-        return;
+    if (inw) {
+        e0 = P.qstart[qi]; e1 = P.qstart[qi + 1];
+        old = P.a_cur[qi];
+        for (int e = e0 + lane; e < e1; e += 32) dirty |= P.dirty_cur[P.cq_c[e]] < qi;
+        dirty = __any_sync(0xffffffffu, dirty);
+        if (!dirty && lane == 0) P.a_new[qi] = old;
     }
+    if (!__syncthreads_or(dirty)) return;      // after the first iterations most blocks have nothing to re-evaluate
+    hmk_load_matrix_smem(sM, P.S.M);
+    if (!dirty) return;
+    HmkScalar sc;
+    sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
     const int32_t q = P.singles[qi];
     long long npairs = 0;
     HmkBestCluster best;
@@ -1838,7 +1845,7 @@ __global__ void hmk_p2_decide(const HmkP2 P) {
         if (cl == HMK_JMIN) continue;
         const int32_t c = P.cq_c[e];
         int32_t size = P.S.c_size[c];
-        const int32_t* t = P.tent + P.wlo[c];
+        const int32_t* t = P.tent_s + P.wlo[c];
         const int32_t nt = P.tent_n[c];
         bool ok = true;
         for (int i = 0; i < nt; i++) {
@@ -1872,7 +1879,7 @@ __global__ void hmk_p2_commit(const HmkP2 P) {
     if (c >= P.ncl) return;
     const int n = P.tent_n[c];
     if (n == 0) return;
-    const int32_t* t = P.tent + P.wlo[c];
+    const int32_t* t = P.tent_s + P.wlo[c];
     int32_t nd = P.dyn_n[c], cnt = P.S.c_count[c], size = P.S.c_size[c];
     for (int i = 0; i < n; i++) {
         const int32_t q = P.singles[t[i]];
@@ -1969,9 +1976,12 @@ __global__ void hmk_segment_starts(const unsigned long long* __restrict__ keys, 
     }
     start[s] = lo;
 }
-__global__ void hmk_split_keys_lo(const unsigned long long* __restrict__ keys, int n, int shift, int32_t* __restrict__ lo) {
+__global__ void hmk_split_keys_lo(const unsigned long long* __restrict__ keys, int n, int shift, int32_t* __restrict__ lo,
+                                  int32_t* __restrict__ hi) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) lo[i] = (int32_t)(uint32_t)(keys[i] & ((1ull << shift) - 1ull));
+    if (i >= n) return;
+    lo[i] = (int32_t)(uint32_t)(keys[i] & ((1ull << shift) - 1ull));
+    if (hi) hi[i] = (int32_t)(uint32_t)(keys[i] >> shift);
 }
 
 __global__ void hmk_finalize(int n, const int32_t* __restrict__ slot, const int32_t* __restrict__ rank,
