@@ -121,7 +121,19 @@ int hmk_measure_peaks(hmk_ctx* ctx, double* out4, char* errbuf, size_t errlen);
  * p2_base, p2_iterate, p2_commit, final */
 #define HMK_NSECTIONS 13
 int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n);
-/* tuning knobs (batch size, tile sizes, ...); unknown names return HMK_STATUS_BAD_ARG */
+/* tuning knobs; unknown names return HMK_STATUS_BAD_ARG.  None of them changes the result.
+ *   batch      phase-1 queries per batch (0 = automatic: 8 profile tiles, at most 512 and what the resolver's
+ *              shared memory holds)
+ *   kb         partner candidates kept per query (1..32, default 8)
+ *   capq       initial capacity of the per-query cluster-candidate arrays (grown on demand)
+ *   lookahead  1 = prepare batch i+1 on a side stream while batch i is resolved (default)
+ *   filter     1 = upper-bound filter + exact verify kernel where it applies (default), 0 = exact kernel only
+ *   reuse      1 = phase 2 takes its founder hits from the phase-1 partner searches when the matrix is
+ *              symmetric (default), 0 = always run the separate founder pass
+ *   qt, waves  profiles per shared-memory tile (0 = as many as fit), grid waves per launch
+ *   p2_chunk, p2_window, hit_cap   phase-2 chunking / window size / initial hit-buffer size
+ *   force_generic  1 = scalar kernel for everything (correctness path)
+ *   profile    1 = time every bulk launch with CUDA events (hmk_stats.bulk_kernel_ms) */
 int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value);
 
 /* SequenceScorer.sequenceScore over a block of pairs (SequenceScorer.java:12-15,
