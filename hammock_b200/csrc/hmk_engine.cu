@@ -335,9 +335,10 @@ private:
                 cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking);
                 cudaMemcpyAsync(h_ctl_, d_ctl_.p, sizeof(HmkCtl), cudaMemcpyDeviceToHost, s3);
                 cudaStreamSynchronize(s3);
-                fprintf(stderr, "HANG: side stream %s; ctl cur %d ncl %d unproc %d steps %d dbg %lld %lld %lld %lld\n",
+                fprintf(stderr, "HANG: side stream %s; ctl cur %d ncl %d unproc %d steps %d dbg %lld %lld %lld %lld lanes %llx %llx %llx %llx\n",
                         cudaStreamQuery(st2_) == cudaErrorNotReady ? "busy" : "idle", h_ctl_->cur, h_ctl_->ncl, h_ctl_->unproc_alive,
-                        h_ctl_->steps, (long long)h_ctl_->dbg[0], (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3]);
+                        h_ctl_->steps, (long long)h_ctl_->dbg[0], (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3],
+                        (unsigned long long)h_ctl_->dbg[4], (unsigned long long)h_ctl_->dbg[5], (unsigned long long)h_ctl_->dbg[6], (unsigned long long)h_ctl_->dbg[7]);
                 fflush(stderr);
                 _exit(3);
             }

@@ -161,6 +161,10 @@ __device__ __forceinline__ void hmk_mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(hmk_smem_u32(bar)), "r"(parity)
             : "memory");
     } while (!ok);
+    // lanes leave the spin loop (and may have been suspended in try_wait) at different times; everything that
+    // follows uses warp-wide primitives, so re-converge here.  Always called by whole warps.  Without this the
+    // resolver dead-locked at a later __syncwarp on some inputs.
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------- bulk arguments
@@ -1141,8 +1145,12 @@ __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
 #endif
 #ifdef HMK_RESOLVE_TRACE
 #define HMK_TRACE(slot, v) do { if (lane == 0) *(volatile long long*)&ctl->dbg[slot] = (long long)(v); } while (0)
+#define HMK_TRACE_LANES(slot) atomicOr((unsigned long long*)&ctl->dbg[slot], 1ull << lane)
+#define HMK_TRACE_CLEAR() do { if (lane == 0) { ctl->dbg[4] = 0; ctl->dbg[5] = 0; ctl->dbg[6] = 0; ctl->dbg[7] = 0; } __syncwarp(); } while (0)
 #else
 #define HMK_TRACE(slot, v) do {} while (0)
+#define HMK_TRACE_LANES(slot) do {} while (0)
+#define HMK_TRACE_CLEAR() do {} while (0)
 #endif
 #define HMK_HASH_SIZE 2048          // >= 2 * HMK_MAXBATCH, power of two
 
@@ -1546,6 +1554,8 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         HMK_TRACE(1, 6);
         wait_rows();
         HMK_TRACE(1, 7);
+        HMK_TRACE_CLEAR();
+        HMK_TRACE_LANES(4);
 
         HMK_TICK(2);   // consumed check + B part
         // ---- A: nearest among actualClusters (complete linkage)                      (:92)
@@ -1583,6 +1593,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 }
                 nt += __popc(tmk);
             }
+            HMK_TRACE_LANES(5);
             HMK_TRACE(1, 71); HMK_TRACE(3, nt);
             HMK_TICK(3);   // static candidates
             // clusters born in this batch whose founder scores >= T
@@ -1605,9 +1616,11 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                     nt += total;
                 }
             }
+            HMK_TRACE_LANES(6);
             HMK_TRACE(1, 72); HMK_TRACE(3, nt);
             if (nt) {
                 __syncwarp();
+                HMK_TRACE(1, 721);
                 for (int i0 = 0; i0 < nt; i0 += 32) {
                     const int i = i0 + lane;
                     if (i < nt) {
@@ -1616,8 +1629,10 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                         if (eval_touched(row, b, cl2)) hmk_consider(best, cl2, t_size[row], t_fid[row], tc_c[i]);
                     }
                 }
+                HMK_TRACE(1, 722);
                 __syncwarp();
             }
+            HMK_TRACE_LANES(7);
             HMK_TRACE(1, 73);
             if (clean && nt == 0) {      // only lane 0 holds a candidate: broadcast instead of reducing
                 best.score = __shfl_sync(FULL, best.score, 0); best.size = __shfl_sync(FULL, best.size, 0);

@@ -94,3 +94,42 @@ def test_fuzz_against_oracle(golden_dir):
         finally:
             ctx.close()
     assert seen["status"] >= {0, 1, 2} and seen["path"] == {0, 1, 2}, seen
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_fuzz_midsize_default_options(golden_dir):
+    """A few thousand to 20 k sequences with the DEFAULT tuning (batches of 448, look-ahead on a side stream,
+    parallel resolver windows, phase-2 hit reuse): the paths the small cases above hardly reach.  Each case runs
+    twice on the same context -- the look-ahead races with the resolver by design, the result must not depend on it."""
+    z = np.load(os.path.join(golden_dir, "matrices.npz"))
+    mats = {k: z[k] for k in z.files}
+    rng = np.random.default_rng(77)
+    ncpu = os.cpu_count() or 1
+    for it in range(10):
+        n = int(rng.integers(3000, 20000))
+        kind = int(rng.integers(0, 4))
+        lo, hi = [(12, 12), (9, 9), (7, 12), (16, 16)][kind]
+        m = str(rng.choice(["blosum62", "blosum62", "blosum45", "pam250"]))
+        d = synth.generate(n, lo, hi, seed=int(rng.integers(1, 1 << 30)), top_abundance=int(rng.choice([50, 100000])))
+        T0, X0, K0 = synth.default_params(d["lengths"])
+        T = int(T0 + rng.choice([0, 0, -4, 5]))
+        K = int(rng.choice([K0, K0, n // 10, n // 3, n]))
+        P = int(rng.choice([0, 0, -1]))
+        opts = {} if it % 3 else {"kb": int(rng.choice([2, 4]))}        # short candidate lists: restarts with the look-ahead on
+        R = O.greedy_cluster(d["residues"], d["offsets"], d["abundance"], mats[m], T, X0, P, K, nthreads=ncpu)
+        ctx = hb.GreedyContext(0, **opts)
+        try:
+            ctx.upload(d["residues"], d["offsets"], d["abundance"], mats[m], T, X0, P, K)
+            for rep in range(2):
+                rc, _ = ctx.run_status()
+                st = ctx.stats()
+                what = f"iter {it} rep {rep} n={n} len={lo}-{hi} {m} T={T} X={X0} P={P} K={K} opts={opts} path={st['fast_path']}"
+                assert rc == R.status, what
+                if rc == 0:
+                    G = ctx.download()
+                    assert (G.cluster_id == R.cluster_id).all(), what
+                    assert (G.member_rank == R.member_rank).all(), what
+                    assert (G.result_order == R.result_order).all() and G.n_multi == R.n_multi, what
+                    assert st["p1_steps"] == R.counters["p1_steps"] and st["p2_assigned"] == R.counters["p2_assigned"], what
+        finally:
+            ctx.close()
