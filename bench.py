@@ -323,6 +323,12 @@ def main():
                 "share_of_step": alone["bulk_kernel_ms"] / alone["total_ms"],
                 "step_ms_without_lookahead": alone["total_ms"]},
             "work": {"bulk_pairs": stats["bulk_pairs"], "scalar_pairs": stats["scalar_pairs"],
+                     # phase 2 reuses the founder scores that the phase-1 partner searches already produced (symmetric
+                     # matrix): the reference scores these (singleton, cluster) pairs a second time
+                     "pairs_served_by_phase1_hits": (stats["p2_queries"] * stats["p1_new_clusters"]
+                                                     if sections.get("p2_filter", 0.0) == 0.0 and stats["p2_hits"] else 0),
+                     "reference_min_pairs": reference_pairs_lower_bound(n, stats["p1_steps"], stats["p1_new_clusters"],
+                                                                        stats["p2_queries"], stats["p1_new_clusters"]),
                      "bulk_cells": stats["bulk_cells"], "p1_steps": stats["p1_steps"], "p1_batches": stats["p1_batches"],
                      "p2_queries": stats["p2_queries"], "p2_assigned": stats["p2_assigned"],
                      "multi_member_clusters": stats["p1_new_clusters"], "p2_iterations": stats["p2_rounds"]},
