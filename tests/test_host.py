@@ -260,3 +260,41 @@ def test_python_writers_format(tmp_path):
     assert p.read_text().splitlines()[1] == "0\tWVTAPRSLPVLA\t30\t30"                                  # ties -> alphabetically first
     hb.save_input_statistics(seqs, ["x"], str(p))
     assert p.read_text() == "\tx\ntotal_count\t49\nunique_count\t14"
+
+
+def test_tuning_options_documented_in_header():
+    """every name hmk_set_option accepts is described in include/hammock_b200.h (and nothing else is)"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "hammock_b200", "csrc", "hmk_engine.cu")).read()
+    hdr = open(os.path.join(root, "include", "hammock_b200.h")).read()
+    accepted = set(re.findall(r'\(s == "([a-z0-9_]+)"\)', src))
+    assert {"batch", "kb", "lookahead", "filter", "reuse"} <= accepted
+    doc = hdr[hdr.index("tuning knobs"):hdr.index("int hmk_set_option")]
+    documented = set()
+    for line in doc.splitlines():
+        m = re.match(r"\s*\*\s{3}([a-z0-9_, ]+?)\s{2,}\S", line)
+        if m:
+            documented |= {w.strip() for w in m.group(1).split(",") if w.strip()}
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """profiles/r01_bench_n1.json is the line bench.py printed on the B200: the keys the driver reads must be there"""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.loads(open(os.path.join(root, "profiles", "r01_bench_n1.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None and "workload" in d["config"]
+    assert abs(d["value"] - d["config"]["n_sequences"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    w = d["work"]
+    assert w["bulk_pairs"] + w["scalar_pairs"] + w["pairs_served_by_phase1_hits"] >= w["reference_min_pairs"]
