@@ -82,3 +82,32 @@ def test_filter_bounds_every_exact_lane(golden_dir, L, X, P):
                 assert (s >= T) == (best[i] >= 128), (name, i, s, best[i])
                 if s >= T:
                     assert best[i] - 128 + T == s
+
+
+def test_score_symmetry_claim_behind_the_phase2_hit_reuse(golden_dir):
+    """S(a, b) == S(b, a) for every pair iff the matrix is symmetric (different lengths: the
+    shorter/longer roles do not depend on the argument order; equal lengths: the matrix gets transposed)."""
+    z = np.load(os.path.join(golden_dir, "matrices.npz"))
+    rng = np.random.default_rng(3)
+    for name in ("blosum62", "pam250", "mcla71", "blosum30"):
+        M = z[name].astype(np.int32)
+        assert (M == M.T).all(), name                 # all bundled matrices are symmetric
+        for _ in range(300):
+            la, lb = int(rng.integers(4, 31)), int(rng.integers(4, 31))
+            a = rng.integers(0, 24, size=la).astype(np.uint8)
+            b = rng.integers(0, 24, size=lb).astype(np.uint8)
+            X = int(rng.integers(0, min(la, lb)))
+            P = int(rng.choice([0, -1, -3, 2]))
+            assert O.score_with_shift(a, b, M, X, P)[0] == O.score_with_shift(b, a, M, X, P)[0], (name, la, lb, X, P)
+    # ... and an asymmetric matrix breaks it for equal lengths only
+    A = z["blosum62"].astype(np.int32).copy()
+    A[np.triu_indices(24, 1)] -= 3
+    diff_equal = diff_unequal = 0
+    for _ in range(300):
+        la = int(rng.integers(5, 13))
+        a = rng.integers(0, 20, size=la).astype(np.uint8)
+        b = rng.integers(0, 20, size=la).astype(np.uint8)
+        c = rng.integers(0, 20, size=la + 2).astype(np.uint8)
+        diff_equal += O.score_with_shift(a, b, A, 2, 0)[0] != O.score_with_shift(b, a, A, 2, 0)[0]
+        diff_unequal += O.score_with_shift(a, c, A, 2, 0)[0] != O.score_with_shift(c, a, A, 2, 0)[0]
+    assert diff_equal > 0 and diff_unequal == 0
