@@ -10,6 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HMK_LIB") or os.path.join(HERE, "libhammock_b200.so")
 
+FLAG_P2_REUSED, FLAG_XHIT_OVERFLOW, FLAG_ASYMMETRIC = 1, 2, 4
 STATUS_OK, STATUS_SHIFT_TOO_BIG, STATUS_NULL_CLUSTER, STATUS_BAD_RESIDUE, STATUS_CUDA, STATUS_BAD_ARG = range(6)
 
 
@@ -35,13 +36,13 @@ class Stats(C.Structure):
                 ("p1_restarts", C.c_int32), ("p2_queries", C.c_int32), ("p2_assigned", C.c_int32),
                 ("p2_rounds", C.c_int32), ("p2_hits", C.c_int64), ("p2_candidates", C.c_int64),
                 ("fast_path", C.c_int32), ("lane_bits", C.c_int32), ("error_step", C.c_int32),
-                ("pad_", C.c_int32)]
+                ("flags", C.c_int32), ("xhits_kept", C.c_int64), ("xhits_capacity", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["hmk_abi_version", "hmk_greedy_cluster", "hmk_create", "hmk_destroy", "hmk_upload", "hmk_run",
+EXPORTS = ["hmk_abi_version", "hmk_greedy_cluster", "hmk_greedy_cluster_multi", "hmk_create", "hmk_destroy", "hmk_upload", "hmk_run",
            "hmk_download", "hmk_get_stats", "hmk_get_section_ms", "hmk_set_option", "hmk_score_block",
            "hmk_timer_begin", "hmk_timer_end", "hmk_measure_peaks", "hmk_nccl_unique_id", "hmk_init_distributed", "hmk_release_cached"]
 SECTIONS = ["p1_select", "p1_partner", "p1_cluster", "p1_intra", "p1_resolve", "p2_setup", "p2_filter", "p2_check",
@@ -65,6 +66,8 @@ def load():
     L.hmk_abi_version.restype = C.c_int
     L.hmk_greedy_cluster.restype = C.c_int
     L.hmk_greedy_cluster.argtypes = [C.POINTER(GreedyIn), C.POINTER(GreedyOut), C.c_int, cp, sz]
+    L.hmk_greedy_cluster_multi.restype = C.c_int
+    L.hmk_greedy_cluster_multi.argtypes = [C.POINTER(GreedyIn), C.POINTER(GreedyOut), i32p, C.c_int32, cp, sz]
     L.hmk_create.restype = C.c_int
     L.hmk_create.argtypes = [C.POINTER(vp), C.c_int, cp, sz]
     L.hmk_destroy.restype = None

@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + SOURCES
+           "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", LIB] + SOURCES
     # the image exports CC/CXX wrappers that lack parts of the toolchain; use the system g++
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]

@@ -24,6 +24,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <dlfcn.h>
@@ -118,6 +119,22 @@ struct DevBuf {
     }
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: the sizes already
+// configured are tracked per Engine (one Engine = one device), never in process-wide statics, so a host
+// that drives device 0 and then device 1 from one process configures both.
+struct SmemConfig {
+    std::map<const void*, size_t> done;
+    template <class K>
+    void ensure(K kernel, size_t smem) {
+        const void* f = reinterpret_cast<const void*>(kernel);
+        size_t& have = done[f];
+        if (smem > have) {
+            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            have = smem;
+        }
+    }
+};
+
 enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_RESOLVE, SEC_P2_SETUP, SEC_P2_FILTER,
        SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
 
@@ -135,6 +152,7 @@ struct Options {
     int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
     int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
+    int64_t p2_spec = 3;          // phase-2 fixed-point iterations enqueued per host round trip
 };
 
 class Engine {
@@ -158,6 +176,7 @@ public:
         for (auto& b : bb_) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
         CK(cudaMallocHost(&h_ctl_, sizeof(HmkCtl)));
         CK(cudaMallocHost(&h_scalars_, 16 * sizeof(int32_t)));
+        CK(cudaMallocHost(&h_p2flags_, HMK_P2_FLAGS * sizeof(int32_t)));
         CK(cudaEventCreate(&ev_a_));
         CK(cudaEventCreate(&ev_b_));
         CK(cudaEventCreate(&ev_c_));
@@ -174,6 +193,7 @@ public:
         if (ev_t1_) cudaEventDestroy(ev_t1_);
         if (h_ctl_) cudaFreeHost(h_ctl_);
         if (h_scalars_) cudaFreeHost(h_scalars_);
+        if (h_p2flags_) cudaFreeHost(h_p2flags_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
         for (auto& b : bb_) if (b.ready) cudaEventDestroy(b.ready);
         if (st2_) cudaStreamDestroy(st2_);
@@ -199,6 +219,10 @@ public:
     }
     void measure_peaks(double* out);
     void init_distributed(int rank, int world, const void* id128);
+    void release_comm() {
+        if (comm_) { cudaSetDevice(device_); NcclApi::get().CommDestroy(comm_); comm_ = nullptr; }
+        rank_ = 0; world_ = 1;
+    }
 
 private:
     // ---- problem
@@ -206,12 +230,13 @@ private:
     int rank_ = 0, world_ = 1;
     NcclApi::Comm comm_ = nullptr;
     DevBuf<int32_t> d_gcount_, d_gs_;
-    DevBuf<unsigned long long> d_gq_, d_gc_;
+    DevBuf<unsigned long long> d_gq_;
     void allgather(const void* send, void* recv, size_t bytes, cudaStream_t s) {
         NK(NcclApi::get().AllGather(send, recv, bytes, HMK_NCCL_CHAR, comm_, s));
     }
     int sm_count_ = 148;
     size_t smem_optin_ = 0;
+    SmemConfig smem_cfg_;
     cudaStream_t st_ = nullptr;
     int32_t n_ = 0, T_ = 0, X_ = 0, P_ = 0, K_ = 0;
     int32_t min_len_ = 0, max_len_ = 0;
@@ -236,6 +261,7 @@ private:
     DevBuf<HmkCtl> d_ctl_;
     HmkCtl* h_ctl_ = nullptr;
     int32_t* h_scalars_ = nullptr;
+    int32_t* h_p2flags_ = nullptr;
     // ---- phase-1 per-batch buffers, double buffered: while batch i is resolved on the main stream the
     // partner search of batch i+1 already runs on the side stream
     struct BatchBuf {
@@ -258,7 +284,7 @@ private:
     void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s);
     // ---- phase-1 scratch
     DevBuf<int32_t> d_qid_, d_nq_,
-        d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_, d_dirty_b_;
+        d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_;
     // phase-1 partner-search hits kept for phase 2 (opt.reuse): buffer, 64-bit counters [0] appended, [1] valid
     DevBuf<int4> d_xhits_;
     DevBuf<unsigned long long> d_xcount_;
@@ -272,9 +298,9 @@ private:
     DevBuf<unsigned int> d_counts_;   // [0] hit_count, [1] cand_count
     DevBuf<unsigned long long> d_pairctr_;
     // ---- phase-2 scratch
-    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cq_q_, d_cc_q_, d_qstart_, d_cstart_,
-        d_a0_, d_a1_, d_dyn_, d_dyn_n_, d_flags_, d_base_cl_, d_wlo_, d_tent_, d_tent_s_, d_tent_n_;
-    DevBuf<unsigned long long> d_key_q_, d_key_c_, d_key_tmp_;
+    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_qstart_, d_cstart_, d_ccount_,
+        d_a0_, d_dyn_, d_dyn_n_, d_flags_, d_base_cl_, d_tent_, d_tent_n_, d_p2flags_;
+    DevBuf<unsigned long long> d_key_q_, d_key_tmp_;
     DevBuf<unsigned char> d_cub_;
     DevBuf<uint32_t> d_fprof_;
     // ---- outputs
@@ -328,7 +354,8 @@ public:
 private:
     void fetch_ctl() {
         CK(cudaMemcpyAsync(h_ctl_, d_ctl_.p, sizeof(HmkCtl), cudaMemcpyDeviceToHost, st_));
-        if (getenv("HMK_DEBUG_HANG")) {      // debugging aid: report where the device is stuck instead of waiting forever
+#ifdef HMK_DEBUG
+        if (getenv("HMK_DEBUG_HANG")) {      // debugging aid (debug builds only): report where the device is stuck
             for (int i = 0; i < 5000 && cudaStreamQuery(st_) == cudaErrorNotReady; i++) usleep(1000);
             if (cudaStreamQuery(st_) == cudaErrorNotReady) {
                 cudaStream_t s3;
@@ -340,9 +367,10 @@ private:
                         h_ctl_->steps, (long long)h_ctl_->dbg[0], (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3],
                         (unsigned long long)h_ctl_->dbg[4], (unsigned long long)h_ctl_->dbg[5], (unsigned long long)h_ctl_->dbg[6], (unsigned long long)h_ctl_->dbg[7]);
                 fflush(stderr);
-                _exit(3);
+                throw CudaError("device did not answer within 5 s (HMK_DEBUG_HANG)");
             }
         }
+#endif
         CK(cudaStreamSynchronize(st_));
     }
     int phase1();
@@ -419,13 +447,18 @@ void Engine::upload(const hmk_greedy_in* in) {
     CK(cudaSetDevice(device_));
     if (!in || in->n < 0 || (in->n > 0 && (!in->residues || !in->offsets || !in->abundance)) || !in->matrix)
         throw std::invalid_argument("hmk_upload: null input");
+    uploaded_ = false;
+    ran_ = false;
+    if (in->n > 0 && in->offsets[0] != 0) throw std::invalid_argument("hmk_upload: offsets[0] must be 0");
+    for (int i = 0; i < in->n; i++)      // int32 prefix offsets: monotone also rules out a total length beyond int32
+        if (in->offsets[i + 1] < in->offsets[i]) throw std::invalid_argument("hmk_upload: offsets not monotone");
     n_ = in->n; T_ = in->threshold; X_ = in->max_shift; P_ = in->shift_penalty; K_ = in->max_clusters;
-    h_off_.assign(in->offsets, in->offsets + n_ + 1);
+    if (n_) h_off_.assign(in->offsets, in->offsets + n_ + 1);
+    else h_off_.assign(1, 0);
     const size_t total = n_ ? (size_t)h_off_[n_] : 0;
     min_len_ = n_ ? INT32_MAX : 0; max_len_ = 0;
     for (int i = 0; i < n_; i++) {
         int l = h_off_[i + 1] - h_off_[i];
-        if (l < 0) throw std::invalid_argument("hmk_upload: offsets not monotone");
         min_len_ = std::min(min_len_, l); max_len_ = std::max(max_len_, l);
     }
     d_res_.reserve(total + 16); d_off_.reserve(n_ + 1); d_ab_.reserve(n_); d_M_.reserve(HMK_NRES * HMK_NRES);
@@ -526,67 +559,49 @@ void Engine::launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* pro
 }
 
 template <int NW, int MODE>
-static void launch_fast_inst(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
-    static bool configured = false;
-    static size_t configured_smem = 0;
-    if (!configured || smem > configured_smem) {
-        CK(cudaFuncSetAttribute(hmk_bulk_fast<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-        configured_smem = smem;
-    }
+static void launch_fast_inst(SmemConfig& cfg, const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    cfg.ensure(hmk_bulk_fast<NW, MODE>, smem);
     hmk_bulk_fast<NW, MODE><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
 }
 
 template <int MODE>
-static void launch_long_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
-    static size_t configured_smem = 0;
-    if (smem > configured_smem) {
-        CK(cudaFuncSetAttribute(hmk_bulk_long<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_smem = smem;
-    }
+static void launch_long_mode(SmemConfig& cfg, const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    cfg.ensure(hmk_bulk_long<MODE>, smem);
     hmk_bulk_long<MODE><<<grid, HMK_LONG_THREADS, smem, st>>>(a);
 }
 
 template <int MODE>
-static void launch_filter_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
-    static size_t configured_smem = 0;
+static void launch_filter_mode(SmemConfig& cfg, const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
     if (MODE == HMK_MODE_DENSE) {      // every score is wanted: exact kernel on the filter-layout profiles
-        if (smem > configured_smem) {
-            CK(cudaFuncSetAttribute(hmk_bulk_fast<2, HMK_MODE_DENSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured_smem = smem;
-        }
+        cfg.ensure(hmk_bulk_fast<2, HMK_MODE_DENSE, true>, smem);
         hmk_bulk_fast<2, HMK_MODE_DENSE, true><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
     } else {
         constexpr int M2 = MODE == HMK_MODE_DENSE ? HMK_MODE_EMIT : MODE;
-        if (smem > configured_smem) {
-            CK(cudaFuncSetAttribute(hmk_bulk_filter<M2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(hmk_bulk_filter<M2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured_smem = smem;
+        if (a.sc.L == 12) {
+            cfg.ensure(hmk_bulk_filter<M2, 12>, smem);
+            hmk_bulk_filter<M2, 12><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
+        } else {
+            cfg.ensure(hmk_bulk_filter<M2, 0>, smem);
+            hmk_bulk_filter<M2, 0><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
         }
-        if (a.sc.L == 12) hmk_bulk_filter<M2, 12><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
-        else hmk_bulk_filter<M2, 0><<<grid, HMK_BULK_THREADS, smem, st>>>(a);
     }
 }
 
 template <int MODE>
-static void launch_fast_mode(const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
-    if (a.sc.long_layout) { launch_long_mode<MODE>(a, grid, smem, st); return; }
-    if (a.sc.filter) { launch_filter_mode<MODE>(a, grid, smem, st); return; }
+static void launch_fast_mode(SmemConfig& cfg, const HmkBulkArgs& a, int grid, size_t smem, cudaStream_t st) {
+    if (a.sc.long_layout) { launch_long_mode<MODE>(cfg, a, grid, smem, st); return; }
+    if (a.sc.filter) { launch_filter_mode<MODE>(cfg, a, grid, smem, st); return; }
     switch (a.sc.nw) {
-        case 1: launch_fast_inst<1, MODE>(a, grid, smem, st); break;
-        case 2: launch_fast_inst<2, MODE>(a, grid, smem, st); break;
-        case 3: launch_fast_inst<3, MODE>(a, grid, smem, st); break;
-        default: launch_fast_inst<4, MODE>(a, grid, smem, st); break;
+        case 1: launch_fast_inst<1, MODE>(cfg, a, grid, smem, st); break;
+        case 2: launch_fast_inst<2, MODE>(cfg, a, grid, smem, st); break;
+        case 3: launch_fast_inst<3, MODE>(cfg, a, grid, smem, st); break;
+        default: launch_fast_inst<4, MODE>(cfg, a, grid, smem, st); break;
     }
 }
 
 template <int MODE>
-static void launch_generic_mode(const HmkGenericArgs& g, int grid, size_t smem, cudaStream_t st) {
-    static size_t configured_smem = 0;
-    if (smem > configured_smem) {
-        CK(cudaFuncSetAttribute(hmk_bulk_generic<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_smem = smem;
-    }
+static void launch_generic_mode(SmemConfig& cfg, const HmkGenericArgs& g, int grid, size_t smem, cudaStream_t st) {
+    cfg.ensure(hmk_bulk_generic<MODE>, smem);
     hmk_bulk_generic<MODE><<<grid, HMK_GENERIC_THREADS, smem, st>>>(g);
 }
 
@@ -636,18 +651,18 @@ void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const
         size_t smem = (((size_t)a.qt * sch->prof_words * 4 + 15) & ~(size_t)15) + 16 +
                       hmk_carve_bytes(a.qt, a.kb, sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS, false);
         if (sch->filter) smem += 16 + (size_t)(HMK_BULK_THREADS / 32) * HMK_CQCAP * 12;   // candidate queues
-        if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(a, grid, smem, s);
-        else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(a, grid, smem, s);
-        else launch_fast_mode<HMK_MODE_DENSE>(a, grid, smem, s);
+        if (mode == HMK_MODE_TOPK) launch_fast_mode<HMK_MODE_TOPK>(smem_cfg_, a, grid, smem, s);
+        else if (mode == HMK_MODE_EMIT) launch_fast_mode<HMK_MODE_EMIT>(smem_cfg_, a, grid, smem, s);
+        else launch_fast_mode<HMK_MODE_DENSE>(smem_cfg_, a, grid, smem, s);
     } else {
         HmkGenericArgs g;
         g.b = a; g.prof_ids = prof_ids; g.prof_is_query = prof_is_query;
         g.res = d_res_.p; g.off = d_off_.p; g.M = d_M_.p; g.maxlen = std::max(max_len_, 1);
         size_t smem = HMK_NRES * HMK_NRES * 4 + hmk_carve_bytes(a.qt, a.kb, HMK_GENERIC_THREADS, true) +
                       (size_t)a.qt * 4 + (size_t)a.qt * g.maxlen + 16;
-        if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(g, grid, smem, s);
-        else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(g, grid, smem, s);
-        else launch_generic_mode<HMK_MODE_DENSE>(g, grid, smem, s);
+        if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(smem_cfg_, g, grid, smem, s);
+        else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(smem_cfg_, g, grid, smem, s);
+        else launch_generic_mode<HMK_MODE_DENSE>(smem_cfg_, g, grid, smem, s);
     }
     CK(cudaGetLastError());
     if (opt.profile) { CK(cudaEventRecord(e1, s)); bulk_events_.push_back({e0, e1}); }
@@ -915,11 +930,7 @@ int Engine::phase1() {
             const size_t room = avail > fixed ? avail - fixed : 0;
             const int cache_entries = (int)std::min<size_t>(room / HMK_RESOLVE_CAND_BYTES, (size_t)nq * capq);
             const size_t smem = fixed + (size_t)cache_entries * HMK_RESOLVE_CAND_BYTES;
-            static size_t configured = 0;
-            if (smem > configured) {
-                CK(cudaFuncSetAttribute(hmk_p1_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-                configured = avail;
-            }
+            smem_cfg_.ensure(hmk_p1_resolve_kernel, avail);
             hmk_p1_resolve_kernel<<<1, HMK_RESOLVE_THREADS, smem, st_>>>(state(), pb, cache_entries);
         }
         CK(cudaGetLastError());
@@ -935,9 +946,11 @@ int Engine::phase1() {
         fetch_ctl();
         cb.valid = false;
         const int st = h_ctl_->status;
+#ifdef HMK_DEBUG
         if (getenv("HMK_DEBUG_BATCH"))
             fprintf(stderr, "batch %d nq %d: cur %d ncl %d unproc %d status %d steps %d ahead %d\n", cb.batch_id, nq, h_ctl_->cur, h_ctl_->ncl,
                     h_ctl_->unproc_alive, st, h_ctl_->steps, (int)ahead);
+#endif
         if (st != HMK_P1_CONTINUE && nb.valid) {     // the look-ahead batch does not follow this one after all
             CK(cudaStreamSynchronize(st2_));
             nb.valid = false;
@@ -967,8 +980,8 @@ void Engine::phase2() {
     size_t hit_cap = d_hits_.cap ? d_hits_.cap : (size_t)opt.hit_cap;
     d_hits_.reserve(hit_cap);
     size_t cand_cap = std::max<size_t>(1 << 20, (size_t)ns / 2);
-    d_key_q_.reserve(cand_cap); d_key_c_.reserve(cand_cap); d_cand_score_.reserve(cand_cap);
-    cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
+    d_key_q_.reserve(cand_cap); d_cand_score_.reserve(cand_cap);
+    cand_cap = std::min(d_key_q_.cap, d_cand_score_.cap);
     size_t ncand = 0;
     // candidate keys: two tight fields; 2^bits > count, so the all-ones padding keys of the multi-GPU exchange
     // stay above every real key
@@ -1005,14 +1018,14 @@ void Engine::phase2() {
             if (nh) {
                 if (ncand + nh > cand_cap) {
                     size_t nc = std::max(cand_cap * 2, ncand + nh);
-                    d_key_q_.grow_keep(nc, ncand, st_); d_key_c_.grow_keep(nc, ncand, st_); d_cand_score_.grow_keep(nc, ncand, st_);
+                    d_key_q_.grow_keep(nc, ncand, st_); d_cand_score_.grow_keep(nc, ncand, st_);
                     cand_cap = nc;
                 }
                 HmkCheckArgs c{};
                 c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
                 c.hit_t_is_query = 0; c.qids = nullptr; c.sidx = d_sidx_.p;
-                c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
-                c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits; c.qbits = qbits;
+                c.cand_key_q = d_key_q_.p; c.cand_score = d_cand_score_.p;
+                c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits;
                 c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
                 hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
                 CK(cudaGetLastError());
@@ -1037,6 +1050,8 @@ void Engine::phase2() {
         memcpy(&nx, h_scalars_ + 10, sizeof(nx));
         xhit_want_ = (size_t)nx;
         reused = nx <= d_xhits_.cap;      // else: some hits were dropped -> separate founder pass below
+        stats.xhits_kept = (int64_t)nx; stats.xhits_capacity = (int64_t)d_xhits_.cap;
+        if (!reused) stats.flags |= HMK_FLAG_XHIT_OVERFLOW;
         if (world_ > 1) {                 // every rank must take the same path
             d_gcount_.reserve(world_ + 1);
             int32_t mine = reused ? 1 : 0;
@@ -1048,6 +1063,7 @@ void Engine::phase2() {
             for (int r = 0; r < world_; r++) reused = reused && all[r] != 0;
         }
     }
+    if (reused) stats.flags |= HMK_FLAG_P2_REUSED;
     if (reused) {
         sec(SEC_P2_CHECK);
         for (;;) {
@@ -1056,8 +1072,8 @@ void Engine::phase2() {
             HmkCheckArgs c{};
             c.S = state(); c.hits = d_xhits_.p; c.hit_t_is_query = 2; c.xhit_count = d_xcount_.p; c.hit_valid = d_xcount_.p + 1;
             c.qids = nullptr; c.sidx = d_sidx_.p;
-            c.cand_key_q = d_key_q_.p; c.cand_key_c = d_key_c_.p; c.cand_score = d_cand_score_.p;
-            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits; c.qbits = qbits;
+            c.cand_key_q = d_key_q_.p; c.cand_score = d_cand_score_.p;
+            c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
             hmk_member_check<<<sm_count_ * 8, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
@@ -1068,8 +1084,8 @@ void Engine::phase2() {
             ncand = (uint32_t)h_scalars_[1];
             if (ncand <= cand_cap) break;
             const size_t nc = ncand + ncand / 16;      // candidates beyond the capacity were only counted: redo
-            d_key_q_.reserve(nc); d_key_c_.reserve(nc); d_cand_score_.reserve(nc);
-            cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
+            d_key_q_.reserve(nc); d_cand_score_.reserve(nc);
+            cand_cap = std::min(d_key_q_.cap, d_cand_score_.cap);
         }
         unsigned long long nv;
         memcpy(&nv, h_scalars_ + 10, sizeof(nv));
@@ -1114,105 +1130,101 @@ void Engine::phase2() {
         for (int r = 0; r < world_; r++) { maxc = std::max<size_t>(maxc, counts[r]); total += counts[r]; }
         if (maxc > 0) {
             if (maxc > cand_cap) {
-                d_key_q_.grow_keep(maxc, ncand, st_); d_key_c_.grow_keep(maxc, ncand, st_); d_cand_score_.grow_keep(maxc, ncand, st_);
+                d_key_q_.grow_keep(maxc, ncand, st_); d_cand_score_.grow_keep(maxc, ncand, st_);
                 cand_cap = maxc;
             }
             if (maxc > ncand) {
                 CK(cudaMemsetAsync(d_key_q_.p + ncand, 0xff, sizeof(unsigned long long) * (maxc - ncand), st_));
-                CK(cudaMemsetAsync(d_key_c_.p + ncand, 0xff, sizeof(unsigned long long) * (maxc - ncand), st_));
                 CK(cudaMemsetAsync(d_cand_score_.p + ncand, 0, sizeof(int32_t) * (maxc - ncand), st_));
             }
             DevBuf<unsigned long long>& gq = d_gq_;   // persistent: swapped with the local lists below
-            DevBuf<unsigned long long>& gc = d_gc_;
             DevBuf<int32_t>& gs = d_gs_;
-            gq.reserve(maxc * world_); gc.reserve(maxc * world_); gs.reserve(maxc * world_);
+            gq.reserve(maxc * world_); gs.reserve(maxc * world_);
             NK(NcclApi::get().GroupStart());
             allgather(d_key_q_.p, gq.p, sizeof(unsigned long long) * maxc, st_);
-            allgather(d_key_c_.p, gc.p, sizeof(unsigned long long) * maxc, st_);
             allgather(d_cand_score_.p, gs.p, sizeof(int32_t) * maxc, st_);
             NK(NcclApi::get().GroupEnd());
             std::swap(d_key_q_.p, gq.p); std::swap(d_key_q_.cap, gq.cap);
-            std::swap(d_key_c_.p, gc.p); std::swap(d_key_c_.cap, gc.cap);
             std::swap(d_cand_score_.p, gs.p); std::swap(d_cand_score_.cap, gs.cap);
         }
         ncand = total;
         ncand_padded_ = maxc * world_;
-        cand_cap = std::min(d_key_q_.cap, std::min(d_key_c_.cap, d_cand_score_.cap));
+        cand_cap = std::min(d_key_q_.cap, d_cand_score_.cap);
     } else ncand_padded_ = ncand;
     stats.p2_candidates = (int64_t)ncand;
     sec(SEC_P2_SORT);
     if (ncand == 0) { sec(-1); return; }
     const int nc = (int)ncand;
     const int ncp = (int)ncand_padded_;   // >= nc: padded entries carry key ~0 and sort to the end
-    // group by query (ascending cluster inside a query) and by cluster (ascending query inside a cluster)
+    // group by query (ascending cluster inside a query); per cluster only the NUMBER of candidate pairs is needed
+    // (room for its joiners), so there is no second sort
     sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, cbits + qbits);
-    d_cq_c_.reserve(nc); d_cq_q_.reserve(nc); d_cc_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2);
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p, d_cq_q_.p);
+    d_cq_c_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2); d_ccount_.reserve(ncl + 1);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p, nullptr);
     hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, cbits, d_qstart_.p);
-    {
-        size_t bytes = 0;
-        d_key_tmp_.reserve(ncp);
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, cbits + qbits, st_));
-        d_cub_.reserve(bytes);
-        CK(cub::DeviceRadixSort::SortKeys(d_cub_.p, bytes, d_key_c_.p, d_key_tmp_.p, ncp, 0, cbits + qbits, st_));
-    }
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, qbits, d_cc_q_.p, nullptr);
-    hmk_segment_starts<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_key_tmp_.p, nc, ncl, qbits, d_cstart_.p);
+    CK(cudaMemsetAsync(d_ccount_.p, 0, sizeof(int32_t) * (ncl + 1), st_));
+    hmk_p2_count_clusters<<<sm_count_ * 8, 256, 0, st_>>>(d_cq_c_.p, nc, d_ccount_.p);
+    hmk_exclusive_scan<<<1, 1024, 0, st_>>>(d_ccount_.p, ncl, d_cstart_.p);
     CK(cudaGetLastError());
-    launches_ += 8;
-    d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_wlo_.reserve(ncl); d_tent_.reserve(nc); d_tent_s_.reserve(nc);
-    d_tent_n_.reserve(ncl); d_a0_.reserve(ns); d_a1_.reserve(ns); d_dirty_a_.reserve(ncl); d_dirty_b_.reserve(ncl);
+    launches_ += 4;
+    d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_tent_.reserve(nc);
+    d_tent_n_.reserve(2 * (size_t)ncl); d_a0_.reserve(2 * (size_t)ns); d_dirty_a_.reserve(2 * (size_t)ncl);
+    d_p2flags_.reserve(HMK_P2_FLAGS);
     CK(cudaMemsetAsync(d_dyn_n_.p, 0, sizeof(int32_t) * ncl, st_));
-    CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * ns, st_));
-    CK(cudaMemsetAsync(d_a1_.p, 0xff, sizeof(int32_t) * ns, st_));
+    CK(cudaMemsetAsync(d_base_cl_.p, 0, sizeof(int32_t) * nc, st_));
+    CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * 2 * (size_t)ns, st_));
     HmkP2 P{};
     P.S = state(); P.packed = fast_scalar_ ? d_packed_.p : nullptr; P.L = max_len_;
-    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_q = d_cq_q_.p; P.cq_s = d_cand_score_.p;
-    P.cstart = d_cstart_.p; P.cc_q = d_cc_q_.p; P.dyn = d_dyn_.p; P.dyn_n = d_dyn_n_.p;
-    P.base_cl = d_base_cl_.p; P.wlo = d_wlo_.p; P.tent = d_tent_.p; P.tent_s = d_tent_s_.p; P.tent_n = d_tent_n_.p;
-    P.changed = d_flags_.p + 1;
-    int32_t* cur = d_a0_.p;
-    int32_t* nxt = d_a1_.p;
+    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_s = d_cand_score_.p;
+    P.base_cl = d_base_cl_.p; P.cstart = d_cstart_.p; P.dyn = d_dyn_.p; P.dyn_n = d_dyn_n_.p;
+    P.tent = d_tent_.p; P.tent_n = d_tent_n_.p; P.a = d_a0_.p; P.dirty = d_dirty_a_.p; P.flags = d_p2flags_.p;
+    // the unrolled pair scorer of hmk_p2_decide: uniform length 12, max shift 3, lane-sized matrix entries
+    const bool p2_fast = fast_scalar_ && fast_ && max_len_ == HMK_MAXL1 && X_ == 3;
     // window size adapts to how hard the fixed point is: dense inputs (everything joins) need many
     // iterations per window unless few queries per cluster are in flight at a time
     const int Wmax = (int)std::max<int64_t>(1, opt.p2_window);
     int W = std::min(Wmax, std::max(1024, 8 * ncl));
     const int cgrid = (ncl + 255) / 256;
+    const int spec = (int)std::max<int64_t>(1, std::min<int64_t>(opt.p2_spec, 16));
+    int it = 0;
     for (int qa = 0; qa < ns;) {
         const int qb = std::min(ns, qa + W);
-        int iters = 0;
         P.qa = qa; P.qb = qb;
-        sec(SEC_P2_BASE);
-        hmk_p2_window_lo<<<cgrid, 256, 0, st_>>>(P);
-        hmk_p2_base<<<sm_count_ * 8, 256, 0, st_>>>(P);
-        launches_ += 2;
-        const int qgrid = (qb - qa + 7) / 8;      // one warp per query, 8 warps per block
         sec(SEC_P2_ITERATE);
-        int32_t* dcur = d_dirty_a_.p;
-        int32_t* dnxt = d_dirty_b_.p;
-        CK(cudaMemsetAsync(dcur, 0xff, sizeof(int32_t) * ncl, st_));      // -1: everything is dirty at first
-        for (;;) {
-            P.a_cur = cur; P.a_new = nxt; P.dirty_cur = dcur; P.dirty_nxt = dnxt;
-            CK(cudaMemsetAsync(dnxt, 0x7f, sizeof(int32_t) * ncl, st_));  // "no change"
-            CK(cudaMemsetAsync(d_tent_n_.p, 0, sizeof(int32_t) * ncl, st_));
-            CK(cudaMemsetAsync(d_flags_.p + 1, 0, sizeof(int32_t), st_));
-            hmk_p2_build_tent<<<(qb - qa + 255) / 256, 256, 0, st_>>>(P);
-            hmk_p2_sort_tent<<<(ncl * 32 + 255) / 256, 256, 0, st_>>>(P);
-            hmk_p2_decide<<<qgrid, 256, 0, st_>>>(P);
+        P.it = it;
+        hmk_p2_window_setup<<<cgrid, 256, 0, st_>>>(P);
+        launches_++;
+        const int qgrid = (qb - qa + 7) / 8;      // one warp per query, 8 warps per block
+        int iters = 0, converged = -1;
+        while (converged < 0) {
+            // a group of iterations without a host round trip: once one of them changes nothing, the rest return at once
+            const int g0 = it;
+            for (int k = 0; k < spec; k++) CK(cudaMemsetAsync(d_p2flags_.p + (it + k) % HMK_P2_FLAGS, 0, sizeof(int32_t), st_));
+            for (int k = 0; k < spec; k++, it++) {
+                P.it = it; P.first = iters == 0 && k == 0;
+                hmk_p2_build_tent<<<(qb - qa + 255) / 256, 256, 0, st_>>>(P);
+                hmk_p2_sort_tent<<<(ncl * 32 + 255) / 256, 256, 0, st_>>>(P);
+                if (p2_fast) hmk_p2_decide<true><<<qgrid, 256, 0, st_>>>(P);
+                else hmk_p2_decide<false><<<qgrid, 256, 0, st_>>>(P);
+                launches_ += 3;
+            }
             CK(cudaGetLastError());
-            launches_ += 3;
-            stats.p2_rounds++;
-            iters++;
-            CK(cudaMemcpyAsync(h_scalars_ + 8, d_flags_.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+            CK(cudaMemcpyAsync(h_p2flags_, d_p2flags_.p, sizeof(int32_t) * HMK_P2_FLAGS, cudaMemcpyDeviceToHost, st_));
             CK(cudaStreamSynchronize(st_));
-            if (!h_scalars_[8]) break;          // fixed point: tent lists == final joiners of this window
-            std::swap(cur, nxt);
-            std::swap(dcur, dnxt);
+            for (int k = 0; k < spec && converged < 0; k++) {
+                iters++;
+                if (!h_p2flags_[(g0 + k) % HMK_P2_FLAGS]) converged = g0 + k;      // fixed point: tent lists == final joiners of this window
+            }
         }
+        stats.p2_rounds += iters;
         sec(SEC_P2_COMMIT);
+        P.it = converged;
         hmk_p2_commit<<<cgrid, 256, 0, st_>>>(P);
         CK(cudaGetLastError());
         launches_++;
+        // the next window starts on the parity the converged iteration wrote last: a[] of later queries is still -1
+        // on both, tent_n / dirty are reset by the window setup
+        it = converged + 1;
         qa = qb;
         if (iters > 8) W = std::max(256, W / 2);
         else if (iters <= 5) W = std::min(Wmax, W * 2);
@@ -1237,6 +1249,7 @@ int Engine::run() {
     if (bad_residue_) return HMK_ERR_BAD_RESIDUE;
     stats.fast_path = fast_ ? 1 : (mixed_ ? 2 : 0);     // 2: packed kernel per length bucket (mixed lengths)
     stats.lane_bits = (fast_ || mixed_) ? (sc_.lane16 ? 16 : 8) : 32;
+    if (!sym_) stats.flags |= HMK_FLAG_ASYMMETRIC;
     CK(cudaEventRecord(ev_a_, st_));
     if (n_) {
         hmk_fill_i32<<<sm_count_ * 2, 256, 0, st_>>>(d_slot_.p, -1, (size_t)n_);
@@ -1286,12 +1299,14 @@ int Engine::run() {
     stats.bulk_kernel_ms = bulk_ms;
     stats.bulk_pairs = (int64_t)pc[0];
     stats.scalar_pairs = h_ctl_->scalar_pairs;
+#ifdef HMK_DEBUG
     if (getenv("HMK_DEBUG_TIMING"))
         fprintf(stderr, "resolver: %lld windows applied %lld lanes, %lld sequential steps\n", (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5],
                 (long long)h_ctl_->dbg[6]);
     if (getenv("HMK_DEBUG_TIMING"))
         fprintf(stderr, "resolver cycles: staging %lld window(rest) %lld bpart %lld static %lld eval %lld apply %lld window(pick) %lld window(bounds) %lld\n", (long long)h_ctl_->dbg[0],
                 (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3], (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5], (long long)h_ctl_->dbg[7], (long long)h_ctl_->dbg[6]);
+#endif
     if (min_len_ == max_len_) {
         stats.bulk_cells = stats.bulk_pairs * hmk_pair_cells(max_len_, max_len_, X_);
         stats.bulk_ops = stats.bulk_cells + stats.bulk_pairs * (2 * (int64_t)X_ + 1);
@@ -1312,6 +1327,8 @@ int Engine::run() {
 void Engine::download(hmk_greedy_out* out) {
     CK(cudaSetDevice(device_));
     if (!ran_) throw std::invalid_argument("hmk_download without a successful hmk_run");
+    if (!out || (n_ > 0 && (!out->cluster_id || !out->member_rank || !out->result_order)))
+        throw std::invalid_argument("hmk_download: null output array");
     const int ncl = h_ctl_->ncl;
     if (n_) {
         CK(cudaMemcpyAsync(out->cluster_id, d_cluster_id_.p, sizeof(int32_t) * n_, cudaMemcpyDeviceToHost, st_));
@@ -1406,9 +1423,33 @@ struct hmk_ctx {
     explicit hmk_ctx(int device) : engine(device) {}
 };
 
+// Contexts kept between one-shot calls, keyed by device.  Every access holds cache_mutex().  The map is
+// deliberately leaked at process exit: destroying it from a static destructor would call cudaFree /
+// cudaStreamDestroy / ncclCommDestroy after the CUDA runtime has been torn down.  A host that wants the
+// memory back calls hmk_release_cached().
+static std::mutex& cache_mutex() {
+    static std::mutex* mu = new std::mutex();
+    return *mu;
+}
 static std::map<int, std::unique_ptr<hmk_ctx>>& cached_ctx() {
-    static std::map<int, std::unique_ptr<hmk_ctx>> m;
-    return m;
+    static auto* m = new std::map<int, std::unique_ptr<hmk_ctx>>();
+    return *m;
+}
+// the device set of the last hmk_greedy_cluster_multi call (its contexts live in cached_ctx())
+static std::vector<int>& cached_group() {
+    static auto* g = new std::vector<int>();
+    return *g;
+}
+// caller holds cache_mutex().  The communicators of a group are destroyed inside one NCCL group call: one
+// thread destroying them one after the other could wait for its own later calls.
+static void clear_cached() {
+    if (!cached_group().empty() && NcclApi::get().ok) {
+        NcclApi::get().GroupStart();
+        for (auto& kv : cached_ctx()) if (kv.second) kv.second->engine.release_comm();
+        NcclApi::get().GroupEnd();
+    }
+    cached_group().clear();
+    cached_ctx().clear();
 }
 
 static void set_err(char* errbuf, size_t errlen, const char* msg) {
@@ -1447,7 +1488,10 @@ extern "C" {
 
 int hmk_abi_version(void) { return HMK_ABI_VERSION; }
 
-void hmk_release_cached(void) { cached_ctx().clear(); }
+void hmk_release_cached(void) {
+    std::lock_guard<std::mutex> lock(cache_mutex());
+    clear_cached();
+}
 
 int hmk_create(hmk_ctx** ctx, int device, char* errbuf, size_t errlen) {
     if (!ctx) return HMK_STATUS_BAD_ARG;
@@ -1536,21 +1580,24 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return HMK_STATUS_BAD_ARG;
     Options& o = ctx->engine.opt;
     std::string s(name);
-    if (s == "batch") o.batch = value;
-    else if (s == "qt") o.qt = value;
-    else if (s == "capq") o.capq = value;
-    else if (s == "lookahead") o.lookahead = value;
-    else if (s == "filter") o.filter = value;
-    else if (s == "reuse") o.reuse = value;
-    else if (s == "kb") o.kb = value;
-    else if (s == "waves") o.waves = value;
-    else if (s == "p2_chunk") o.p2_chunk = value;
-    else if (s == "hit_cap") o.hit_cap = value;
-    else if (s == "force_generic") o.force_generic = value;
-    else if (s == "profile") o.profile = value;
-    else if (s == "p2_window") o.p2_window = value;
-    else return HMK_STATUS_BAD_ARG;
-    return HMK_STATUS_OK;
+    // every knob has a range; values outside it are rejected instead of reaching a launch configuration
+    struct Knob { const char* name; int64_t* slot; int64_t lo, hi; };
+    const Knob knobs[] = {
+        {"batch", &o.batch, 0, HMK_MAXBATCH},       {"qt", &o.qt, 0, 255},
+        {"capq", &o.capq, 1, 1 << 20},              {"lookahead", &o.lookahead, 0, 2},
+        {"filter", &o.filter, 0, 1},                {"reuse", &o.reuse, 0, 1},
+        {"kb", &o.kb, 1, 32},                       {"waves", &o.waves, 1, 16},
+        {"p2_chunk", &o.p2_chunk, 1024, 1 << 24},   {"hit_cap", &o.hit_cap, 1024, (int64_t)1 << 30},
+        {"force_generic", &o.force_generic, 0, 1},  {"profile", &o.profile, 0, 1},
+        {"p2_window", &o.p2_window, 1, 1 << 24},    {"p2_spec", &o.p2_spec, 1, 16},
+    };
+    for (const Knob& k : knobs) {
+        if (s != k.name) continue;
+        if (value < k.lo || value > k.hi) return HMK_STATUS_BAD_ARG;
+        *k.slot = value;
+        return HMK_STATUS_OK;
+    }
+    return HMK_STATUS_BAD_ARG;
 }
 
 int hmk_score_block(hmk_ctx* ctx, const int32_t* first_ids, int32_t n_first, const int32_t* second_ids,
@@ -1566,9 +1613,9 @@ int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device,
     if (!in || !out) return HMK_STATUS_BAD_ARG;
     // one cached context per device: repeated calls reuse its device buffers (released by
     // hmk_release_cached or at process exit); calls are serialised
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
+    std::lock_guard<std::mutex> lock(cache_mutex());
     return guarded(errbuf, errlen, [&] {
+        if (!cached_group().empty()) clear_cached();      // contexts of a multi-GPU group carry a communicator: start afresh
         auto& slot = cached_ctx()[device];
         if (!slot) slot.reset(new hmk_ctx(device));
         hmk_ctx& ctx = *slot;
@@ -1579,6 +1626,74 @@ int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device,
         ctx.engine.download(out);
         return HMK_STATUS_OK;
     });
+}
+
+
+int hmk_greedy_cluster_multi(const hmk_greedy_in* in, hmk_greedy_out* out, const int32_t* devices, int32_t n_gpus,
+                             char* errbuf, size_t errlen) {
+    if (!in || !out || n_gpus < 1 || n_gpus > 64) return HMK_STATUS_BAD_ARG;
+    std::vector<int> devs(n_gpus);
+    for (int r = 0; r < n_gpus; r++) devs[r] = devices ? devices[r] : r;
+    for (int r = 0; r < n_gpus; r++)
+        for (int q = 0; q < r; q++)
+            if (devs[q] == devs[r]) { set_err(errbuf, errlen, "hmk_greedy_cluster_multi: duplicate device"); return HMK_STATUS_BAD_ARG; }
+    if (n_gpus == 1) return hmk_greedy_cluster(in, out, devs[0], errbuf, errlen);
+    std::lock_guard<std::mutex> lock(cache_mutex());
+    // one worker thread per device for every stage; a stage ends when all its threads have joined, so a
+    // failure before the first collective (allocation, bad input) is reported without leaving ranks waiting
+    std::vector<int> rcs(n_gpus, HMK_STATUS_OK);
+    std::vector<std::string> errs(n_gpus);
+    auto stage = [&](auto&& body) {
+        std::vector<std::thread> th;
+        for (int r = 0; r < n_gpus; r++)
+            th.emplace_back([&, r] {
+                char eb[512] = {0};
+                rcs[r] = guarded(eb, sizeof eb, [&] { return body(r); });
+                errs[r] = eb;
+            });
+        for (auto& t : th) t.join();
+        for (int r = 0; r < n_gpus; r++)
+            if (rcs[r] != HMK_STATUS_OK) return r;
+        return -1;
+    };
+    auto fail = [&](int r) {
+        set_err(errbuf, errlen, errs[r].c_str());
+        return rcs[r];
+    };
+    out->n_result = 0; out->n_multi = 0; out->error_step = -1;
+    if (cached_group() != devs) {       // (re)build the group: contexts + one NCCL communicator over them
+        clear_cached();
+        NcclApi::UniqueId id;
+        int rc0 = guarded(errbuf, errlen, [&] {
+            NcclApi& api = NcclApi::get();
+            if (!api.ok) throw CudaError("NCCL unavailable: " + api.error);
+            NK(api.GetUniqueId(&id));
+            return HMK_STATUS_OK;
+        });
+        if (rc0) return rc0;
+        std::vector<std::unique_ptr<hmk_ctx>> fresh(n_gpus);
+        int bad = stage([&](int r) {
+            fresh[r].reset(new hmk_ctx(devs[r]));
+            fresh[r]->engine.init_distributed(r, n_gpus, id.internal);
+            return HMK_STATUS_OK;
+        });
+        if (bad >= 0) return fail(bad);
+        for (int r = 0; r < n_gpus; r++) cached_ctx()[devs[r]] = std::move(fresh[r]);
+        cached_group() = devs;
+    }
+    std::vector<hmk_ctx*> ctx(n_gpus);
+    for (int r = 0; r < n_gpus; r++) ctx[r] = cached_ctx()[devs[r]].get();
+    int bad = stage([&](int r) { ctx[r]->engine.upload(in); return HMK_STATUS_OK; });
+    if (bad >= 0) return fail(bad);
+    bad = stage([&](int r) { return ctx[r]->engine.run(); });     // replicated decisions: every rank returns the same status
+    out->error_step = ctx[0]->engine.error_step;
+    if (bad >= 0) {
+        if (errs[bad].empty()) set_err(errbuf, errlen, status_text(rcs[bad]));
+        else set_err(errbuf, errlen, errs[bad].c_str());
+        if (rcs[bad] == HMK_STATUS_CUDA) clear_cached();      // a rank died mid-run: the group is not reusable
+        return rcs[bad];
+    }
+    return guarded(errbuf, errlen, [&] { ctx[0]->engine.download(out); return HMK_STATUS_OK; });
 }
 
 }  // extern "C"

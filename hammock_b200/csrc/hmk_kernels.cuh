@@ -976,9 +976,8 @@ struct HmkCheckArgs {
     // phase 1 output: per-query arrays ac_slot/ac_score[qi * capq + k], k < ac_cnt[qi]
     int32_t* ac_cnt; int32_t* ac_slot; int32_t* ac_score; int32_t capq;
     // phase 2 output: flat candidate arrays
-    unsigned long long* cand_key_q;   // (query index << cbits) | slot      -- fields packed tight: the radix sorts only
-    unsigned long long* cand_key_c;   // (slot << qbits) | query index         touch cbits + qbits bits
-    int32_t cbits, qbits;
+    unsigned long long* cand_key_q;   // (query index << cbits) | slot      -- fields packed tight: the radix sort only
+    int32_t cbits;                    //                                       touches cbits + qbits bits
     int32_t* cand_score;
     unsigned int* cand_count;
     unsigned int cand_cap;
@@ -1036,7 +1035,6 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         {
             const uint32_t gq = (uint32_t)qi;
             a.cand_key_q[pos] = ((unsigned long long)gq << a.cbits) | (uint32_t)c;
-            a.cand_key_c[pos] = ((unsigned long long)(uint32_t)c << a.qbits) | gq;
             a.cand_score[pos] = cl;
         }
     }
@@ -1734,13 +1732,25 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
 
 // ---------------------------------------------------------------- phase 2: windowed resolution
 // Candidate pairs (query q, cluster c) -- founder and every phase-1 member score >= T -- are
-// held grouped by query (cq_*) and grouped by cluster in query order (cc_q).  Queries are
-// resolved in windows of consecutive queries.  Inside a window the reference's sequential
-// decisions (LimitedGreedySequenceClusterer.java:59-66) are the unique fixed point of
+// held grouped by query (cq_*).  Queries are resolved in windows of consecutive queries.
+// Inside a window the reference's sequential decisions
+// (LimitedGreedySequenceClusterer.java:59-66) are the unique fixed point of
 //     A[q] = best valid cluster of q given { q' < q : A[q'] = c } as extra members of c,
 // reached by iterating that map from A = "nobody joins" (after t iterations the first t
 // queries are final; in practice a handful of iterations suffice).  Members that joined in
-// earlier windows are final and folded into base_cl once per window.
+// earlier windows are final.
+//
+// Per cluster the joiners live in one array dyn[cstart[c] ..]: first the dyn_n[c] FINAL phase-2 members
+// (query indices, join order == query order), then the tent_n[c] tentative joiners of the current
+// iteration, sorted.  Room: a cluster can never receive more joiners than it has candidate pairs.
+//
+// Iterations are enqueued in groups without a host round trip: iteration `it` leaves flags[it % R] != 0
+// iff some assignment changed, and every kernel of iteration it > 0 returns at once when the previous
+// iteration did not change anything (the fixed point has been reached; nothing may be touched any more).
+// Buffers indexed by iteration parity: a[2][ns], dirty[2][ncl], tent_n[2][ncl].
+#define HMK_P2_FLAGS 64
+#define HMK_P2_CLEAN 0x7f7f7f7f
+
 struct HmkP2 {
     HmkState S;
     const uint64_t* packed;   // NULL -> generic scalar scorer
@@ -1749,77 +1759,86 @@ struct HmkP2 {
     const int32_t* singles;   // [ns] ascending ids of the phase-2 queries
     const int32_t* qstart;    // [ns+1] into cq_*
     const int32_t* cq_c;      // candidate cluster slot (ascending inside a query)
-    const int32_t* cq_s;      // complete-linkage min over the phase-1 members
-    const int32_t* cq_q;      // query index of the pair (the key's other field)
-    const int32_t* cstart;    // [ncl+1] into cc_q / dyn / tent
-    const int32_t* cc_q;      // query index (into singles), ascending inside a cluster
-    int32_t* dyn;             // final phase-2 members (sequence ids): dyn[cstart[c] + t]
+    const int32_t* cq_s;      // complete-linkage min over the phase-1 members ("static" score)
+    int32_t* base_cl;         // per pair: HMK_JMIN = a FINAL phase-2 member of the cluster scores < T against the query
+    const int32_t* cstart;    // [ncl+1] into dyn / tent (candidate pairs per cluster, prefix sums)
+    int32_t* dyn;             // see above (query indices)
     int32_t* dyn_n;           // [ncl]
-    int32_t* base_cl;         // per pair: min over phase-1 and final phase-2 members, JMIN = invalid
-    int32_t* wlo;             // [ncl] first cc_q position of the current window
-    int32_t* tent;            // tentative in-window joiners (query indices) in arrival order: tent[wlo[c] + t]
-    int32_t* tent_s;          // ... in query order (hmk_p2_sort_tent)
-    int32_t* tent_n;          // [ncl]
-    const int32_t* a_cur;     // [ns] tentative assignment of this iteration (-1 = none)
-    int32_t* a_new;
-    int32_t* changed;
-    const int32_t* dirty_cur; // [ncl] smallest query whose tentative assignment to/from c changed last iteration
-    int32_t* dirty_nxt;
+    int32_t* tent;            // tentative joiners in arrival order (scratch, same offsets as the dyn tail)
+    int32_t* tent_n;          // [2][ncl]
+    int32_t* a;               // [2][ns] tentative assignment (-1 = none)
+    int32_t* dirty;           // [2][ncl] smallest query whose tentative assignment to/from c changed in the last iteration
+    int32_t* flags;           // [HMK_P2_FLAGS]
     int32_t qa, qb;           // window = queries [qa, qb)
+    int32_t it;               // iteration index (runs on across windows; parity selects the buffers)
+    int32_t first;            // 1: first iteration of its window (never skipped)
 };
 
-// fold the members that joined in earlier windows into the per-pair base value
-__global__ void hmk_p2_base(const HmkP2 P) {
-    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
-    hmk_load_matrix_smem(sM, P.S.M);
-    HmkScalar sc;
-    sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
-    const int e0 = P.qstart[P.qa], e1 = P.qstart[P.qb];
-    long long npairs = 0;
-    for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
-        const int32_t q = P.singles[P.cq_q[e]];
-        const int32_t c = P.cq_c[e];
-        int32_t cl = P.cq_s[e];
-        const int32_t* dm = P.dyn + P.cstart[c];
-        const int32_t nd = P.dyn_n[c];
-        for (int t = 0; t < nd; t++) {
-            int32_t s = hmk_scalar_score(P.S, sc, dm[t], q);   // ClinkageClusterScorer.java:36-44
-            npairs++;
-            if (s < cl) cl = s;
-            if (s < P.S.T) { cl = HMK_JMIN; break; }
-        }
-        P.base_cl[e] = cl;
-    }
-    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
-    if ((threadIdx.x & 31) == 0 && npairs) atomicAdd((unsigned long long*)&P.S.ctl->scalar_pairs, (unsigned long long)npairs);
+__device__ __forceinline__ bool hmk_p2_skip(const HmkP2& P) {
+    return !P.first && __ldcg(P.flags + (P.it - 1) % HMK_P2_FLAGS) == 0;
 }
 
-__global__ void hmk_p2_window_lo(const HmkP2 P) {
+// candidate pairs per cluster (cq_c is grouped by query, so neighbours rarely collide)
+__global__ void hmk_p2_count_clusters(const int32_t* __restrict__ cq_c, int n, int32_t* __restrict__ cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(cnt + cq_c[i], 1);
+}
+
+// single block: out[0..n] = exclusive prefix sums of cnt[0..n)
+__global__ void __launch_bounds__(1024) hmk_exclusive_scan(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ out) {
+    __shared__ int32_t part[1024];
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    int32_t s = 0;
+    for (int i = lo; i < hi; i++) s += cnt[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t run = 0;
+        for (int i = 0; i < (int)blockDim.x; i++) { const int32_t v = part[i]; part[i] = run; run += v; }
+        out[n] = run;
+    }
+    __syncthreads();
+    int32_t run = part[threadIdx.x];
+    for (int i = lo; i < hi; i++) { out[i] = run; run += cnt[i]; }
+}
+
+// start of a window: nobody joins, everything is dirty
+__global__ void hmk_p2_window_setup(const HmkP2 P) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.ncl) return;
-    int lo = P.cstart[c], hi = P.cstart[c + 1];
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.cc_q[mid] < P.qa) lo = mid + 1; else hi = mid; }
-    P.wlo[c] = lo;
+    const int par = P.it & 1;
+    P.tent_n[(size_t)par * P.ncl + c] = 0;
+    P.dirty[(size_t)par * P.ncl + c] = -1;
 }
 
 __global__ void hmk_p2_build_tent(const HmkP2 P) {
+    if (hmk_p2_skip(P)) return;
     const int qi = P.qa + blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= P.qb) return;
-    const int32_t c = P.a_cur[qi];
+    const int par = P.it & 1;
+    const int32_t c = P.a[(size_t)par * P.ns + qi];
     if (c < 0) return;
-    const int pos = atomicAdd(P.tent_n + c, 1);
-    P.tent[P.wlo[c] + pos] = qi;
+    const int pos = atomicAdd(P.tent_n + (size_t)par * P.ncl + c, 1);
+    P.tent[P.cstart[c] + P.dyn_n[c] + pos] = qi;
 }
 
-// one warp per cluster: rank sort of its tentative joiners (distinct query indices) into tent_s.  A popular
-// cluster can collect hundreds of joiners per window; a one-thread insertion sort made it the tail of every iteration
+// one warp per cluster: rank sort of its tentative joiners (distinct query indices) into the dyn tail.  A popular
+// cluster can collect hundreds of joiners per window.  Also resets the next iteration's counters.
 __global__ void hmk_p2_sort_tent(const HmkP2 P) {
+    if (hmk_p2_skip(P)) return;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= P.ncl) return;
-    const int n = P.tent_n[c];
-    const int32_t* t = P.tent + P.wlo[c];
-    int32_t* o = P.tent_s + P.wlo[c];
+    const int par = P.it & 1;
+    const int n = P.tent_n[(size_t)par * P.ncl + c];
+    if (lane == 0) {
+        P.tent_n[(size_t)(par ^ 1) * P.ncl + c] = 0;
+        P.dirty[(size_t)(par ^ 1) * P.ncl + c] = HMK_P2_CLEAN;
+    }
+    if (n == 0) return;
+    const int base = P.cstart[c] + P.dyn_n[c];
+    const int32_t* t = P.tent + base;
+    int32_t* o = P.dyn + base;
     for (int i = lane; i < n; i += 32) {
         const int32_t v = t[i];
         int r = 0;
@@ -1828,12 +1847,61 @@ __global__ void hmk_p2_sort_tent(const HmkP2 P) {
     }
 }
 
+// S(member, query) for many members against ONE query per warp.  FAST: uniform length 12, max shift 3, packed
+// words, matrix in shared memory; the query's row offsets are kept in registers, so a pair costs 77 x (address
+// add + LDS + accumulate) and the warp's loads of a step hit one matrix row (conflict free).
+template <bool FAST>
+struct HmkQueryScorer {
+    const HmkState& S;
+    HmkScalar sc;
+    int32_t q;
+    int32_t qrow[HMK_MAXL1];
+    __device__ __forceinline__ HmkQueryScorer(const HmkState& S_, const HmkScalar& sc_, int32_t q_) : S(S_), sc(sc_), q(q_) {
+        if (FAST) {
+            const uint64_t wq = sc.packed[q];
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
+        }
+    }
+    __device__ __forceinline__ int32_t score(int32_t member) const {
+        if (!FAST) return hmk_scalar_score(S, sc, member, q);
+        const uint64_t wm = sc.packed[member];
+        int32_t rm[HMK_MAXL1];
+#pragma unroll
+        for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
+        int32_t best = HMK_JMIN;
+#pragma unroll
+        for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
+            int32_t v = 2 * (k < 0 ? -k : k) * S.P;
+#pragma unroll
+            for (int j = 0; j < HMK_MAXL1; j++)
+                if (j - k >= 0 && j - k < HMK_MAXL1) v += sc.sM[qrow[j - k] + rm[j]];
+            best = v > best ? v : best;
+        }
+        return best;
+    }
+};
+
 // one warp per window query: its decision given the tentative joiners before it.  A query is
 // re-evaluated only if one of its candidate clusters changed (tentatively) at a position
-// before it in the previous iteration (dirty_cur[c] < qi).
-__global__ void hmk_p2_decide(const HmkP2 P) {
+// before it in the previous iteration (dirty[c] < qi).
+// Evaluation is lazy: the static score of a pair bounds its final score from above, so a candidate whose
+// static score is below the best valid score found so far is never evaluated.  Per chunk of 32 candidates:
+// (1) one lane per candidate scores the FIRST member the cluster gained in phase 2 (this rejects almost every
+// unrelated candidate), (2) the survivors with more members are evaluated one after the other, best static
+// score first, with the 32 lanes striding over the member list.
+template <bool FAST>
+__global__ void __launch_bounds__(256) hmk_p2_decide(const HmkP2 P) {
     __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    if (hmk_p2_skip(P)) return;
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int par = P.it & 1;
+    const int32_t* a_cur = P.a + (size_t)par * P.ns;
+    int32_t* a_new = P.a + (size_t)(par ^ 1) * P.ns;
+    const int32_t* dirty_cur = P.dirty + (size_t)par * P.ncl;
+    int32_t* dirty_nxt = P.dirty + (size_t)(par ^ 1) * P.ncl;
+    const int32_t* tent_n = P.tent_n + (size_t)par * P.ncl;
     const int qi = P.qa + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const bool inw = qi < P.qb;
     int e0 = 0, e1 = 0;
@@ -1841,10 +1909,10 @@ __global__ void hmk_p2_decide(const HmkP2 P) {
     bool dirty = false;
     if (inw) {
         e0 = P.qstart[qi]; e1 = P.qstart[qi + 1];
-        old = P.a_cur[qi];
-        for (int e = e0 + lane; e < e1; e += 32) dirty |= P.dirty_cur[P.cq_c[e]] < qi;
-        dirty = __any_sync(0xffffffffu, dirty);
-        if (!dirty && lane == 0) P.a_new[qi] = old;
+        old = a_cur[qi];
+        for (int e = e0 + lane; e < e1; e += 32) dirty |= dirty_cur[P.cq_c[e]] < qi;
+        dirty = __any_sync(FULL, dirty);
+        if (!dirty && lane == 0) a_new[qi] = old;
     }
     if (!__syncthreads_or(dirty)) return;      // after the first iterations most blocks have nothing to re-evaluate
     hmk_load_matrix_smem(sM, P.S.M);
@@ -1852,58 +1920,117 @@ __global__ void hmk_p2_decide(const HmkP2 P) {
     HmkScalar sc;
     sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
     const int32_t q = P.singles[qi];
+    const HmkQueryScorer<FAST> scorer(P.S, sc, q);
+    const int32_t T = P.S.T;
     long long npairs = 0;
-    HmkBestCluster best;
+    HmkBestCluster best;        // warp-uniform
     best.score = HMK_JMIN; best.size = 0; best.fid = 0; best.slot = -1;
-    for (int e = e0 + lane; e < e1; e += 32) {
-        int32_t cl = P.base_cl[e];
-        if (cl == HMK_JMIN) continue;
-        const int32_t c = P.cq_c[e];
-        int32_t size = P.S.c_size[c];
-        const int32_t* t = P.tent_s + P.wlo[c];
-        const int32_t nt = P.tent_n[c];
-        bool ok = true;
-        for (int i = 0; i < nt; i++) {
-            const int32_t mi = t[i];
-            if (mi >= qi) break;
-            const int32_t m = P.singles[mi];
-            const int32_t s = hmk_scalar_score(P.S, sc, m, q);
-            npairs++;
-            if (s < P.S.T) { ok = false; break; }
-            if (s < cl) cl = s;
-            size = hmk_wadd(size, P.S.ab[m]);
+    for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        int32_t c = -1, st = HMK_JMIN, cl = 0, off = 0, nd = 0, tn = 0;
+        uint32_t szadd = 0;
+        bool alive = false;
+        if (e < e1) {
+            c = P.cq_c[e]; st = P.cq_s[e]; cl = st;
+            alive = P.base_cl[e] != HMK_JMIN && !(best.slot >= 0 && st < best.score);
         }
-        if (ok) hmk_consider(best, cl, size, P.S.c_founder[c], c);
+        if (alive) { off = P.cstart[c]; nd = P.dyn_n[c]; tn = tent_n[c]; }
+        bool more = false;
+        if (alive && nd + tn > 0) {       // (1) the first phase-2 member
+            const int32_t mi = P.dyn[off];
+            if (nd == 0 && mi >= qi) tn = 0;            // every tentative joiner comes after q
+            else {
+                const int32_t m = P.singles[mi];
+                const int32_t s = scorer.score(m);
+                npairs++;
+                if (s < T) { alive = false; if (nd > 0) P.base_cl[e] = HMK_JMIN; }
+                else {
+                    cl = s < cl ? s : cl;
+                    if (nd == 0) szadd = (uint32_t)P.S.ab[m];
+                    more = nd + tn > 1;
+                }
+            }
+        }
+        {   // candidates that are already decided: fold them into the warp's best (prunes step 2)
+            HmkBestCluster mine;
+            mine.score = HMK_JMIN; mine.size = 0; mine.fid = 0; mine.slot = -1;
+            if (alive && !more) hmk_consider(mine, cl, (int32_t)((uint32_t)P.S.c_size[c] + szadd), P.S.c_founder[c], c);
+            if (__any_sync(FULL, mine.slot >= 0)) {
+                hmk_best_reduce(mine);
+                if (mine.slot >= 0) hmk_consider(best, mine.score, mine.size, mine.fid, mine.slot);
+            }
+        }
+        unsigned todo = __ballot_sync(FULL, more);
+        while (todo) {                    // (2) survivors with more members, best static score first
+            const bool in_todo = (todo >> lane) & 1u;
+            const int32_t mx = __reduce_max_sync(FULL, in_todo ? st : HMK_JMIN);
+            if (best.slot >= 0 && mx < best.score) break;          // nothing left can reach the best any more
+            const int pick = __ffs(__ballot_sync(FULL, in_todo && st == mx)) - 1;
+            const int32_t poff = __shfl_sync(FULL, off, pick), pnd = __shfl_sync(FULL, nd, pick), ptot = pnd + __shfl_sync(FULL, tn, pick);
+            bool ok = true, final_fail = false;
+            int32_t mn = HMK_JMAX;
+            uint32_t sz = 0;
+            for (int i0 = 1; i0 < ptot; i0 += 32) {
+                const int i = i0 + lane;
+                bool act = i < ptot;
+                const int32_t mi = act ? P.dyn[poff + i] : 0;
+                const bool behind = act && i >= pnd && mi >= qi;      // tentative joiners at or behind q do not count
+                act = act && !behind;
+                bool bad = false;
+                if (act) {
+                    const int32_t m = P.singles[mi];
+                    const int32_t s = scorer.score(m);
+                    npairs++;
+                    bad = s < T;
+                    mn = s < mn ? s : mn;
+                    if (i >= pnd) sz += (uint32_t)P.S.ab[m];
+                }
+                const unsigned badm = __ballot_sync(FULL, bad);
+                if (badm) { ok = false; final_fail = __any_sync(FULL, bad && i < pnd); break; }
+                if (__any_sync(FULL, behind)) break;                  // sorted: everything further is behind q as well
+            }
+            mn = __reduce_min_sync(FULL, mn);
+            sz = __reduce_add_sync(FULL, sz);
+            int32_t k_cl = 0, k_size = 0, k_fid = 0, k_c = -1;
+            if (lane == pick) {
+                if (!ok && final_fail) P.base_cl[e] = HMK_JMIN;
+                if (ok) { k_cl = mn < cl ? mn : cl; k_size = (int32_t)((uint32_t)P.S.c_size[c] + szadd + sz); k_fid = P.S.c_founder[c]; k_c = c; }
+            }
+            if (ok) {
+                k_cl = __shfl_sync(FULL, k_cl, pick); k_size = __shfl_sync(FULL, k_size, pick);
+                k_fid = __shfl_sync(FULL, k_fid, pick); k_c = __shfl_sync(FULL, k_c, pick);
+                hmk_consider(best, k_cl, k_size, k_fid, k_c);
+            }
+            todo &= ~(1u << pick);
+        }
     }
-    hmk_best_reduce(best);
     if (lane == 0) {
-        P.a_new[qi] = best.slot;
+        a_new[qi] = best.slot;
         if (best.slot != old) {
-            *P.changed = 1;
-            if (old >= 0) atomicMin(P.dirty_nxt + old, qi);
-            if (best.slot >= 0) atomicMin(P.dirty_nxt + best.slot, qi);
+            P.flags[P.it % HMK_P2_FLAGS] = 1;
+            if (old >= 0) atomicMin(dirty_nxt + old, qi);
+            if (best.slot >= 0) atomicMin(dirty_nxt + best.slot, qi);
         }
     }
-    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
+    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(FULL, npairs, s);
     if (lane == 0 && npairs) atomicAdd((unsigned long long*)&P.S.ctl->scalar_pairs, (unsigned long long)npairs);
 }
 
-// window converged: the tentative joiners become final members, in query order
+// window converged in iteration P.it: the tentative joiners become final members, in query order
 __global__ void hmk_p2_commit(const HmkP2 P) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.ncl) return;
-    const int n = P.tent_n[c];
+    const int n = P.tent_n[(size_t)(P.it & 1) * P.ncl + c];
     if (n == 0) return;
-    const int32_t* t = P.tent_s + P.wlo[c];
     int32_t nd = P.dyn_n[c], cnt = P.S.c_count[c], size = P.S.c_size[c];
+    const int32_t* t = P.dyn + P.cstart[c] + nd;
     for (int i = 0; i < n; i++) {
         const int32_t q = P.singles[t[i]];
-        P.dyn[P.cstart[c] + nd++] = q;
         P.S.rank[q] = cnt++;
         size = hmk_wadd(size, P.S.ab[q]);
         P.S.slot[q] = c;
     }
-    P.dyn_n[c] = nd; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
+    P.dyn_n[c] = nd + n; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
 }
 
 // ---------------------------------------------------------------- small utilities

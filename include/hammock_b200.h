@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HMK_ABI_VERSION 1
+#define HMK_ABI_VERSION 2
 
 /* status codes: the reference's failure modes on this path */
 #define HMK_STATUS_OK 0
@@ -78,8 +78,15 @@ typedef struct {
     int32_t fast_path;        /* 0: generic scalar kernel, 1: packed SWAR kernel (one length), 2: packed per length bucket */
     int32_t lane_bits;        /* 8 or 16 on the fast path                                             */
     int32_t error_step;       /* phase-1 step of HMK_STATUS_NULL_CLUSTER in the last run, else -1     */
-    int32_t pad_;
+    int32_t flags;            /* HMK_FLAG_* of the last run                                           */
+    int64_t xhits_kept;       /* phase-1 partner-search hits the run wanted to keep for phase 2       */
+    int64_t xhits_capacity;   /* entries the kept-hit buffer had; kept > capacity == overflow         */
 } hmk_stats;
+/* hmk_stats.flags */
+#define HMK_FLAG_P2_REUSED 1      /* phase 2 took its founder hits from the phase-1 partner searches   */
+#define HMK_FLAG_XHIT_OVERFLOW 2  /* the kept-hit buffer overflowed: this run paid the separate founder  */
+                                  /* pass (about 1.4x slower); the next run on this context sizes it right */
+#define HMK_FLAG_ASYMMETRIC 4     /* substitution matrix not symmetric: hit reuse not applicable        */
 
 typedef struct hmk_ctx hmk_ctx;
 
@@ -89,6 +96,15 @@ int hmk_abi_version(void);
  * keeps one context per device between calls (device buffers stay allocated, so repeated calls do not
  * pay allocation again); hmk_release_cached frees them. */
 int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen);
+/* The same blocking call on n_gpus devices of THIS process (SURVEY.md 8b's `n_gpus`): the reference's host is
+ * one JVM that calls cluster() once, synchronously (Hammock.java:409), so the library itself runs one worker
+ * thread per device and builds the NCCL communicator (one unique id, ncclCommInitRank per thread).
+ * devices == NULL means devices 0 .. n_gpus-1.  Contexts and the communicator are kept for the next call
+ * with the same device list.  The result is identical to the one-GPU result. */
+int hmk_greedy_cluster_multi(const hmk_greedy_in* in, hmk_greedy_out* out, const int32_t* devices, int32_t n_gpus,
+                             char* errbuf, size_t errlen);
+/* Frees the contexts the two calls above keep.  Call it before the process unloads CUDA if the memory
+ * matters; the library never tears them down from a static destructor. */
 void hmk_release_cached(void);
 
 /* Handle API: the same work split into upload / device-resident run / download, so that a
@@ -121,17 +137,18 @@ int hmk_measure_peaks(hmk_ctx* ctx, double* out4, char* errbuf, size_t errlen);
  * p2_base, p2_iterate, p2_commit, final */
 #define HMK_NSECTIONS 13
 int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n);
-/* tuning knobs; unknown names return HMK_STATUS_BAD_ARG.  None of them changes the result.
+/* tuning knobs; unknown names and out-of-range values return HMK_STATUS_BAD_ARG.  None of them changes the result.
  *   batch      phase-1 queries per batch (0 = automatic: 8 profile tiles, at most 512 and what the resolver's
  *              shared memory holds)
  *   kb         partner candidates kept per query (1..32, default 8)
  *   capq       initial capacity of the per-query cluster-candidate arrays (grown on demand)
- *   lookahead  1 = prepare batch i+1 on a side stream while batch i is resolved (default)
+ *   lookahead  batches prepared ahead on a side stream while batch i is resolved: 0, 1 or 2 (default 2)
  *   filter     1 = upper-bound filter + exact verify kernel where it applies (default), 0 = exact kernel only
  *   reuse      1 = phase 2 takes its founder hits from the phase-1 partner searches when the matrix is
  *              symmetric (default), 0 = always run the separate founder pass
  *   qt, waves  profiles per shared-memory tile (0 = as many as fit), grid waves per launch
  *   p2_chunk, p2_window, hit_cap   phase-2 chunking / window size / initial hit-buffer size
+ *   p2_spec    phase-2 fixed-point iterations enqueued per host round trip (1..16, default 3)
  *   force_generic  1 = scalar kernel for everything (correctness path)
  *   profile    1 = time every bulk launch with CUDA events (hmk_stats.bulk_kernel_ms) */
 int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value);

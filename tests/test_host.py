@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for sym in declared:
         assert getattr(L, sym) is not None
-    assert L.hmk_abi_version() == 1
+    assert L.hmk_abi_version() == 2 and re.search(r"#define HMK_ABI_VERSION 2\b", hdr)
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -268,7 +268,8 @@ def test_tuning_options_documented_in_header():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = open(os.path.join(root, "hammock_b200", "csrc", "hmk_engine.cu")).read()
     hdr = open(os.path.join(root, "include", "hammock_b200.h")).read()
-    accepted = set(re.findall(r'\(s == "([a-z0-9_]+)"\)', src))
+    table = src[src.index("const Knob knobs[]"):src.index("for (const Knob& k : knobs)")]
+    accepted = set(re.findall(r'\{"([a-z0-9_]+)", &o\.', table))
     assert {"batch", "kb", "lookahead", "filter", "reuse"} <= accepted
     doc = hdr[hdr.index("tuning knobs"):hdr.index("int hmk_set_option")]
     documented = set()
