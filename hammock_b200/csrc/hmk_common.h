@@ -86,7 +86,8 @@ enum {
     HMK_P1_DONE = 1,      // K clusters reached or list exhausted
     HMK_P1_NPE = 2,       // reference would throw NullPointerException at this step
     HMK_P1_RESTART = 3,   // partner list exhausted but truncated: rescore from ctl.cur
-    HMK_P1_GROW = 4       // per-query cluster-candidate arrays too small: grow and rescore from ctl.cur
+    HMK_P1_GROW = 4,      // per-query cluster-candidate arrays too small: grow and rescore from ctl.cur
+    HMK_P1_GROWHITS = 5   // the founder-hit buffer of the cluster search was too small (needed size in ctl.pad0): redo it
 };
 
 struct HmkCtl {

@@ -135,6 +135,7 @@ struct SmemConfig {
     }
 };
 
+enum { HMK_NBATCHBUF = 3 };   // the batch being resolved + up to two prepared ahead
 enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_RESOLVE, SEC_P2_SETUP, SEC_P2_FILTER,
        SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
 
@@ -143,7 +144,7 @@ struct Options {
     int64_t capq = 256;         // initial per-query capacity of the cluster-candidate arrays
     int64_t reuse = 1;          // 1: phase 2 takes its founder hits from the phase-1 partner searches (symmetric matrices)
     int64_t filter = 1;         // 1: filter + verify kernel where it applies (u8 lanes, two words, one length <= 12)
-    int64_t lookahead = 1;      // 1: prepare the next batch's partner search while the current batch resolves
+    int64_t lookahead = 2;      // batches whose partner search is prepared on the side stream while the current batch resolves (0..2)
     int64_t qt = 0;             // profiles per CTA tile (0 = as many as shared memory holds)
     int64_t kb = 8;             // partner candidates kept per query
     int64_t waves = 2;          // CTAs per SM targeted by the stripe split
@@ -153,6 +154,7 @@ struct Options {
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
     int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
     int64_t p2_spec = 3;          // phase-2 fixed-point iterations enqueued per host round trip
+    int64_t xhit_cap = 0;         // capacity of the kept-hit buffer (0 = automatic: the last run's need, else 96 per sequence)
 };
 
 class Engine {
@@ -279,12 +281,13 @@ private:
         int nq = 0;
         int batch_id = 0;
     };
-    BatchBuf bb_[2];
+    BatchBuf bb_[HMK_NBATCHBUF];
     cudaStream_t st2_ = nullptr;
     void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s);
     // ---- phase-1 scratch
     DevBuf<int32_t> d_qid_, d_nq_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_;
+    DevBuf<int4> d_ac_full_, d_ac_best_;
     // phase-1 partner-search hits kept for phase 2 (opt.reuse): buffer, 64-bit counters [0] appended, [1] valid
     DevBuf<int4> d_xhits_;
     DevBuf<unsigned long long> d_xcount_;
@@ -445,10 +448,10 @@ void Engine::choose_scheme(const int32_t* M) {
 
 void Engine::upload(const hmk_greedy_in* in) {
     CK(cudaSetDevice(device_));
+    uploaded_ = false;      // a rejected upload leaves nothing to run
+    ran_ = false;
     if (!in || in->n < 0 || (in->n > 0 && (!in->residues || !in->offsets || !in->abundance)) || !in->matrix)
         throw std::invalid_argument("hmk_upload: null input");
-    uploaded_ = false;
-    ran_ = false;
     if (in->n > 0 && in->offsets[0] != 0) throw std::invalid_argument("hmk_upload: offsets[0] must be 0");
     for (int i = 0; i < in->n; i++)      // int32 prefix offsets: monotone also rules out a total length beyond int32
         if (in->offsets[i + 1] < in->offsets[i]) throw std::invalid_argument("hmk_upload: offsets not monotone");
@@ -845,22 +848,23 @@ int Engine::phase1() {
     if (B <= 0) B = fast_ ? (sc_.filter ? 8 : 3) * qt_max() : 192;   // measured optimum on the 1 M workload
     B = std::max(1, std::min(B, HMK_MAXBATCH));
     opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
+    const size_t resolve_avail = smem_optin_ - 3 * HMK_HASH_SIZE * 4 - 1024;   // minus the kernel's static shared memory
     {   // the resolver keeps the whole batch's bookkeeping in shared memory
-        const size_t avail = smem_optin_ - 3 * HMK_HASH_SIZE * 4 - 1024;
-        auto need = [&](int b) {
-            return hmk_resolve_fixed_bytes(b, (b + 31) / 32, (int)opt.kb, (b + 3) & ~3, (b * (int)opt.kb + 3) & ~3) + 64;
-        };
-        while (B > 32 && need(B) > avail) B -= 32;
+        auto need = [&](int b) { return hmk_resolve_fixed_bytes(b, (b + 31) / 32, (int)opt.kb) + 64; };
+        while (B > 32 && need(B) > resolve_avail) B -= 32;
     }
-    opt.kb = std::max<int64_t>(1, std::min<int64_t>(opt.kb, 32));
     size_t capq = (size_t)std::max<int64_t>(1, opt.capq);
     d_ac_cnt_.reserve(B); d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
+    d_ac_full_.reserve((size_t)B * capq); d_ac_best_.reserve(B);
     batch_id_ = 0;
     reuse_ = opt.reuse && sym_ && K_ > 0 && n_ > 1;
     if (reuse_) {
         // room for every partner-search hit: the last run's need if known, else ~96 per sequence; a run that
-        // overflows falls back to the separate founder pass in phase 2 and remembers the size it needed
-        size_t want = xhit_want_ ? xhit_want_ + xhit_want_ / 8 : std::max<size_t>((size_t)1 << 20, (size_t)n_ * 96);
+        // overflows falls back to the separate founder pass in phase 2 (HMK_FLAG_XHIT_OVERFLOW) and remembers the
+        // size it needed
+        size_t want = opt.xhit_cap > 0 ? (size_t)opt.xhit_cap
+                      : xhit_want_   ? xhit_want_ + xhit_want_ / 8
+                                     : std::max<size_t>((size_t)1 << 20, (size_t)n_ * 96);
         want = std::min<size_t>(want, (size_t)1 << 30);
         d_xhits_.reserve(want); d_xcount_.reserve(2); d_qbatch_.reserve(n_);
         CK(cudaMemsetAsync(d_xcount_.p, 0, 2 * sizeof(unsigned long long), st_));
@@ -868,22 +872,17 @@ int Engine::phase1() {
     }
     size_t hit_cap = (size_t)opt.hit_cap;
     d_hits_.reserve(hit_cap);
-    bb_[0].valid = bb_[1].valid = false;
-    int which = 0;
+    for (auto& b : bb_) b.valid = false;
+    const int depth = (int)std::max<int64_t>(0, std::min<int64_t>(opt.lookahead, HMK_NBATCHBUF - 1));
+    int head = 0;
     fetch_ctl();
     while (h_ctl_->ncl < K_ && h_ctl_->unproc_alive > 0) {
-        BatchBuf& cb = bb_[which];
-        BatchBuf& nb = bb_[which ^ 1];
+        BatchBuf& cb = bb_[head];
         const int cur = h_ctl_->cur, ncl = h_ctl_->ncl;
         sec(SEC_P1_PARTNER);
         if (!cb.valid) stage_partner_search(cb, std::min(B, h_ctl_->unproc_alive), cur, nullptr, st_);   // not prepared ahead
         else CK(cudaStreamWaitEvent(st_, cb.ready, 0));
         const int nq = cb.nq;
-        // look ahead: the next batch's partner search (and everything else that does not depend on the
-        // clustering state) runs on the side stream while this batch is resolved; it is issued right
-        // behind the resolver so that the resolver's CTA is placed first.  It only needs this batch's last
-        // query id; whatever this batch consumes in the meantime is filtered by the resolver's consumed set
-        const bool ahead = opt.lookahead && !nb.valid && nq == B && h_ctl_->unproc_alive >= nq + 3 * B;
         const int32_t* d_qid = cb.qid.p;
         const uint32_t* d_prof = cb.prof.p;
         // A: clusters whose founder scores >= T, then complete linkage over their members
@@ -906,65 +905,76 @@ int Engine::phase1() {
             CK(cudaGetLastError());
             launches_++;
         }
+        hmk_p1_prepare_candidates<<<(nq * 32 + 255) / 256, 256, 0, st_>>>(state(), nq, (int)capq, d_ac_cnt_.p, d_ac_slot_.p, d_ac_score_.p,
+                                                                         d_ac_full_.p, d_ac_best_.p);
+        launches_++;
         const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * (int)opt.kb + 3) & ~3;
         const int nw = (nq + 31) / 32;
         HmkP1Batch pb{};
         pb.nq = nq; pb.batch_id = cb.batch_id; pb.qid = d_qid; pb.kb = (int)opt.kb;
         pb.bk_key = cb.bk_key.p; pb.bk_cnt = cb.bk_cnt.p; pb.bk_ovf = cb.bk_ovf.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
+        pb.ac_full = d_ac_full_.p; pb.best = d_ac_best_.p;
+        pb.hit_count = d_counts_.p; pb.hit_cap = (unsigned int)hit_cap;   // truncated hit lists: the resolver returns HMK_P1_GROWHITS
         pb.ib = cb.ib.p; pb.ib_stride = ib_stride; pb.ibm = cb.ibm.p; pb.ibm2 = cb.ibm2.p; pb.nw = nw;
         pb.pcand = cb.pcand.p;
         pb.pd = cb.pd.p; pb.pd_stride = pd_stride;
-        // the resolver must not run on truncated hit lists: checked on the host first
-        CK(cudaMemcpyAsync(h_scalars_, d_counts_.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
-        CK(cudaStreamSynchronize(st_));
-        if ((size_t)(uint32_t)h_scalars_[0] > hit_cap) {   // grow and redo this batch (state untouched)
-            hit_cap = (size_t)(uint32_t)h_scalars_[0] * 5 / 4 + 1024;
-            d_hits_.reserve(hit_cap);
-            continue;       // cb stays valid: only the cluster search is redone
-        }
         sec(SEC_P1_RESOLVE);
         {
-            const size_t fixed = hmk_resolve_fixed_bytes(nq, nw, (int)opt.kb, ib_stride, pd_stride) + 64;
-            const size_t avail = smem_optin_ - 3 * HMK_HASH_SIZE * 4 - 1024;   // minus the kernel's static shared memory
-            const size_t room = avail > fixed ? avail - fixed : 0;
+            const size_t fixed = hmk_resolve_fixed_bytes(nq, nw, (int)opt.kb) + 64;
+            const size_t room = resolve_avail > fixed ? resolve_avail - fixed : 0;
             const int cache_entries = (int)std::min<size_t>(room / HMK_RESOLVE_CAND_BYTES, (size_t)nq * capq);
             const size_t smem = fixed + (size_t)cache_entries * HMK_RESOLVE_CAND_BYTES;
-            smem_cfg_.ensure(hmk_p1_resolve_kernel, avail);
+            smem_cfg_.ensure(hmk_p1_resolve_kernel, resolve_avail);
             hmk_p1_resolve_kernel<<<1, HMK_RESOLVE_THREADS, smem, st_>>>(state(), pb, cache_entries);
         }
         CK(cudaGetLastError());
         launches_++;
-        stats.p1_batches++;
-        if (ahead) {
-            sec(SEC_P1_INTRA);   // host time of issuing the look-ahead
+        // look ahead: the partner searches of the next `depth` batches (and everything else that does not depend on
+        // the clustering state) run on the side stream while this batch is resolved; they are issued right behind
+        // the resolver so that the resolver's CTA is placed first.  A batch only needs its predecessor's last query
+        // id; whatever the batches before it consume in the meantime is filtered by the resolver's consumed set.
+        sec(SEC_P1_INTRA);   // host time of issuing the look-ahead
+        for (int d = 1; d <= depth; d++) {
+            BatchBuf& prev = bb_[(head + d - 1) % HMK_NBATCHBUF];
+            BatchBuf& nb = bb_[(head + d) % HMK_NBATCHBUF];
+            if (nb.valid) continue;
+            if (!prev.valid || prev.nq != B || h_ctl_->unproc_alive < nq + (2 + d) * B) break;
             plan_sms_ = sm_count_ - 1;
-            stage_partner_search(nb, B, cur, cb.qid.p + (nq - 1), st2_);
+            CK(cudaStreamWaitEvent(st2_, prev.ready, 0));      // prev.qid is written on the stream that staged prev
+            stage_partner_search(nb, B, cur, prev.qid.p + (prev.nq - 1), st2_);
             plan_sms_ = 0;
         }
         sec(-1);
         fetch_ctl();
-        cb.valid = false;
         const int st = h_ctl_->status;
 #ifdef HMK_DEBUG
         if (getenv("HMK_DEBUG_BATCH"))
-            fprintf(stderr, "batch %d nq %d: cur %d ncl %d unproc %d status %d steps %d ahead %d\n", cb.batch_id, nq, h_ctl_->cur, h_ctl_->ncl,
-                    h_ctl_->unproc_alive, st, h_ctl_->steps, (int)ahead);
+            fprintf(stderr, "batch %d nq %d: cur %d ncl %d unproc %d status %d steps %d\n", cb.batch_id, nq, h_ctl_->cur, h_ctl_->ncl,
+                    h_ctl_->unproc_alive, st, h_ctl_->steps);
 #endif
-        if (st != HMK_P1_CONTINUE && nb.valid) {     // the look-ahead batch does not follow this one after all
+        if (st == HMK_P1_GROWHITS) {   // the state is untouched: redo the cluster search of this batch with a bigger buffer
+            hit_cap = (size_t)(uint32_t)h_ctl_->pad0 * 5 / 4 + 1024;
+            d_hits_.reserve(hit_cap);
+            h_ctl_->status = HMK_P1_CONTINUE;
+            continue;       // cb (and the batches prepared behind it) stay valid
+        }
+        stats.p1_batches++;
+        cb.valid = false;
+        if (st != HMK_P1_CONTINUE) {     // the prepared batches do not follow this one after all
             CK(cudaStreamSynchronize(st2_));
-            nb.valid = false;
+            for (auto& b : bb_) b.valid = false;
         }
         if (st == HMK_P1_NPE) { error_step = h_ctl_->npe_step; stats.error_step = error_step; return HMK_ERR_NULL_CLUSTER; }
         if (st == HMK_P1_DONE) break;
         if (st == HMK_P1_GROW) {   // a query had more valid clusters than its arrays hold
             capq *= 2;
-            d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq);
+            d_ac_slot_.reserve((size_t)B * capq); d_ac_score_.reserve((size_t)B * capq); d_ac_full_.reserve((size_t)B * capq);
         }
-        which ^= 1;
+        head = (head + 1) % HMK_NBATCHBUF;
     }
     CK(cudaStreamSynchronize(st2_));
-    bb_[0].valid = bb_[1].valid = false;
+    for (auto& b : bb_) b.valid = false;
     return HMK_OK;
 }
 
@@ -1590,6 +1600,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
         {"p2_chunk", &o.p2_chunk, 1024, 1 << 24},   {"hit_cap", &o.hit_cap, 1024, (int64_t)1 << 30},
         {"force_generic", &o.force_generic, 0, 1},  {"profile", &o.profile, 0, 1},
         {"p2_window", &o.p2_window, 1, 1 << 24},    {"p2_spec", &o.p2_spec, 1, 16},
+        {"xhit_cap", &o.xhit_cap, 0, (int64_t)1 << 30},
     };
     for (const Knob& k : knobs) {
         if (s != k.name) continue;

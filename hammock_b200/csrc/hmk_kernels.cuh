@@ -1070,6 +1070,10 @@ struct HmkP1Batch {
     const int32_t* ac_cnt;    // [nq] pre-batch clusters whose every pre-batch member scores >= T
     const int32_t* ac_slot;   // [nq][capq]
     const int32_t* ac_score;  // min over the pre-batch members
+    const int4* ac_full;      // [nq][capq] the same candidates as (slot, score, Cluster.size(), founder id) -- hmk_p1_prepare_candidates
+    const int4* best;         // [nq] the best of them under the reference's key as (score, size, founder id, slot); slot -1 = none
+    const unsigned int* hit_count;   // founder hits the cluster search produced / room it had: the resolver refuses to run on
+    unsigned int hit_cap;            //   a truncated hit list (HMK_P1_GROWHITS, state untouched)
     const int32_t* ib;        // ib[b*ib_stride + b2] = S(member = qid[b2], query = qid[b])
     int32_t ib_stride;
     const uint32_t* ibm;      // [nq][nw]
@@ -1135,6 +1139,28 @@ __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
     b.score = mx; b.size = ms; b.fid = mf;
 }
 
+// One warp per batch query, right behind the member check: the query's valid pre-batch clusters with everything a
+// resolver step needs in one 16-byte record, and the best of them under the reference's key.  The best stays an
+// upper bound of what a pre-batch cluster can offer for the whole batch (complete-linkage scores only fall when
+// members are added), which is what the resolver's windows test against.
+__global__ void hmk_p1_prepare_candidates(const HmkState S, int nq, int capq, const int32_t* __restrict__ ac_cnt,
+                                          const int32_t* __restrict__ ac_slot, const int32_t* __restrict__ ac_score,
+                                          int4* __restrict__ ac_full, int4* __restrict__ best) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= nq) return;
+    HmkBestCluster bb;
+    bb.score = HMK_JMIN; bb.size = 0; bb.fid = 0; bb.slot = -1;
+    const int cnt = min(ac_cnt[b], capq);
+    for (int e = lane; e < cnt; e += 32) {
+        const size_t g = (size_t)b * capq + e;
+        const int32_t c = ac_slot[g], sc = ac_score[g], sz = S.c_size[c], fd = S.c_founder[c];
+        ac_full[g] = make_int4(c, sc, sz, fd);
+        hmk_consider(bb, sc, sz, fd, c);
+    }
+    hmk_best_reduce(bb);
+    if (lane == 0) best[b] = make_int4(bb.score, bb.size, bb.fid, bb.slot);
+}
+
 #define HMK_RESOLVE_THREADS 256
 #ifdef HMK_RESOLVE_TIMING
 #define HMK_TICK(i) do { long long t_ = clock64(); dbg[i] += t_ - tlast; tlast = t_; } while (0)
@@ -1153,9 +1179,8 @@ __device__ __forceinline__ void hmk_best_reduce(HmkBestCluster& b) {
 #define HMK_HASH_SIZE 2048          // >= 2 * HMK_MAXBATCH, power of two
 
 // shared-memory bytes of the resolver for a batch of nq queries, before the candidate cache
-__host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb, int ib_stride, int pd_stride) {
-    size_t o = (size_t)(ib_stride + pd_stride) * 4;       // one row of ib and of pd (first: 16-byte aligned)
-    o += (size_t)nq * 4 * 5;                 // qid, qab, bk_cnt, bk_ovf, ac_raw
+__host__ __device__ inline size_t hmk_resolve_fixed_bytes(int nq, int nw, int kb) {
+    size_t o = (size_t)nq * 4 * 5;           // qid, qab, bk_cnt, bk_ovf, ac_raw
     o += (size_t)(nq + 1) * 4;               // ac_off
     o += (size_t)nq * nw * 4 * 3;            // ibm, ibm2, t_mask
     o += (size_t)nq * 4 * 10;                // t_fb, t_size, t_fid, t_count, t_tail, t_nmem, t_first, f_slot, f_pick, f_tidx
@@ -1180,8 +1205,6 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     extern __shared__ __align__(128) unsigned char rs_raw[];
     const int nq = B.nq, nw = B.nw, kb = B.kb;
     unsigned char* p = rs_raw;
-    int32_t* s_ibrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.ib_stride * 4;   // scores of the step's query vs the batch queries
-    int32_t* s_pdrow = reinterpret_cast<int32_t*>(p);   p += (size_t)B.pd_stride * 4;   //   ... and vs all partner candidates
     int32_t* s_qid = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
     int32_t* s_qab = reinterpret_cast<int32_t*>(p);     p += (size_t)nq * 4;
     int32_t* s_bkcnt = reinterpret_cast<int32_t*>(p);   p += (size_t)nq * 4;
@@ -1216,8 +1239,12 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     __shared__ int32_t h_tkey[HMK_HASH_SIZE], h_trow[HMK_HASH_SIZE];   // map: cluster slot -> row
     __shared__ int32_t s_wb[32];                         // window scratch: partner taken by each lane
     __shared__ int s_ncached;                            // queries [0, s_ncached) have their candidates cached
-    __shared__ __align__(8) uint64_t row_bar[2];         // TMA completion barriers of the two row buffers
 
+    // the cluster search must have seen every founder hit (nothing below has touched the state yet)
+    if (*B.hit_count > B.hit_cap) {
+        if (threadIdx.x == 0) { S.ctl->status = HMK_P1_GROWHITS; S.ctl->pad0 = (int32_t)min(*B.hit_count, 0x7fffffffu); }
+        return;
+    }
     for (int i = threadIdx.x; i < HMK_HASH_SIZE; i += blockDim.x) { h_cons[i] = -1; h_tkey[i] = -1; }
     for (int i = threadIdx.x; i < nq; i += blockDim.x) {
         const int32_t q = B.qid[i];
@@ -1261,33 +1288,14 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
             int lo = 0, hi = ncached - 1;          // query of entry e
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_acoff[mid] <= e) lo = mid; else hi = mid - 1; }
-            const size_t g = (size_t)lo * B.capq + (e - s_acoff[lo]);
-            const int32_t c = B.ac_slot[g];
-            s_cand[e] = make_int4(c, B.ac_score[g], S.c_size[c], S.c_founder[c]);
+            s_cand[e] = B.ac_full[(size_t)lo * B.capq + (e - s_acoff[lo])];
         }
     }
-    __syncthreads();
-    {   // in parallel: each query's best pre-batch candidate.  For cached queries it stays THE best as long as none
-        // of their candidates changes (dirty bits); for every query its score stays an upper bound of what a
-        // pre-batch cluster can offer, because complete-linkage scores only fall when members are added.
-        const int wl = threadIdx.x & 31;
-        for (int i = threadIdx.x; i < nw; i += blockDim.x) { s_dirty[i] = 0; s_fmask[i] = 0; }
-        for (int b = threadIdx.x >> 5; b < nq; b += blockDim.x >> 5) {
-            HmkBestCluster bb;
-            bb.score = HMK_JMIN; bb.size = 0; bb.fid = 0; bb.slot = -1;
-            const int cnt = min(s_acraw[b], B.capq);
-            if (b < ncached) {
-                for (int e = wl; e < cnt; e += 32) { const int4 v = s_cand[s_acoff[b] + e]; hmk_consider(bb, v.y, v.z, v.w, v.x); }
-            } else {
-                for (int e = wl; e < cnt; e += 32) {
-                    const int32_t c = B.ac_slot[(size_t)b * B.capq + e];
-                    hmk_consider(bb, B.ac_score[(size_t)b * B.capq + e], S.c_size[c], S.c_founder[c], c);
-                }
-            }
-            hmk_best_reduce(bb);
-            if (wl == 0) s_best[b] = make_int4(bb.score, bb.size, bb.fid, bb.slot);
-        }
-    }
+    // each query's best pre-batch candidate (hmk_p1_prepare_candidates).  For cached queries it stays THE best as long
+    // as none of their candidates changes (dirty bits); for every query its score stays an upper bound of what a
+    // pre-batch cluster can offer, because complete-linkage scores only fall when members are added.
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) { s_dirty[i] = 0; s_fmask[i] = 0; }
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_best[i] = B.best[i];
     __syncthreads();
     if (threadIdx.x >= 32) return;
     HMK_TICK(0);   // staging
@@ -1326,15 +1334,15 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     auto eval_touched = [&](int row, int b, int32_t& cl) -> bool {
         const uint32_t* tm = t_mask + row * nw;
         const uint32_t* hm = s_ibm + b * nw;
-        const int32_t* ibr = s_ibrow;
-        const int32_t* pdr = s_pdrow;
+        const int32_t* ibr = B.ib + (size_t)b * B.ib_stride;     // S(member = batch query b2, query b): the few entries
+        const int32_t* pdr = B.pd + (size_t)b * B.pd_stride;     // a step needs are read straight from L2
         const int32_t fb = t_fb[row];
         if (t_nmem[row] == 1) {     // the usual case: one batch query (+ its partner if the cluster was born here)
             const int b2 = t_first[row];
             if (((hm[b2 >> 5] >> (b2 & 31)) & 1u) == 0) return false;
-            int32_t mn1 = ibr[b2];
+            int32_t mn1 = __ldcg(ibr + b2);
             if (fb >= 0) {
-                const int32_t s = pdr[fb * kb + f_pick[fb]];
+                const int32_t s = __ldcg(pdr + fb * kb + f_pick[fb]);
                 if (s < S.T) return false;
                 mn1 = s < mn1 ? s : mn1;
             }
@@ -1345,7 +1353,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             if (tm[w] & ~hm[w]) return false;
         int32_t mn = cl;
         if (fb >= 0) {     // cluster born in this batch: its partner was one of the founder's candidates
-            const int32_t s = pdr[fb * kb + f_pick[fb]];
+            const int32_t s = __ldcg(pdr + fb * kb + f_pick[fb]);
             if (s < S.T) return false;
             mn = s < mn ? s : mn;
         }
@@ -1354,38 +1362,13 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             while (m) {
                 const int b2 = w * 32 + __ffs(m) - 1;
                 m &= m - 1;
-                const int32_t s = ibr[b2];
+                const int32_t s = __ldcg(ibr + b2);
                 mn = s < mn ? s : mn;
             }
         }
         cl = mn;
         return true;
     };
-    // rows b of ib / pd (scores of query b against the batch queries / all partner candidates) are fetched by the
-    // TMA bulk-copy engine when a step takes the sequential path
-    const uint32_t row_bytes = (uint32_t)(B.ib_stride + B.pd_stride) * 4;
-    uint32_t row_uses = 0;          // completed phases of row_bar[0]
-    auto fetch_rows = [&](int b) {
-#ifdef HMK_NO_TMA_ROWS
-        for (int i = lane; i < B.ib_stride; i += 32) s_ibrow[i] = B.ib[(size_t)b * B.ib_stride + i];
-        for (int i = lane; i < B.pd_stride; i += 32) s_pdrow[i] = B.pd[(size_t)b * B.pd_stride + i];
-        __syncwarp();
-        return;
-#endif
-        if (lane == 0) {
-            hmk_mbar_expect_tx(&row_bar[0], row_bytes);
-            hmk_bulk_g2s(s_ibrow, B.ib + (size_t)b * B.ib_stride, (uint32_t)B.ib_stride * 4, &row_bar[0]);
-            hmk_bulk_g2s(s_pdrow, B.pd + (size_t)b * B.pd_stride, (uint32_t)B.pd_stride * 4, &row_bar[0]);
-        }
-    };
-#ifdef HMK_NO_TMA_ROWS
-    auto wait_rows = [&]() { row_uses++; };
-#else
-    auto wait_rows = [&]() { hmk_mbar_wait(&row_bar[0], row_uses & 1u); row_uses++; };
-#endif
-    if (lane == 0) hmk_mbar_init(&row_bar[0], 1);
-    __syncwarp();
-
     // ------------------------------------------------------------------------------------------------
     // Most steps are "q founds a new cluster with its best still-alive partner" and do not interact with
     // their neighbours.  A WINDOW of up to 32 consecutive batch queries is therefore evaluated with one
@@ -1529,7 +1512,6 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
         const int32_t acnt = s_acraw[b];
         if (acnt > B.capq) { status = HMK_P1_GROW; cur = q; break; }   // candidate arrays too small: host grows them
         const int32_t bcnt = s_bkcnt[b];
-        fetch_rows(b);
         uint32_t fmask = lane < nw ? s_fmask[lane] : 0u;   // this lane's word of the founder mask
 
         // ---- B: nearest among initialList[index+1 ..]                               (:93)
@@ -1545,12 +1527,10 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 bscore = s_bksc[b * kb + bpick];
                 bkind = 1;
             } else if (s_bkovf[b]) {
-                wait_rows();
                 status = HMK_P1_RESTART; cur = q; break;    // list truncated: rescore from q
             }
         }
         HMK_TRACE(1, 6);
-        wait_rows();
         HMK_TRACE(1, 7);
         HMK_TRACE_CLEAR();
         HMK_TRACE_LANES(4);
@@ -1577,10 +1557,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                 if (e < acnt) {
                     int32_t sz, fd;
                     if (b < ncached) { const int4 v = s_cand[s_acoff[b] + e]; c = v.x; cl = v.y; sz = v.z; fd = v.w; }
-                    else {
-                        c = B.ac_slot[(size_t)b * B.capq + e]; cl = B.ac_score[(size_t)b * B.capq + e];
-                        sz = __ldcg(S.c_size + c); fd = __ldcg(S.c_founder + c);
-                    }
+                    else { const int4 v = B.ac_full[(size_t)b * B.capq + e]; c = v.x; cl = v.y; sz = v.z; fd = v.w; }
                     row = tn ? touched_row(c) : -1;
                     if (row < 0) hmk_consider(best, cl, sz, fd, c);
                 }

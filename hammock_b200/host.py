@@ -654,9 +654,22 @@ def nccl_unique_id() -> bytes:
     return bytes(buf)
 
 
+def result_digest(cluster_id, member_rank, result_order) -> str:
+    """sha256 over cluster_id || member_rank || result_order as little-endian int32 -- the three arrays from which the
+    host rebuilds the List<Cluster> the reference returns (members, their order, the order of the list).  The golden
+    digests under tests/golden/*_digest.json hash the same bytes of a full CPU-oracle run."""
+    import hashlib
+    h = hashlib.sha256()
+    for a in (cluster_id, member_rank, result_order):
+        h.update(np.ascontiguousarray(a, dtype="<i4").tobytes())
+    return h.hexdigest()
+
+
 def greedy_cluster_arrays(residues, offsets, abundance, matrix, threshold, max_shift, shift_penalty, max_clusters,
-                          device: int = 0):
-    """One blocking hmk_greedy_cluster call on host arrays -> (status, GreedyResult | None, error_step)."""
+                          device: int = 0, devices: Optional[Sequence[int]] = None):
+    """One blocking hmk_greedy_cluster call on host arrays -> (status, GreedyResult | None, error_step, message).
+    `devices`: run hmk_greedy_cluster_multi on these GPUs of this process instead (one worker thread per device
+    inside the library)."""
     L = _lib.load()
     residues = np.ascontiguousarray(residues, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -670,7 +683,11 @@ def greedy_cluster_arrays(residues, offsets, abundance, matrix, threshold, max_s
                         _ptr(matrix, C.c_int32), int(threshold), int(max_shift), int(shift_penalty), int(max_clusters))
     out = _lib.GreedyOut(_ptr(cid, C.c_int32), _ptr(rank, C.c_int32), _ptr(order, C.c_int32), 0, 0, -1)
     err = C.create_string_buffer(512)
-    rc = L.hmk_greedy_cluster(C.byref(gin), C.byref(out), device, err, 512)
+    if devices is not None:
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = L.hmk_greedy_cluster_multi(C.byref(gin), C.byref(out), _ptr(devs, C.c_int32), len(devs), err, 512)
+    else:
+        rc = L.hmk_greedy_cluster(C.byref(gin), C.byref(out), device, err, 512)
     if rc:
         return rc, None, int(out.error_step), err.value
     return 0, GreedyResult(cid[:n], rank[:n], order[:out.n_result].copy(), int(out.n_multi), {}), -1, b""

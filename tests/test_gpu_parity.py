@@ -1,6 +1,7 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
 (libhammock_b200.so) and is compared bit-exactly with the CPU oracle on the same inputs, with
 the committed goldens, and -- at full BASELINE sizes -- through size-independent properties."""
+import json
 import os
 
 import numpy as np
@@ -46,7 +47,7 @@ def oracle_run(d, M, T, X, P, K, **kw):
 
 def test_library_loads_on_gpu():
     L = _lib.load()
-    assert L.hmk_abi_version() == 1
+    assert L.hmk_abi_version() == 2
 
 
 def test_scorer_kats_gpu(mats):
@@ -156,7 +157,8 @@ def test_empty_and_tiny_inputs(blosum62):
 
 
 @pytest.mark.parametrize("opts", [{}, {"force_generic": 1}, {"batch": 7, "kb": 1}, {"batch": 64, "kb": 2, "qt": 16},
-                                  {"batch": 1000, "waves": 1}, {"p2_chunk": 1024, "hit_cap": 2048, "p2_window": 100, "capq": 1}])
+                                  {"batch": 512, "waves": 1}, {"p2_chunk": 1024, "hit_cap": 1024, "p2_window": 100, "capq": 1},
+                                  {"lookahead": 0, "p2_spec": 1}, {"lookahead": 1, "batch": 16, "p2_spec": 16, "p2_window": 64}])
 def test_musi_golden_gpu(golden_dir, blosum62, opts):
     z = np.load(os.path.join(golden_dir, "musi.npz"))
     T, X, P, K = (int(v) for v in z["params"])
@@ -218,6 +220,11 @@ SYNTH_CASES = [
     (3000, 7, 12, "blosum62", 0, None, False, {"reuse": 0, "batch": 24}),
     (3000, 10, 10, "blosum62", -1, None, False, {"batch": 8, "kb": 1}),     # truncated partner lists -> restarts, hits of re-done batches
     (3000, 11, 11, "blosum62", 0, 200, True, {"batch": 20, "kb": 2}),
+    (6000, 12, 12, "blosum62", 0, 60, False, {"p2_window": 256, "p2_spec": 2}),      # few clusters, many joiners per cluster and window
+    (6000, 12, 12, "blosum62", 0, 60, False, {"p2_window": 100000, "p2_spec": 5, "hit_cap": 1024}),
+    (5000, 12, 12, "blosum62", 0, None, False, {"batch": 32, "lookahead": 2, "hit_cap": 1024}),   # founder-hit buffer grows in the resolver
+    (5000, 12, 12, "blosum62", 0, None, False, {"batch": 32, "lookahead": 1}),
+    (5000, 12, 12, "blosum62", 0, None, False, {"batch": 32, "lookahead": 0}),
 ]
 
 
@@ -255,7 +262,7 @@ def test_uniform_random_with_orphans(blosum62):
             assert_same(R, G, f"T={T}")
 
 
-def test_s100k_vs_oracle(blosum62):
+def test_s100k_vs_oracle(blosum62, golden_dir):
     """BASELINE config 1: synthetic 100k unique peptides, length 7-12, Zipf abundance, BLOSUM62"""
     d = synth.generate(100000, 7, 12)
     T, X, K = synth.default_params(d["lengths"])
@@ -264,9 +271,11 @@ def test_s100k_vs_oracle(blosum62):
     rc, G, st = run_gpu(d, blosum62, T, X, 0, K)
     assert rc == 0 and R.status == 0
     assert_same(R, G, "S100k")
+    gold = json.load(open(os.path.join(golden_dir, "s100k_digest.json")))
+    assert hb.result_digest(G.cluster_id, G.member_rank, G.result_order) == gold["sha256"]
 
 
-def test_s1m_properties(blosum62):
+def test_s1m_properties(blosum62, golden_dir):
     """BASELINE config 2 at full size (1M unique 12-mers): the oracle cannot finish, so check
     (a) a prefix of phase 1 against the bounded oracle, (b) complete linkage of every cluster,
     (c) maximality for sampled singletons, (d) independence from batch size."""
@@ -280,6 +289,14 @@ def test_s1m_properties(blosum62):
     G = ctx.download()
     st = ctx.stats()
     assert G.n_multi == K and st["p1_new_clusters"] == K
+    # (0) bit-exact against the FULL oracle run on this input: tests/golden/s1m_digest.json
+    # (scripts/make_s1m_digest.py; sha256 over cluster_id || member_rank || result_order)
+    gold = json.load(open(os.path.join(golden_dir, "s1m_digest.json")))
+    assert (gold["n"], gold["threshold"], gold["max_shift"], gold["max_clusters"]) == (1000000, T, X, K)
+    assert hb.result_digest(G.cluster_id, G.member_rank, G.result_order) == gold["sha256"]
+    assert (st["p1_steps"], st["p1_joins"], st["p1_orphans"], st["p2_assigned"]) == (
+        gold["counters"]["p1_steps"], gold["counters"]["p1_joins"], gold["counters"]["p1_orphans"], gold["counters"]["p2_assigned"])
+    assert st["flags"] & _lib.FLAG_P2_REUSED and not st["flags"] & _lib.FLAG_XHIT_OVERFLOW
     # (a) first 150 phase-1 steps of the oracle: same founders and partners
     R = oracle_run(d, blosum62, T, X, 0, K, max_p1_steps=150, max_p2_queries=1)
     founders = R.result_order[:R.n_multi]
@@ -318,6 +335,7 @@ def test_s1m_properties(blosum62):
     assert rc == 0
     G2 = ctx.download()
     assert (G2.cluster_id == G.cluster_id).all() and (G2.member_rank == G.member_rank).all()
+    assert hb.result_digest(G2.cluster_id, G2.member_rank, G2.result_order) == gold["sha256"]
     ctx.close()
 
 
