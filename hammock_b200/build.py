@@ -33,11 +33,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """defines/out: instrumented variants for profiling sessions, e.g. defines=("HMK_DEBUG", "HMK_RESOLVE_TIMING"),
+    out=".../libhammock_b200_timing.so" (load it with HMK_LIB=...); the product is the plain build."""
+    if out == LIB and not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", LIB] + SOURCES
+           "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", out] + [f"-D{d}" for d in defines] + SOURCES
     # the image exports CC/CXX wrappers that lack parts of the toolchain; use the system g++
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
@@ -45,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 HOST_SRC = os.path.join(HERE, "host_cpp", "hammock_greedy.cpp")

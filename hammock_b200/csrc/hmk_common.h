@@ -102,4 +102,5 @@ struct HmkCtl {
     int64_t scalar_pairs;  // pair scores computed one at a time (resolvers, member checks)
     int64_t scalar_cells;
     int64_t dbg[8];        // resolver cycle counters (only filled when built with -DHMK_RESOLVE_TIMING)
+    int64_t cnt[4];        // resolver statistics: windows tried, steps they applied, sequential steps
 };

@@ -153,7 +153,6 @@ struct Options {
     int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
     int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
-    int64_t p2_spec = 3;          // phase-2 fixed-point iterations enqueued per host round trip
     int64_t xhit_cap = 0;         // capacity of the kept-hit buffer (0 = automatic: the last run's need, else 96 per sequence)
 };
 
@@ -178,7 +177,7 @@ public:
         for (auto& b : bb_) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
         CK(cudaMallocHost(&h_ctl_, sizeof(HmkCtl)));
         CK(cudaMallocHost(&h_scalars_, 16 * sizeof(int32_t)));
-        CK(cudaMallocHost(&h_p2flags_, HMK_P2_FLAGS * sizeof(int32_t)));
+        CK(cudaMallocHost(&h_p2flags_, HMK_P2_CTL * sizeof(int32_t)));
         CK(cudaEventCreate(&ev_a_));
         CK(cudaEventCreate(&ev_b_));
         CK(cudaEventCreate(&ev_c_));
@@ -301,8 +300,10 @@ private:
     DevBuf<unsigned int> d_counts_;   // [0] hit_count, [1] cand_count
     DevBuf<unsigned long long> d_pairctr_;
     // ---- phase-2 scratch
-    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_qstart_, d_cstart_, d_ccount_,
-        d_a0_, d_dyn_, d_dyn_n_, d_flags_, d_base_cl_, d_tent_, d_tent_n_, d_p2flags_;
+    DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cq_q_, d_qstart_, d_cstart_, d_ccount_,
+        d_a0_, d_flags_, d_base_cl_, d_tent_, d_cinfo_, d_work_, d_stamp_, d_cc_q_, d_cc_c_;
+    DevBuf<unsigned long long> d_pairparts_;
+    DevBuf<HmkDynEntry> d_dyn_;
     DevBuf<unsigned long long> d_key_q_, d_key_tmp_;
     DevBuf<unsigned char> d_cub_;
     DevBuf<uint32_t> d_fprof_;
@@ -900,7 +901,7 @@ int Engine::phase1() {
             c.hit_t_is_query = 1; c.qids = d_qid; c.sidx = nullptr;
             c.ac_cnt = d_ac_cnt_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p; c.capq = (int32_t)capq;
             c.cand_count = d_counts_.p + 1; c.cand_cap = 0; c.linked = 1;
-            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
+            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
             hmk_member_check<<<sm_count_ * 2, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
             launches_++;
@@ -1036,7 +1037,7 @@ void Engine::phase2() {
                 c.hit_t_is_query = 0; c.qids = nullptr; c.sidx = d_sidx_.p;
                 c.cand_key_q = d_key_q_.p; c.cand_score = d_cand_score_.p;
                 c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits;
-                c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
+                c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
                 hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
                 CK(cudaGetLastError());
                 launches_++;
@@ -1084,7 +1085,7 @@ void Engine::phase2() {
             c.qids = nullptr; c.sidx = d_sidx_.p;
             c.cand_key_q = d_key_q_.p; c.cand_score = d_cand_score_.p;
             c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits;
-            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_;
+            c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
             hmk_member_check<<<sm_count_ * 8, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
             launches_++;
@@ -1169,74 +1170,70 @@ void Engine::phase2() {
     // group by query (ascending cluster inside a query); per cluster only the NUMBER of candidate pairs is needed
     // (room for its joiners), so there is no second sort
     sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, cbits + qbits);
-    d_cq_c_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2); d_ccount_.reserve(ncl + 1);
-    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p, nullptr);
+    d_cq_c_.reserve(nc); d_cq_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2); d_ccount_.reserve(ncl + 1);
+    hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p, d_cq_q_.p);
     hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, cbits, d_qstart_.p);
     CK(cudaMemsetAsync(d_ccount_.p, 0, sizeof(int32_t) * (ncl + 1), st_));
     hmk_p2_count_clusters<<<sm_count_ * 8, 256, 0, st_>>>(d_cq_c_.p, nc, d_ccount_.p);
     hmk_exclusive_scan<<<1, 1024, 0, st_>>>(d_ccount_.p, ncl, d_cstart_.p);
+    d_cinfo_.reserve((size_t)ncl * HMK_CI);
+    hmk_p2_init_cinfo<<<(ncl + 255) / 256, 256, 0, st_>>>(ncl, d_cstart_.p, d_cinfo_.p);
     CK(cudaGetLastError());
-    launches_ += 4;
-    d_dyn_.reserve(nc); d_dyn_n_.reserve(ncl); d_base_cl_.reserve(nc); d_tent_.reserve(nc);
-    d_tent_n_.reserve(2 * (size_t)ncl); d_a0_.reserve(2 * (size_t)ns); d_dirty_a_.reserve(2 * (size_t)ncl);
-    d_p2flags_.reserve(HMK_P2_FLAGS);
-    CK(cudaMemsetAsync(d_dyn_n_.p, 0, sizeof(int32_t) * ncl, st_));
-    CK(cudaMemsetAsync(d_base_cl_.p, 0, sizeof(int32_t) * nc, st_));
+    launches_ += 5;
+    // the pairs once more, grouped by cluster with ascending queries inside a cluster: a STABLE sort of the query-ordered
+    // list by the cluster field alone (cbits bits, two radix passes); the clusters' offsets are cstart
+    d_cc_q_.reserve(nc); d_cc_c_.reserve(nc);
+    {
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_cq_c_.p, d_cc_c_.p, d_cq_q_.p, d_cc_q_.p, nc, 0, cbits, st_));
+        d_cub_.reserve(bytes);
+        CK(cub::DeviceRadixSort::SortPairs(d_cub_.p, bytes, d_cq_c_.p, d_cc_c_.p, d_cq_q_.p, d_cc_q_.p, nc, 0, cbits, st_));
+        launches_ += 4;
+    }
+    const int Wmax = (int)std::max<int64_t>(1, opt.p2_window);
+    d_dyn_.reserve(nc); d_base_cl_.reserve(nc); d_tent_.reserve(nc);
+    d_a0_.reserve(2 * (size_t)ns); d_dirty_a_.reserve(2 * (size_t)ncl); d_stamp_.reserve(ns);
+    d_work_.reserve(2 * (size_t)Wmax + HMK_P2_CTL + 2 * HMK_P2_CHG);
     CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * 2 * (size_t)ns, st_));
+    CK(cudaMemsetAsync(d_stamp_.p, 0xff, sizeof(int32_t) * (size_t)ns, st_));
     HmkP2 P{};
     P.S = state(); P.packed = fast_scalar_ ? d_packed_.p : nullptr; P.L = max_len_;
-    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_s = d_cand_score_.p;
-    P.base_cl = d_base_cl_.p; P.cstart = d_cstart_.p; P.dyn = d_dyn_.p; P.dyn_n = d_dyn_n_.p;
-    P.tent = d_tent_.p; P.tent_n = d_tent_n_.p; P.a = d_a0_.p; P.dirty = d_dirty_a_.p; P.flags = d_p2flags_.p;
-    // the unrolled pair scorer of hmk_p2_decide: uniform length 12, max shift 3, lane-sized matrix entries
+    P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_q = d_cq_q_.p; P.cq_s = d_cand_score_.p;
+    P.cstart = d_cstart_.p; P.cc_q = d_cc_q_.p;
+    P.base_cl = d_base_cl_.p; P.cinfo = d_cinfo_.p; P.dyn = d_dyn_.p;
+    P.tent = d_tent_.p; P.a = d_a0_.p; P.dirty = d_dirty_a_.p; P.stamp = d_stamp_.p;
+    P.wcap = Wmax; P.work = d_work_.p; P.ctl = d_work_.p + 2 * (size_t)Wmax; P.chg = P.ctl + HMK_P2_CTL;
+    P.pair_parts = d_pairparts_.p;
+    // the unrolled pair scorer: uniform length 12, max shift 3, lane-sized matrix entries
     const bool p2_fast = fast_scalar_ && fast_ && max_len_ == HMK_MAXL1 && X_ == 3;
+    const void* kernel = p2_fast ? (const void*)hmk_p2_window<true> : (const void*)hmk_p2_window<false>;
+    int per_sm = 0;      // the cooperative grid must be resident as a whole
+    if (p2_fast) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmk_p2_window<true>, 256, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmk_p2_window<false>, 256, 0));
+    if (per_sm < 1) throw CudaError("hmk_p2_window does not fit on an SM");
     // window size adapts to how hard the fixed point is: dense inputs (everything joins) need many
-    // iterations per window unless few queries per cluster are in flight at a time
-    const int Wmax = (int)std::max<int64_t>(1, opt.p2_window);
-    int W = std::min(Wmax, std::max(1024, 8 * ncl));
-    const int cgrid = (ncl + 255) / 256;
-    const int spec = (int)std::max<int64_t>(1, std::min<int64_t>(opt.p2_spec, 16));
-    int it = 0;
+    // iterations per window unless few queries per cluster are in flight at a time.  The first windows are small: the
+    // members they make final let the base pass reject most candidate pairs of every later window up front
+    int W = std::min(Wmax, std::max(1024, ncl / 4));
+    int gen = 0;
+    sec(SEC_P2_ITERATE);
     for (int qa = 0; qa < ns;) {
         const int qb = std::min(ns, qa + W);
-        P.qa = qa; P.qb = qb;
-        sec(SEC_P2_ITERATE);
-        P.it = it;
-        hmk_p2_window_setup<<<cgrid, 256, 0, st_>>>(P);
+        P.qa = qa; P.qb = qb; P.gen0 = gen; P.max_iters = qb - qa + 2;
+        const int grid = std::max(1, std::min(per_sm * sm_count_, std::max((qb - qa + 7) / 8, (ncl + 255) / 256)));
+        void* args[] = {(void*)&P};
+        CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(256), args, 0, st_));
         launches_++;
-        const int qgrid = (qb - qa + 7) / 8;      // one warp per query, 8 warps per block
-        int iters = 0, converged = -1;
-        while (converged < 0) {
-            // a group of iterations without a host round trip: once one of them changes nothing, the rest return at once
-            const int g0 = it;
-            for (int k = 0; k < spec; k++) CK(cudaMemsetAsync(d_p2flags_.p + (it + k) % HMK_P2_FLAGS, 0, sizeof(int32_t), st_));
-            for (int k = 0; k < spec; k++, it++) {
-                P.it = it; P.first = iters == 0 && k == 0;
-                hmk_p2_build_tent<<<(qb - qa + 255) / 256, 256, 0, st_>>>(P);
-                hmk_p2_sort_tent<<<(ncl * 32 + 255) / 256, 256, 0, st_>>>(P);
-                if (p2_fast) hmk_p2_decide<true><<<qgrid, 256, 0, st_>>>(P);
-                else hmk_p2_decide<false><<<qgrid, 256, 0, st_>>>(P);
-                launches_ += 3;
-            }
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h_p2flags_, d_p2flags_.p, sizeof(int32_t) * HMK_P2_FLAGS, cudaMemcpyDeviceToHost, st_));
-            CK(cudaStreamSynchronize(st_));
-            for (int k = 0; k < spec && converged < 0; k++) {
-                iters++;
-                if (!h_p2flags_[(g0 + k) % HMK_P2_FLAGS]) converged = g0 + k;      // fixed point: tent lists == final joiners of this window
-            }
-        }
+        CK(cudaMemcpyAsync(h_p2flags_, P.ctl, sizeof(int32_t) * HMK_P2_CTL, cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        const int iters = h_p2flags_[8];
         stats.p2_rounds += iters;
-        sec(SEC_P2_COMMIT);
-        P.it = converged;
-        hmk_p2_commit<<<cgrid, 256, 0, st_>>>(P);
-        CK(cudaGetLastError());
-        launches_++;
-        // the next window starts on the parity the converged iteration wrote last: a[] of later queries is still -1
-        // on both, tent_n / dirty are reset by the window setup
-        it = converged + 1;
+        gen += iters + 1;
+#ifdef HMK_DEBUG
+        if (getenv("HMK_DEBUG_P2")) fprintf(stderr, "p2 window [%d, %d) W %d grid %d: %d iterations\n", qa, qb, W, grid, iters);
+#endif
         qa = qb;
-        if (iters > 8) W = std::max(256, W / 2);
+        if (iters > 8) W = std::min(Wmax, std::max(256, W / 2));
         else if (iters <= 5) W = std::min(Wmax, W * 2);
     }
     sec(-1);
@@ -1272,6 +1269,8 @@ int Engine::run() {
     *h_ctl_ = c0;
     CK(cudaMemcpyAsync(d_ctl_.p, h_ctl_, sizeof(HmkCtl), cudaMemcpyHostToDevice, st_));
     CK(cudaMemsetAsync(d_pairctr_.p, 0, 4 * sizeof(unsigned long long), st_));
+    d_pairparts_.reserve(HMK_PAIR_SHARDS * 16);
+    CK(cudaMemsetAsync(d_pairparts_.p, 0, HMK_PAIR_SHARDS * 16 * sizeof(unsigned long long), st_));
     // DataException "Shift too big" (ShiftedScorer.java:59-62): thrown by the first pair score
     // touching a sequence not longer than maxShift; step 0 of phase 1 scores every sequence.
     if (K_ > 0 && n_ >= 2 && X_ >= min_len_) return HMK_ERR_SHIFT_TOO_BIG;
@@ -1289,8 +1288,12 @@ int Engine::run() {
     CK(cudaEventRecord(ev_c_, st_));
     fetch_ctl();
     unsigned long long pc[4] = {0, 0, 0, 0};
+    std::vector<unsigned long long> parts(HMK_PAIR_SHARDS * 16);
     CK(cudaMemcpyAsync(pc, d_pairctr_.p, sizeof(pc), cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(parts.data(), d_pairparts_.p, parts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
+    unsigned long long scalar_sharded = 0;
+    for (int i = 0; i < HMK_PAIR_SHARDS; i++) scalar_sharded += parts[(size_t)i * 16];
     float ms1 = 0, ms2 = 0;
     CK(cudaEventElapsedTime(&ms1, ev_a_, ev_b_));
     CK(cudaEventElapsedTime(&ms2, ev_b_, ev_c_));
@@ -1308,11 +1311,11 @@ int Engine::run() {
     }
     stats.bulk_kernel_ms = bulk_ms;
     stats.bulk_pairs = (int64_t)pc[0];
-    stats.scalar_pairs = h_ctl_->scalar_pairs;
+    stats.scalar_pairs = h_ctl_->scalar_pairs + (int64_t)scalar_sharded;
 #ifdef HMK_DEBUG
     if (getenv("HMK_DEBUG_TIMING"))
-        fprintf(stderr, "resolver: %lld windows applied %lld lanes, %lld sequential steps\n", (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5],
-                (long long)h_ctl_->dbg[6]);
+        fprintf(stderr, "resolver: %lld windows applied %lld lanes, %lld sequential steps\n", (long long)h_ctl_->cnt[0], (long long)h_ctl_->cnt[1],
+                (long long)h_ctl_->cnt[2]);
     if (getenv("HMK_DEBUG_TIMING"))
         fprintf(stderr, "resolver cycles: staging %lld window(rest) %lld bpart %lld static %lld eval %lld apply %lld window(pick) %lld window(bounds) %lld\n", (long long)h_ctl_->dbg[0],
                 (long long)h_ctl_->dbg[1], (long long)h_ctl_->dbg[2], (long long)h_ctl_->dbg[3], (long long)h_ctl_->dbg[4], (long long)h_ctl_->dbg[5], (long long)h_ctl_->dbg[7], (long long)h_ctl_->dbg[6]);
@@ -1599,7 +1602,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
         {"kb", &o.kb, 1, 32},                       {"waves", &o.waves, 1, 16},
         {"p2_chunk", &o.p2_chunk, 1024, 1 << 24},   {"hit_cap", &o.hit_cap, 1024, (int64_t)1 << 30},
         {"force_generic", &o.force_generic, 0, 1},  {"profile", &o.profile, 0, 1},
-        {"p2_window", &o.p2_window, 1, 1 << 24},    {"p2_spec", &o.p2_spec, 1, 16},
+        {"p2_window", &o.p2_window, 1, 1 << 24},
         {"xhit_cap", &o.xhit_cap, 0, (int64_t)1 << 30},
     };
     for (const Knob& k : knobs) {

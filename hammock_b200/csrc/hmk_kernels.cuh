@@ -14,6 +14,7 @@
 // Profile tiles are staged global->shared with the TMA bulk-copy engine
 // (cp.async.bulk + mbarrier; SASS UBLKCP).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -165,6 +166,12 @@ __device__ __forceinline__ void hmk_mbar_wait(uint64_t* bar, uint32_t parity) {
     // follows uses warp-wide primitives, so re-converge here.  Always called by whole warps.  Without this the
     // resolver dead-locked at a later __syncwarp on some inputs.
     __syncwarp();
+}
+
+// every warp adds its pair-score count once; one address for all of them serialises in L2, so the counter is sharded
+#define HMK_PAIR_SHARDS 64
+__device__ __forceinline__ void hmk_count_pairs(unsigned long long* parts, long long n) {
+    if (n) atomicAdd(parts + (size_t)((blockIdx.x * 8 + (threadIdx.x >> 5)) % HMK_PAIR_SHARDS) * 16, (unsigned long long)n);
 }
 
 // ---------------------------------------------------------------- bulk arguments
@@ -984,6 +991,7 @@ struct HmkCheckArgs {
     int32_t linked;
     const uint64_t* packed;      // non-NULL: uniform length <= 12, use the packed scalar scorer
     int32_t L;
+    unsigned long long* pair_parts;   // sharded pair-score counter
 };
 
 __global__ void hmk_member_check(const HmkCheckArgs a) {
@@ -1039,7 +1047,7 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         }
     }
     for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, s);
-    if ((threadIdx.x & 31) == 0 && npairs) atomicAdd((unsigned long long*)&a.S.ctl->scalar_pairs, (unsigned long long)npairs);
+    if ((threadIdx.x & 31) == 0) hmk_count_pairs(a.pair_parts, npairs);
     if (a.hit_t_is_query == 2) {
         for (int s = 16; s > 0; s >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, s);
         if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd(a.hit_valid, (unsigned long long)nvalid);
@@ -1699,7 +1707,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     if (lane == 0) for (int i = 0; i < 8; i++) ctl->dbg[i] += dbg[i];
 #endif
     if (lane == 0) {
-        ctl->dbg[4] += n_win; ctl->dbg[5] += n_win_steps; ctl->dbg[6] += n_seq;
+        ctl->cnt[0] += n_win; ctl->cnt[1] += n_win_steps; ctl->cnt[2] += n_seq;
         ctl->cur = cur; ctl->ncl = ncl; ctl->unproc_alive = unproc; ctl->status = status;
         if (npe_step >= 0) ctl->npe_step = npe_step;
         ctl->steps = steps; ctl->joins = joins; ctl->creates = creates; ctl->orphans = orphans;
@@ -1725,8 +1733,20 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
 // iff some assignment changed, and every kernel of iteration it > 0 returns at once when the previous
 // iteration did not change anything (the fixed point has been reached; nothing may be touched any more).
 // Buffers indexed by iteration parity: a[2][ns], dirty[2][ncl], tent_n[2][ncl].
-#define HMK_P2_FLAGS 64
 #define HMK_P2_CLEAN 0x7f7f7f7f
+#define HMK_P2_CHG 1024          // changed clusters listed per iteration; more: every query gathers dirty[] itself
+
+// one joiner of a cluster: everything a later query needs to score against it comes with ONE 16-byte load
+struct __align__(16) HmkDynEntry {
+    uint64_t w;     // packed residues (uniform length <= 12), else unused
+    int32_t qi;     // query index (into singles)
+    int32_t ab;     // abundance
+};
+// per cluster, one 16-byte record: [0] offset into dyn / tent, [1] final phase-2 members, [2 + parity] tentative joiners
+#define HMK_CI 4
+// control words of a window (P.ctl): per parity [0..1] work-list entries, [2..3] entries consumed, [4..5] clusters on the
+// changed list, [6..7] "some assignment changed"; [8] iterations the window took (read by the host)
+#define HMK_P2_CTL 16
 
 struct HmkP2 {
     HmkState S;
@@ -1736,24 +1756,26 @@ struct HmkP2 {
     const int32_t* singles;   // [ns] ascending ids of the phase-2 queries
     const int32_t* qstart;    // [ns+1] into cq_*
     const int32_t* cq_c;      // candidate cluster slot (ascending inside a query)
+    const int32_t* cq_q;      // query index of the pair
     const int32_t* cq_s;      // complete-linkage min over the phase-1 members ("static" score)
-    int32_t* base_cl;         // per pair: HMK_JMIN = a FINAL phase-2 member of the cluster scores < T against the query
-    const int32_t* cstart;    // [ncl+1] into dyn / tent (candidate pairs per cluster, prefix sums)
-    int32_t* dyn;             // see above (query indices)
-    int32_t* dyn_n;           // [ncl]
+    const int32_t* cstart;    // [ncl+1] candidate pairs per cluster, prefix sums
+    const int32_t* cc_q;      // the pairs grouped by cluster: query indices, ascending inside a cluster
+    int32_t* base_cl;         // per pair: static score with the first FINAL phase-2 member folded in; HMK_JMIN = some final member scores < T
+    int32_t* cinfo;           // [ncl][HMK_CI]
+    HmkDynEntry* dyn;         // per cluster: final members (join order == query order), then the sorted tentative joiners
     int32_t* tent;            // tentative joiners in arrival order (scratch, same offsets as the dyn tail)
-    int32_t* tent_n;          // [2][ncl]
     int32_t* a;               // [2][ns] tentative assignment (-1 = none)
     int32_t* dirty;           // [2][ncl] smallest query whose tentative assignment to/from c changed in the last iteration
-    int32_t* flags;           // [HMK_P2_FLAGS]
+    int32_t* stamp;           // [ns] generation in which the query was last put on a work list
+    int32_t* work;            // [2][wcap] queries to re-evaluate
+    int32_t* chg;             // [2][HMK_P2_CHG] clusters whose tentative joiner list changed in the last iteration
+    int32_t* ctl;             // [HMK_P2_CTL]
+    int32_t wcap;
+    unsigned long long* pair_parts;   // scalar pair-score counter, sharded over HMK_PAIR_SHARDS cache lines
     int32_t qa, qb;           // window = queries [qa, qb)
-    int32_t it;               // iteration index (runs on across windows; parity selects the buffers)
-    int32_t first;            // 1: first iteration of its window (never skipped)
+    int32_t gen0;             // generation of the window's first iteration (unique across windows)
+    int32_t max_iters;
 };
-
-__device__ __forceinline__ bool hmk_p2_skip(const HmkP2& P) {
-    return !P.first && __ldcg(P.flags + (P.it - 1) % HMK_P2_FLAGS) == 0;
-}
 
 // candidate pairs per cluster (cq_c is grouped by query, so neighbours rarely collide)
 __global__ void hmk_p2_count_clusters(const int32_t* __restrict__ cq_c, int n, int32_t* __restrict__ cnt) {
@@ -1779,188 +1801,116 @@ __global__ void __launch_bounds__(1024) hmk_exclusive_scan(const int32_t* __rest
     for (int i = lo; i < hi; i++) { out[i] = run; run += cnt[i]; }
 }
 
-// start of a window: nobody joins, everything is dirty
-__global__ void hmk_p2_window_setup(const HmkP2 P) {
+__global__ void hmk_p2_init_cinfo(int ncl, const int32_t* __restrict__ cstart, int32_t* __restrict__ cinfo) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.ncl) return;
-    const int par = P.it & 1;
-    P.tent_n[(size_t)par * P.ncl + c] = 0;
-    P.dirty[(size_t)par * P.ncl + c] = -1;
+    if (c >= ncl) return;
+    reinterpret_cast<int4*>(cinfo)[c] = make_int4(cstart[c], 0, 0, 0);
 }
 
-__global__ void hmk_p2_build_tent(const HmkP2 P) {
-    if (hmk_p2_skip(P)) return;
-    const int qi = P.qa + blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= P.qb) return;
-    const int par = P.it & 1;
-    const int32_t c = P.a[(size_t)par * P.ns + qi];
-    if (c < 0) return;
-    const int pos = atomicAdd(P.tent_n + (size_t)par * P.ncl + c, 1);
-    P.tent[P.cstart[c] + P.dyn_n[c] + pos] = qi;
-}
-
-// one warp per cluster: rank sort of its tentative joiners (distinct query indices) into the dyn tail.  A popular
-// cluster can collect hundreds of joiners per window.  Also resets the next iteration's counters.
-__global__ void hmk_p2_sort_tent(const HmkP2 P) {
-    if (hmk_p2_skip(P)) return;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= P.ncl) return;
-    const int par = P.it & 1;
-    const int n = P.tent_n[(size_t)par * P.ncl + c];
-    if (lane == 0) {
-        P.tent_n[(size_t)(par ^ 1) * P.ncl + c] = 0;
-        P.dirty[(size_t)(par ^ 1) * P.ncl + c] = HMK_P2_CLEAN;
+// S(member, query) with both sequences given as packed words: uniform length 12, max shift 3, matrix in shared memory.
+// qrow[j] = 24 * (query residue j).  77 x (address add + LDS + accumulate); when a warp scores 32 members against ONE
+// query, the loads of a step hit one matrix row (conflict free).
+__device__ __forceinline__ int32_t hmk_score12x3(const int32_t (&qrow)[HMK_MAXL1], uint64_t wm, const int32_t* sM, int32_t P) {
+    int32_t rm[HMK_MAXL1];
+#pragma unroll
+    for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
+    int32_t best = HMK_JMIN;
+#pragma unroll
+    for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
+        int32_t v = 2 * (k < 0 ? -k : k) * P;
+#pragma unroll
+        for (int j = 0; j < HMK_MAXL1; j++)
+            if (j - k >= 0 && j - k < HMK_MAXL1) v += sM[qrow[j - k] + rm[j]];
+        best = v > best ? v : best;
     }
-    if (n == 0) return;
-    const int base = P.cstart[c] + P.dyn_n[c];
-    const int32_t* t = P.tent + base;
-    int32_t* o = P.dyn + base;
-    for (int i = lane; i < n; i += 32) {
-        const int32_t v = t[i];
-        int r = 0;
-        for (int j = 0; j < n; j++) r += t[j] < v;
-        o[r] = v;
-    }
+    return best;
+}
+__device__ __forceinline__ void hmk_qrow12(uint64_t wq, int32_t (&qrow)[HMK_MAXL1]) {
+#pragma unroll
+    for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
 }
 
-// S(member, query) for many members against ONE query per warp.  FAST: uniform length 12, max shift 3, packed
-// words, matrix in shared memory; the query's row offsets are kept in registers, so a pair costs 77 x (address
-// add + LDS + accumulate) and the warp's loads of a step hit one matrix row (conflict free).
+// S(member entry, query) -- FAST: hmk_score12x3 on the entry's packed word; else the general scalar scorer
 template <bool FAST>
 struct HmkQueryScorer {
-    const HmkState& S;
+    const HmkP2& P;
     HmkScalar sc;
     int32_t q;
     int32_t qrow[HMK_MAXL1];
-    __device__ __forceinline__ HmkQueryScorer(const HmkState& S_, const HmkScalar& sc_, int32_t q_) : S(S_), sc(sc_), q(q_) {
-        if (FAST) {
-            const uint64_t wq = sc.packed[q];
-#pragma unroll
-            for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
-        }
+    __device__ __forceinline__ HmkQueryScorer(const HmkP2& P_, const int32_t* sM, int32_t q_) : P(P_), q(q_) {
+        sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
+        if (FAST) hmk_qrow12(P.packed[q], qrow);
     }
-    __device__ __forceinline__ int32_t score(int32_t member) const {
-        if (!FAST) return hmk_scalar_score(S, sc, member, q);
-        const uint64_t wm = sc.packed[member];
-        int32_t rm[HMK_MAXL1];
-#pragma unroll
-        for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
-        int32_t best = HMK_JMIN;
-#pragma unroll
-        for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
-            int32_t v = 2 * (k < 0 ? -k : k) * S.P;
-#pragma unroll
-            for (int j = 0; j < HMK_MAXL1; j++)
-                if (j - k >= 0 && j - k < HMK_MAXL1) v += sc.sM[qrow[j - k] + rm[j]];
-            best = v > best ? v : best;
-        }
-        return best;
+    __device__ __forceinline__ int32_t score(const HmkDynEntry& m) const {
+        if (FAST) return hmk_score12x3(qrow, m.w, sc.sM, P.S.P);
+        return hmk_scalar_score(P.S, sc, P.singles[m.qi], q);
     }
 };
 
-// one warp per window query: its decision given the tentative joiners before it.  A query is
-// re-evaluated only if one of its candidate clusters changed (tentatively) at a position
-// before it in the previous iteration (dirty[c] < qi).
-// Evaluation is lazy: the static score of a pair bounds its final score from above, so a candidate whose
-// static score is below the best valid score found so far is never evaluated.  Per chunk of 32 candidates:
-// (1) one lane per candidate scores the FIRST member the cluster gained in phase 2 (this rejects almost every
-// unrelated candidate), (2) the survivors with more members are evaluated one after the other, best static
-// score first, with the 32 lanes striding over the member list.
+// The decision of one query given the tentative joiners before it (one warp).
+// Evaluation is lazy: the static score of a pair bounds its final score from above, so a candidate whose static score
+// is below the best valid score found so far is never evaluated.  The base pass has already folded the first final member
+// of every cluster into base_cl (and killed almost every unrelated candidate), so per chunk of 32 candidates the few
+// survivors are evaluated one after the other, best static score first, with the 32 lanes striding over the member list.
+// Every global load chain is short: pair -> cluster record (16 B) -> member entry (16 B, carries the packed word).
 template <bool FAST>
-__global__ void __launch_bounds__(256) hmk_p2_decide(const HmkP2 P) {
-    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
-    if (hmk_p2_skip(P)) return;
+__device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_t* sM, int qi, int par, long long& npairs) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int par = P.it & 1;
     const int32_t* a_cur = P.a + (size_t)par * P.ns;
     int32_t* a_new = P.a + (size_t)(par ^ 1) * P.ns;
-    const int32_t* dirty_cur = P.dirty + (size_t)par * P.ncl;
     int32_t* dirty_nxt = P.dirty + (size_t)(par ^ 1) * P.ncl;
-    const int32_t* tent_n = P.tent_n + (size_t)par * P.ncl;
-    const int qi = P.qa + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const bool inw = qi < P.qb;
-    int e0 = 0, e1 = 0;
-    int32_t old = -1;
-    bool dirty = false;
-    if (inw) {
-        e0 = P.qstart[qi]; e1 = P.qstart[qi + 1];
-        old = a_cur[qi];
-        for (int e = e0 + lane; e < e1; e += 32) dirty |= dirty_cur[P.cq_c[e]] < qi;
-        dirty = __any_sync(FULL, dirty);
-        if (!dirty && lane == 0) a_new[qi] = old;
-    }
-    if (!__syncthreads_or(dirty)) return;      // after the first iterations most blocks have nothing to re-evaluate
-    hmk_load_matrix_smem(sM, P.S.M);
-    if (!dirty) return;
-    HmkScalar sc;
-    sc.packed = P.packed; sc.sM = sM; sc.L = P.L;
-    const int32_t q = P.singles[qi];
-    const HmkQueryScorer<FAST> scorer(P.S, sc, q);
     const int32_t T = P.S.T;
-    long long npairs = 0;
+    const int4* cinfo = reinterpret_cast<const int4*>(P.cinfo);
+    const int e0 = P.qstart[qi], e1 = P.qstart[qi + 1];
+    const int32_t old = a_cur[qi];
+    const int32_t q = P.singles[qi];
+    const HmkQueryScorer<FAST> scorer(P, sM, q);
     HmkBestCluster best;        // warp-uniform
     best.score = HMK_JMIN; best.size = 0; best.fid = 0; best.slot = -1;
     for (int eb = e0; eb < e1; eb += 32) {
         const int e = eb + lane;
-        int32_t c = -1, st = HMK_JMIN, cl = 0, off = 0, nd = 0, tn = 0;
-        uint32_t szadd = 0;
-        bool alive = false;
-        if (e < e1) {
-            c = P.cq_c[e]; st = P.cq_s[e]; cl = st;
-            alive = P.base_cl[e] != HMK_JMIN && !(best.slot >= 0 && st < best.score);
-        }
-        if (alive) { off = P.cstart[c]; nd = P.dyn_n[c]; tn = tent_n[c]; }
-        bool more = false;
-        if (alive && nd + tn > 0) {       // (1) the first phase-2 member
-            const int32_t mi = P.dyn[off];
-            if (nd == 0 && mi >= qi) tn = 0;            // every tentative joiner comes after q
-            else {
-                const int32_t m = P.singles[mi];
-                const int32_t s = scorer.score(m);
-                npairs++;
-                if (s < T) { alive = false; if (nd > 0) P.base_cl[e] = HMK_JMIN; }
-                else {
-                    cl = s < cl ? s : cl;
-                    if (nd == 0) szadd = (uint32_t)P.S.ab[m];
-                    more = nd + tn > 1;
-                }
-            }
-        }
-        {   // candidates that are already decided: fold them into the warp's best (prunes step 2)
+        int32_t c = -1, st = HMK_JMIN, cl = HMK_JMIN, off = 0, nd = 0, tn = 0;
+        if (e < e1) { cl = P.base_cl[e]; st = P.cq_s[e]; c = P.cq_c[e]; }
+        const bool alive = cl != HMK_JMIN && !(best.slot >= 0 && st < best.score);
+        if (alive) { const int4 ci = cinfo[c]; off = ci.x; nd = ci.y; tn = par ? ci.w : ci.z; }
+        const int start = nd > 0 ? 1 : 0;             // member 0 of the final members is in base_cl already
+        const bool more = alive && nd + tn > start;
+        {   // candidates without further members are decided: fold them into the warp's best (prunes the rest)
             HmkBestCluster mine;
             mine.score = HMK_JMIN; mine.size = 0; mine.fid = 0; mine.slot = -1;
-            if (alive && !more) hmk_consider(mine, cl, (int32_t)((uint32_t)P.S.c_size[c] + szadd), P.S.c_founder[c], c);
+            if (alive && !more) hmk_consider(mine, cl, P.S.c_size[c], P.S.c_founder[c], c);
             if (__any_sync(FULL, mine.slot >= 0)) {
                 hmk_best_reduce(mine);
                 if (mine.slot >= 0) hmk_consider(best, mine.score, mine.size, mine.fid, mine.slot);
             }
         }
         unsigned todo = __ballot_sync(FULL, more);
-        while (todo) {                    // (2) survivors with more members, best static score first
+        while (todo) {                    // survivors with more members, best static score first
             const bool in_todo = (todo >> lane) & 1u;
             const int32_t mx = __reduce_max_sync(FULL, in_todo ? st : HMK_JMIN);
             if (best.slot >= 0 && mx < best.score) break;          // nothing left can reach the best any more
             const int pick = __ffs(__ballot_sync(FULL, in_todo && st == mx)) - 1;
-            const int32_t poff = __shfl_sync(FULL, off, pick), pnd = __shfl_sync(FULL, nd, pick), ptot = pnd + __shfl_sync(FULL, tn, pick);
+            const int32_t poff = __shfl_sync(FULL, off, pick), pnd = __shfl_sync(FULL, nd, pick),
+                          ptot = pnd + __shfl_sync(FULL, tn, pick);
             bool ok = true, final_fail = false;
             int32_t mn = HMK_JMAX;
             uint32_t sz = 0;
-            for (int i0 = 1; i0 < ptot; i0 += 32) {
+            for (int i0 = pnd > 0 ? 1 : 0; i0 < ptot; i0 += 32) {
                 const int i = i0 + lane;
                 bool act = i < ptot;
-                const int32_t mi = act ? P.dyn[poff + i] : 0;
-                const bool behind = act && i >= pnd && mi >= qi;      // tentative joiners at or behind q do not count
+                HmkDynEntry m;
+                m.w = 0; m.qi = 0; m.ab = 0;
+                if (act) m = P.dyn[poff + i];
+                const bool behind = act && i >= pnd && m.qi >= qi;      // tentative joiners at or behind q do not count
                 act = act && !behind;
                 bool bad = false;
                 if (act) {
-                    const int32_t m = P.singles[mi];
                     const int32_t s = scorer.score(m);
                     npairs++;
                     bad = s < T;
                     mn = s < mn ? s : mn;
-                    if (i >= pnd) sz += (uint32_t)P.S.ab[m];
+                    if (i >= pnd) sz += (uint32_t)m.ab;
                 }
                 const unsigned badm = __ballot_sync(FULL, bad);
                 if (badm) { ok = false; final_fail = __any_sync(FULL, bad && i < pnd); break; }
@@ -1971,7 +1921,7 @@ __global__ void __launch_bounds__(256) hmk_p2_decide(const HmkP2 P) {
             int32_t k_cl = 0, k_size = 0, k_fid = 0, k_c = -1;
             if (lane == pick) {
                 if (!ok && final_fail) P.base_cl[e] = HMK_JMIN;
-                if (ok) { k_cl = mn < cl ? mn : cl; k_size = (int32_t)((uint32_t)P.S.c_size[c] + szadd + sz); k_fid = P.S.c_founder[c]; k_c = c; }
+                if (ok) { k_cl = mn < cl ? mn : cl; k_size = (int32_t)((uint32_t)P.S.c_size[c] + sz); k_fid = P.S.c_founder[c]; k_c = c; }
             }
             if (ok) {
                 k_cl = __shfl_sync(FULL, k_cl, pick); k_size = __shfl_sync(FULL, k_size, pick);
@@ -1984,30 +1934,170 @@ __global__ void __launch_bounds__(256) hmk_p2_decide(const HmkP2 P) {
     if (lane == 0) {
         a_new[qi] = best.slot;
         if (best.slot != old) {
-            P.flags[P.it % HMK_P2_FLAGS] = 1;
-            if (old >= 0) atomicMin(dirty_nxt + old, qi);
-            if (best.slot >= 0) atomicMin(dirty_nxt + best.slot, qi);
+            P.ctl[6 + par] = 1;
+            const int32_t two[2] = {old, best.slot};
+            for (int k = 0; k < 2; k++) {
+                const int32_t c = two[k];
+                if (c < 0) continue;
+                if (atomicMin(dirty_nxt + c, qi) == HMK_P2_CLEAN) {       // first change of this cluster in this iteration
+                    const int pos = atomicAdd(P.ctl + 4 + (par ^ 1), 1);
+                    if (pos < HMK_P2_CHG) P.chg[(size_t)(par ^ 1) * HMK_P2_CHG + pos] = c;
+                }
+            }
         }
     }
-    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(FULL, npairs, s);
-    if (lane == 0 && npairs) atomicAdd((unsigned long long*)&P.S.ctl->scalar_pairs, (unsigned long long)npairs);
+    __syncwarp();
 }
 
-// window converged in iteration P.it: the tentative joiners become final members, in query order
-__global__ void hmk_p2_commit(const HmkP2 P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.ncl) return;
-    const int n = P.tent_n[(size_t)(P.it & 1) * P.ncl + c];
-    if (n == 0) return;
-    int32_t nd = P.dyn_n[c], cnt = P.S.c_count[c], size = P.S.c_size[c];
-    const int32_t* t = P.dyn + P.cstart[c] + nd;
-    for (int i = 0; i < n; i++) {
-        const int32_t q = P.singles[t[i]];
-        P.S.rank[q] = cnt++;
-        size = hmk_wadd(size, P.S.ab[q]);
-        P.S.slot[q] = c;
+// ONE cooperative launch resolves one window: setup, base pass, the fixed-point iterations and the commit are phases of
+// the same grid separated by grid-wide barriers, so an iteration that re-evaluates a handful of queries costs a few
+// microseconds instead of three launches and a host round trip.
+//   setup   per cluster: nobody joins
+//   base    one thread per candidate pair of the window: fold the FIRST final phase-2 member of the cluster into the
+//           pair's score (HMK_JMIN if it scores < T).  Unrelated candidates -- nearly all of them -- die here.
+//   iteration t (parity t & 1):
+//     A  every window query goes onto the tentative list of the cluster it currently joins and keeps its assignment
+//        by default; the queries that must be re-evaluated -- a candidate cluster changed (tentatively) at a position
+//        before them in iteration t-1 -- are put on the work list: from the clusters' side when few clusters changed
+//        (their candidate lists are sorted by query), else every query gathers dirty[] for its candidates
+//     B  one warp per cluster: rank sort of the tentative joiners into the dyn tail
+//     C  warps take queries off the work list (iteration 0: the whole window) and decide them
+//   until an iteration changes nothing; commit: the tentative joiners become final members, in query order.
+template <bool FAST>
+__global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    hmk_load_matrix_smem(sM, P.S.M);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    long long npairs = 0;
+    // ---- setup + base
+    for (int c = gtid; c < P.ncl; c += gthreads) {
+        P.cinfo[c * HMK_CI + 2] = 0; P.cinfo[c * HMK_CI + 3] = 0;
+        P.dirty[c] = HMK_P2_CLEAN; P.dirty[(size_t)P.ncl + c] = HMK_P2_CLEAN;
     }
-    P.dyn_n[c] = nd + n; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
+    if (gtid < HMK_P2_CTL) P.ctl[gtid] = 0;
+    {
+        const int e0 = P.qstart[P.qa], e1 = P.qstart[P.qb];
+        for (int e = e0 + gtid; e < e1; e += gthreads) {
+            const int4 ci = reinterpret_cast<const int4*>(P.cinfo)[P.cq_c[e]];      // .x / .y only: not touched by the setup
+            int32_t cl = P.cq_s[e];
+            if (ci.y > 0) {                                // the cluster has final phase-2 members
+                const HmkDynEntry m = P.dyn[ci.x];
+                const HmkQueryScorer<FAST> scorer(P, sM, P.singles[P.cq_q[e]]);
+                const int32_t s = scorer.score(m);
+                npairs++;
+                cl = s < P.S.T ? HMK_JMIN : (s < cl ? s : cl);
+            }
+            P.base_cl[e] = cl;
+        }
+    }
+    grid.sync();
+    int t = 0;
+    for (;; t++) {
+        const int par = t & 1;
+        // ---- A
+        for (int qi = P.qa + gtid; qi < P.qb; qi += gthreads) {
+            const int32_t old = P.a[(size_t)par * P.ns + qi];
+            if (old >= 0) {
+                int32_t* ci = P.cinfo + old * HMK_CI;
+                const int pos = atomicAdd(ci + 2 + par, 1);
+                P.tent[ci[0] + ci[1] + pos] = qi;
+            }
+            P.a[(size_t)(par ^ 1) * P.ns + qi] = old;
+        }
+        if (t > 0) {
+            const int32_t* dirty_cur = P.dirty + (size_t)par * P.ncl;
+            const int nchg = P.ctl[4 + par];
+            const int32_t gen = P.gen0 + t;
+            int32_t* work = P.work + (size_t)par * P.wcap;
+            if (nchg <= HMK_P2_CHG) {
+                for (int k = gwarp; k < nchg; k += gwarps) {
+                    const int32_t c = P.chg[(size_t)par * HMK_P2_CHG + k];
+                    const int32_t from = max(P.qa, dirty_cur[c] + 1);
+                    int lo = P.cstart[c], hi = P.cstart[c + 1];
+                    const int end = hi;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.cc_q[mid] < from) lo = mid + 1; else hi = mid; }
+                    for (int i = lo + lane; i < end; i += 32) {
+                        const int32_t qi = P.cc_q[i];
+                        if (qi >= P.qb) break;
+                        if (atomicMax(P.stamp + qi, gen) < gen) work[atomicAdd(P.ctl + par, 1)] = qi;
+                    }
+                }
+            } else {
+                for (int qi = P.qa + gwarp; qi < P.qb; qi += gwarps) {
+                    bool dirty = false;
+                    const int e1 = P.qstart[qi + 1];
+                    for (int e = P.qstart[qi] + lane; e < e1; e += 32) dirty |= dirty_cur[P.cq_c[e]] < qi;
+                    if (__any_sync(FULL, dirty) && lane == 0) work[atomicAdd(P.ctl + par, 1)] = qi;
+                }
+            }
+        }
+        grid.sync();
+        // ---- B
+        for (int c = gwarp; c < P.ncl; c += gwarps) {
+            int32_t* ci = P.cinfo + c * HMK_CI;
+            const int n = ci[2 + par];
+            const int base = ci[0] + ci[1];
+            __syncwarp();
+            if (lane == 0) { ci[2 + (par ^ 1)] = 0; P.dirty[(size_t)(par ^ 1) * P.ncl + c] = HMK_P2_CLEAN; }
+            if (n == 0) continue;
+            const int32_t* tl = P.tent + base;
+            HmkDynEntry* o = P.dyn + base;
+            for (int i = lane; i < n; i += 32) {
+                const int32_t v = tl[i];
+                int r = 0;
+                for (int j = 0; j < n; j++) r += tl[j] < v;
+                const int32_t id = P.singles[v];
+                HmkDynEntry en;
+                en.w = P.packed ? P.packed[id] : 0ull; en.qi = v; en.ab = P.S.ab[id];
+                o[r] = en;
+            }
+        }
+        if (gtid == 0) { P.ctl[par ^ 1] = 0; P.ctl[2 + (par ^ 1)] = 0; P.ctl[4 + (par ^ 1)] = 0; P.ctl[6 + (par ^ 1)] = 0; }
+        grid.sync();
+        // ---- C
+        {
+            const int nwork = t == 0 ? P.qb - P.qa : P.ctl[par];
+            const int32_t* work = P.work + (size_t)par * P.wcap;
+            for (;;) {
+                int wi = 0;
+                if (lane == 0) wi = atomicAdd(P.ctl + 2 + par, 1);
+                wi = __shfl_sync(FULL, wi, 0);
+                if (wi >= nwork) break;
+                const int qi = t == 0 ? P.qa + wi : work[wi];
+                if (t == 0 && P.qstart[qi] == P.qstart[qi + 1]) continue;       // no candidate: stays unassigned
+                hmk_p2_decide_query<FAST>(P, sM, qi, par, npairs);
+            }
+        }
+        grid.sync();
+        if (!P.ctl[6 + par] || t + 1 >= P.max_iters) break;
+    }
+    // ---- commit (parity of the last iteration: its tentative lists are the final joiners)
+    {
+        const int par = t & 1;
+        for (int c = gtid; c < P.ncl; c += gthreads) {
+            int32_t* ci = P.cinfo + c * HMK_CI;
+            const int n = ci[2 + par];
+            if (n == 0) continue;
+            const int32_t nd = ci[1];
+            int32_t cnt = P.S.c_count[c], size = P.S.c_size[c];
+            const HmkDynEntry* tl = P.dyn + ci[0] + nd;
+            for (int i = 0; i < n; i++) {
+                const int32_t q = P.singles[tl[i].qi];
+                P.S.rank[q] = cnt++;
+                size = hmk_wadd(size, tl[i].ab);
+                P.S.slot[q] = c;
+            }
+            ci[1] = nd + n; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
+        }
+        if (gtid == 0) P.ctl[8] = t + 1;
+    }
+    for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(FULL, npairs, s);
+    if (lane == 0) hmk_count_pairs(P.pair_parts, npairs);
 }
 
 // ---------------------------------------------------------------- small utilities

@@ -41,9 +41,9 @@ def test_option_ranges_are_checked():
     try:
         for name, bad in (("qt", 100000), ("qt", -1), ("p2_chunk", -5), ("p2_window", 0), ("hit_cap", -1), ("hit_cap", 1 << 40),
                           ("waves", 0), ("waves", 1000), ("kb", 0), ("kb", 33), ("batch", 513), ("lookahead", 3), ("capq", 0),
-                          ("p2_spec", 0), ("no_such_option", 1)):
+                          ("xhit_cap", -1), ("p2_spec", 3), ("no_such_option", 1)):
             assert L.hmk_set_option(ctx._h, name.encode(), bad) == _lib.STATUS_BAD_ARG, (name, bad)
-        for name, ok in (("qt", 0), ("qt", 16), ("kb", 32), ("batch", 512), ("lookahead", 2), ("p2_spec", 16), ("hit_cap", 1024)):
+        for name, ok in (("qt", 0), ("qt", 16), ("kb", 32), ("batch", 512), ("lookahead", 2), ("p2_window", 1), ("hit_cap", 1024)):
             assert L.hmk_set_option(ctx._h, name.encode(), ok) == _lib.STATUS_OK, (name, ok)
     finally:
         ctx.close()

@@ -41,8 +41,7 @@ def _case(rng, mats, names):
     opts = {}
     if rng.random() < 0.5:
         opts = {"batch": int(rng.choice([1, 2, 5, 17, 64])), "kb": int(rng.choice([1, 2, 8])), "capq": int(rng.choice([1, 4, 256])),
-                "p2_window": int(rng.choice([1, 7, 64, 65536])), "lookahead": int(rng.integers(0, 2)) + n % 2,
-                "p2_spec": 1 + n % 4}      # (derived from n: the random stream of the cases stays as it was)
+                "p2_window": int(rng.choice([1, 7, 64, 65536])), "lookahead": int(rng.integers(0, 2)) + n % 2}   # (0..2; derived from n so that the random stream stays as it was)
     if rng.random() < 0.4:      # the older code paths stay covered: exact packed kernel, separate phase-2 founder pass
         opts = dict(opts, filter=int(rng.integers(0, 2)), reuse=int(rng.integers(0, 2)))
     M = mats[m]

@@ -158,7 +158,7 @@ def test_empty_and_tiny_inputs(blosum62):
 
 @pytest.mark.parametrize("opts", [{}, {"force_generic": 1}, {"batch": 7, "kb": 1}, {"batch": 64, "kb": 2, "qt": 16},
                                   {"batch": 512, "waves": 1}, {"p2_chunk": 1024, "hit_cap": 1024, "p2_window": 100, "capq": 1},
-                                  {"lookahead": 0, "p2_spec": 1}, {"lookahead": 1, "batch": 16, "p2_spec": 16, "p2_window": 64}])
+                                  {"lookahead": 0, "p2_window": 300}, {"lookahead": 1, "batch": 16, "p2_window": 64}])
 def test_musi_golden_gpu(golden_dir, blosum62, opts):
     z = np.load(os.path.join(golden_dir, "musi.npz"))
     T, X, P, K = (int(v) for v in z["params"])
@@ -220,8 +220,8 @@ SYNTH_CASES = [
     (3000, 7, 12, "blosum62", 0, None, False, {"reuse": 0, "batch": 24}),
     (3000, 10, 10, "blosum62", -1, None, False, {"batch": 8, "kb": 1}),     # truncated partner lists -> restarts, hits of re-done batches
     (3000, 11, 11, "blosum62", 0, 200, True, {"batch": 20, "kb": 2}),
-    (6000, 12, 12, "blosum62", 0, 60, False, {"p2_window": 256, "p2_spec": 2}),      # few clusters, many joiners per cluster and window
-    (6000, 12, 12, "blosum62", 0, 60, False, {"p2_window": 100000, "p2_spec": 5, "hit_cap": 1024}),
+    (6000, 12, 12, "blosum62", 0, 60, False, {"p2_window": 256}),      # few clusters, many joiners per cluster and window
+    (6000, 12, 12, "blosum62", 0, 60, False, {"p2_window": 100000, "hit_cap": 1024}),
     (5000, 12, 12, "blosum62", 0, None, False, {"batch": 32, "lookahead": 2, "hit_cap": 1024}),   # founder-hit buffer grows in the resolver
     (5000, 12, 12, "blosum62", 0, None, False, {"batch": 32, "lookahead": 1}),
     (5000, 12, 12, "blosum62", 0, None, False, {"batch": 32, "lookahead": 0}),
