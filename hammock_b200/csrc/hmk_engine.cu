@@ -377,6 +377,8 @@ private:
 #endif
         CK(cudaStreamSynchronize(st_));
     }
+    // the unrolled one-at-a-time pair scorer applies: uniform length 12, max shift 3, lane-sized matrix entries
+    bool scalar12x3() const { return fast_scalar_ && fast_ && max_len_ == HMK_MAXL1 && X_ == 3; }
     int phase1();
     void phase2();
     int compact_unassigned(int32_t* out);
@@ -902,7 +904,8 @@ int Engine::phase1() {
             c.ac_cnt = d_ac_cnt_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p; c.capq = (int32_t)capq;
             c.cand_count = d_counts_.p + 1; c.cand_cap = 0; c.linked = 1;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
-            hmk_member_check<<<sm_count_ * 2, 256, 0, st_>>>(c);
+            if (scalar12x3()) hmk_member_check<true><<<sm_count_ * 2, 256, 0, st_>>>(c);
+            else hmk_member_check<false><<<sm_count_ * 2, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
             launches_++;
         }
@@ -1038,7 +1041,8 @@ void Engine::phase2() {
                 c.cand_key_q = d_key_q_.p; c.cand_score = d_cand_score_.p;
                 c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits;
                 c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
-                hmk_member_check<<<sm_count_ * 4, 256, 0, st_>>>(c);
+                if (scalar12x3()) hmk_member_check<true><<<sm_count_ * 4, 256, 0, st_>>>(c);
+                else hmk_member_check<false><<<sm_count_ * 4, 256, 0, st_>>>(c);
                 CK(cudaGetLastError());
                 launches_++;
                 CK(cudaMemcpyAsync(h_scalars_ + 1, d_counts_.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
@@ -1086,7 +1090,8 @@ void Engine::phase2() {
             c.cand_key_q = d_key_q_.p; c.cand_score = d_cand_score_.p;
             c.cand_count = d_counts_.p + 1; c.cand_cap = (unsigned int)cand_cap; c.linked = 0; c.cbits = cbits;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
-            hmk_member_check<<<sm_count_ * 8, 256, 0, st_>>>(c);
+            if (scalar12x3()) hmk_member_check<true><<<sm_count_ * 8, 256, 0, st_>>>(c);
+            else hmk_member_check<false><<<sm_count_ * 8, 256, 0, st_>>>(c);
             CK(cudaGetLastError());
             launches_++;
             CK(cudaMemcpyAsync(h_scalars_ + 1, d_counts_.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st_));
@@ -1205,7 +1210,7 @@ void Engine::phase2() {
     P.wcap = Wmax; P.work = d_work_.p; P.ctl = d_work_.p + 2 * (size_t)Wmax; P.chg = P.ctl + HMK_P2_CTL;
     P.pair_parts = d_pairparts_.p;
     // the unrolled pair scorer: uniform length 12, max shift 3, lane-sized matrix entries
-    const bool p2_fast = fast_scalar_ && fast_ && max_len_ == HMK_MAXL1 && X_ == 3;
+    const bool p2_fast = scalar12x3();
     const void* kernel = p2_fast ? (const void*)hmk_p2_window<true> : (const void*)hmk_p2_window<false>;
     int per_sm = 0;      // the cooperative grid must be resident as a whole
     if (p2_fast) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmk_p2_window<true>, 256, 0));

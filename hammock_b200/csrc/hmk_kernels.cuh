@@ -966,6 +966,29 @@ __device__ __forceinline__ int32_t hmk_scalar_score(const HmkState& S, const Hmk
     return best;
 }
 
+// S(member, query) with both sequences given as packed words: uniform length 12, max shift 3, matrix in shared memory.
+// qrow[j] = 24 * (query residue j).  77 x (address add + LDS + accumulate); when a warp scores 32 members against ONE
+// query, the loads of a step hit one matrix row (conflict free).
+__device__ __forceinline__ int32_t hmk_score12x3(const int32_t (&qrow)[HMK_MAXL1], uint64_t wm, const int32_t* sM, int32_t P) {
+    int32_t rm[HMK_MAXL1];
+#pragma unroll
+    for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
+    int32_t best = HMK_JMIN;
+#pragma unroll
+    for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
+        int32_t v = 2 * (k < 0 ? -k : k) * P;
+#pragma unroll
+        for (int j = 0; j < HMK_MAXL1; j++)
+            if (j - k >= 0 && j - k < HMK_MAXL1) v += sM[qrow[j - k] + rm[j]];
+        best = v > best ? v : best;
+    }
+    return best;
+}
+__device__ __forceinline__ void hmk_qrow12(uint64_t wq, int32_t (&qrow)[HMK_MAXL1]) {
+#pragma unroll
+    for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
+}
+
 // ---------------------------------------------------------------- member check (complete linkage)
 // One thread per founder hit: does the query also score >= T against every other current
 // member of that cluster?  (ClinkageClusterScorer.java:30-49; early exit keeps it cheap.)
@@ -994,6 +1017,8 @@ struct HmkCheckArgs {
     unsigned long long* pair_parts;   // sharded pair-score counter
 };
 
+// FAST: uniform length 12, max shift 3 -- the unrolled scorer (hmk_score12x3) on the packed words
+template <bool FAST>
 __global__ void hmk_member_check(const HmkCheckArgs a) {
     __shared__ int32_t sM[HMK_NRES * HMK_NRES];
     hmk_load_matrix_smem(sM, a.S.M);
@@ -1023,8 +1048,10 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         }
         int32_t cl = h.z;
         bool ok = true;
+        int32_t qrow[HMK_MAXL1];
+        if (FAST) hmk_qrow12(a.packed[q], qrow);
         for (int32_t m = a.S.next[a.S.c_founder[c]]; m >= 0; m = a.S.next[m]) {
-            int32_t s = hmk_scalar_score(a.S, sc, m, q);
+            const int32_t s = FAST ? hmk_score12x3(qrow, a.packed[m], sM, a.S.P) : hmk_scalar_score(a.S, sc, m, q);
             npairs++;
             if (s < cl) cl = s;
             if (s < a.S.T) { ok = false; break; }
@@ -1805,29 +1832,6 @@ __global__ void hmk_p2_init_cinfo(int ncl, const int32_t* __restrict__ cstart, i
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncl) return;
     reinterpret_cast<int4*>(cinfo)[c] = make_int4(cstart[c], 0, 0, 0);
-}
-
-// S(member, query) with both sequences given as packed words: uniform length 12, max shift 3, matrix in shared memory.
-// qrow[j] = 24 * (query residue j).  77 x (address add + LDS + accumulate); when a warp scores 32 members against ONE
-// query, the loads of a step hit one matrix row (conflict free).
-__device__ __forceinline__ int32_t hmk_score12x3(const int32_t (&qrow)[HMK_MAXL1], uint64_t wm, const int32_t* sM, int32_t P) {
-    int32_t rm[HMK_MAXL1];
-#pragma unroll
-    for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
-    int32_t best = HMK_JMIN;
-#pragma unroll
-    for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
-        int32_t v = 2 * (k < 0 ? -k : k) * P;
-#pragma unroll
-        for (int j = 0; j < HMK_MAXL1; j++)
-            if (j - k >= 0 && j - k < HMK_MAXL1) v += sM[qrow[j - k] + rm[j]];
-        best = v > best ? v : best;
-    }
-    return best;
-}
-__device__ __forceinline__ void hmk_qrow12(uint64_t wq, int32_t (&qrow)[HMK_MAXL1]) {
-#pragma unroll
-    for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
 }
 
 // S(member entry, query) -- FAST: hmk_score12x3 on the entry's packed word; else the general scalar scorer
