@@ -153,6 +153,7 @@ struct Options {
     int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
     int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
+    int64_t p2_first = 0;         // queries in the first phase-2 window (0 = automatic)
     int64_t xhit_cap = 0;         // capacity of the kept-hit buffer (0 = automatic: the last run's need, else 96 per sequence)
 };
 
@@ -301,8 +302,8 @@ private:
     DevBuf<unsigned long long> d_pairctr_;
     // ---- phase-2 scratch
     DevBuf<int32_t> d_singles_, d_blockcnt_, d_cand_score_, d_cand_score2_, d_cq_c_, d_cq_q_, d_qstart_, d_cstart_, d_ccount_,
-        d_a0_, d_flags_, d_base_cl_, d_tent_, d_cinfo_, d_work_, d_stamp_, d_cc_q_, d_cc_c_;
-    DevBuf<unsigned long long> d_pairparts_;
+        d_a0_, d_flags_, d_base_cl_, d_cinfo_, d_work_, d_stamp_, d_cc_q_, d_cc_c_;
+    DevBuf<unsigned long long> d_pairparts_, d_p2tim_;
     DevBuf<HmkDynEntry> d_dyn_;
     DevBuf<unsigned long long> d_key_q_, d_key_tmp_;
     DevBuf<unsigned char> d_cub_;
@@ -382,7 +383,7 @@ private:
     int phase1();
     void phase2();
     int compact_unassigned(int32_t* out);
-    void sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_bits);
+    void sort_pairs(unsigned long long* keys, int32_t* vals, int n, int begin_bit, int end_bit);
 };
 
 // ---------------------------------------------------------------- upload
@@ -711,14 +712,14 @@ int Engine::compact_unassigned(int32_t* out) {
     return h_scalars_[4];
 }
 
-void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int key_bits) {
+void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int begin_bit, int end_bit) {
     // ancillary plumbing (grouping the sparse candidate list); CUB radix sort, in place via temporaries
     d_key_tmp_.reserve(n);
     d_cand_score2_.reserve(n);
     size_t bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, d_key_tmp_.p, vals, d_cand_score2_.p, n, 0, key_bits, st_));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, d_key_tmp_.p, vals, d_cand_score2_.p, n, begin_bit, end_bit, st_));
     d_cub_.reserve(bytes);
-    CK(cub::DeviceRadixSort::SortPairs(d_cub_.p, bytes, keys, d_key_tmp_.p, vals, d_cand_score2_.p, n, 0, key_bits, st_));
+    CK(cub::DeviceRadixSort::SortPairs(d_cub_.p, bytes, keys, d_key_tmp_.p, vals, d_cand_score2_.p, n, begin_bit, end_bit, st_));
     CK(cudaMemcpyAsync(keys, d_key_tmp_.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToDevice, st_));
     CK(cudaMemcpyAsync(vals, d_cand_score2_.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, st_));
     launches_ += 8;
@@ -1172,19 +1173,14 @@ void Engine::phase2() {
     if (ncand == 0) { sec(-1); return; }
     const int nc = (int)ncand;
     const int ncp = (int)ncand_padded_;   // >= nc: padded entries carry key ~0 and sort to the end
-    // group by query (ascending cluster inside a query); per cluster only the NUMBER of candidate pairs is needed
-    // (room for its joiners), so there is no second sort
-    sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, cbits + qbits);
+    // group by query: a stable radix sort over the query field only (the order of the candidates inside a query does not
+    // matter: every decision is an arg-max under a strict total order)
+    sort_pairs(d_key_q_.p, d_cand_score_.p, ncp, cbits, cbits + qbits);
     d_cq_c_.reserve(nc); d_cq_q_.reserve(nc); d_qstart_.reserve(ns + 2); d_cstart_.reserve(ncl + 2); d_ccount_.reserve(ncl + 1);
     hmk_split_keys_lo<<<(nc + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, cbits, d_cq_c_.p, d_cq_q_.p);
     hmk_segment_starts<<<(ns + 1 + 255) / 256, 256, 0, st_>>>(d_key_q_.p, nc, ns, cbits, d_qstart_.p);
-    CK(cudaMemsetAsync(d_ccount_.p, 0, sizeof(int32_t) * (ncl + 1), st_));
-    hmk_p2_count_clusters<<<sm_count_ * 8, 256, 0, st_>>>(d_cq_c_.p, nc, d_ccount_.p);
-    hmk_exclusive_scan<<<1, 1024, 0, st_>>>(d_ccount_.p, ncl, d_cstart_.p);
-    d_cinfo_.reserve((size_t)ncl * HMK_CI);
-    hmk_p2_init_cinfo<<<(ncl + 255) / 256, 256, 0, st_>>>(ncl, d_cstart_.p, d_cinfo_.p);
     CK(cudaGetLastError());
-    launches_ += 5;
+    launches_ += 2;
     // the pairs once more, grouped by cluster with ascending queries inside a cluster: a STABLE sort of the query-ordered
     // list by the cluster field alone (cbits bits, two radix passes); the clusters' offsets are cstart
     d_cc_q_.reserve(nc); d_cc_c_.reserve(nc);
@@ -1195,20 +1191,29 @@ void Engine::phase2() {
         CK(cub::DeviceRadixSort::SortPairs(d_cub_.p, bytes, d_cq_c_.p, d_cc_c_.p, d_cq_q_.p, d_cc_q_.p, nc, 0, cbits, st_));
         launches_ += 4;
     }
+    d_cinfo_.reserve((size_t)ncl * HMK_CI);
+    hmk_segment_starts_i32<<<(ncl + 1 + 255) / 256, 256, 0, st_>>>(d_cc_c_.p, nc, ncl, d_cstart_.p);
+    hmk_p2_init_cinfo<<<(ncl + 255) / 256, 256, 0, st_>>>(ncl, d_cstart_.p, d_cinfo_.p);
+    CK(cudaGetLastError());
+    launches_ += 2;
     const int Wmax = (int)std::max<int64_t>(1, opt.p2_window);
-    d_dyn_.reserve(nc); d_base_cl_.reserve(nc); d_tent_.reserve(nc);
-    d_a0_.reserve(2 * (size_t)ns); d_dirty_a_.reserve(2 * (size_t)ncl); d_stamp_.reserve(ns);
+    d_dyn_.reserve(nc); d_base_cl_.reserve(nc);
+    d_a0_.reserve(ns); d_dirty_a_.reserve(ncl); d_stamp_.reserve(ns);
     d_work_.reserve(2 * (size_t)Wmax + HMK_P2_CTL + 2 * HMK_P2_CHG);
-    CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * 2 * (size_t)ns, st_));
+    CK(cudaMemsetAsync(d_a0_.p, 0xff, sizeof(int32_t) * (size_t)ns, st_));
     CK(cudaMemsetAsync(d_stamp_.p, 0xff, sizeof(int32_t) * (size_t)ns, st_));
     HmkP2 P{};
     P.S = state(); P.packed = fast_scalar_ ? d_packed_.p : nullptr; P.L = max_len_;
     P.ncl = ncl; P.ns = ns; P.singles = d_singles_.p; P.qstart = d_qstart_.p; P.cq_c = d_cq_c_.p; P.cq_q = d_cq_q_.p; P.cq_s = d_cand_score_.p;
     P.cstart = d_cstart_.p; P.cc_q = d_cc_q_.p;
     P.base_cl = d_base_cl_.p; P.cinfo = d_cinfo_.p; P.dyn = d_dyn_.p;
-    P.tent = d_tent_.p; P.a = d_a0_.p; P.dirty = d_dirty_a_.p; P.stamp = d_stamp_.p;
+    P.a = d_a0_.p; P.dirty = d_dirty_a_.p; P.stamp = d_stamp_.p;
     P.wcap = Wmax; P.work = d_work_.p; P.ctl = d_work_.p + 2 * (size_t)Wmax; P.chg = P.ctl + HMK_P2_CTL;
     P.pair_parts = d_pairparts_.p;
+#ifdef HMK_DEBUG
+    d_p2tim_.reserve(64);
+    P.tim = d_p2tim_.p;
+#endif
     // the unrolled pair scorer: uniform length 12, max shift 3, lane-sized matrix entries
     const bool p2_fast = scalar12x3();
     const void* kernel = p2_fast ? (const void*)hmk_p2_window<true> : (const void*)hmk_p2_window<false>;
@@ -1219,7 +1224,7 @@ void Engine::phase2() {
     // window size adapts to how hard the fixed point is: dense inputs (everything joins) need many
     // iterations per window unless few queries per cluster are in flight at a time.  The first windows are small: the
     // members they make final let the base pass reject most candidate pairs of every later window up front
-    int W = std::min(Wmax, std::max(1024, ncl / 4));
+    int W = std::min<int64_t>(Wmax, opt.p2_first > 0 ? opt.p2_first : std::max(1024, ncl / 4));
     int gen = 0;
     sec(SEC_P2_ITERATE);
     for (int qa = 0; qa < ns;) {
@@ -1235,7 +1240,13 @@ void Engine::phase2() {
         stats.p2_rounds += iters;
         gen += iters + 1;
 #ifdef HMK_DEBUG
-        if (getenv("HMK_DEBUG_P2")) fprintf(stderr, "p2 window [%d, %d) W %d grid %d: %d iterations\n", qa, qb, W, grid, iters);
+        if (getenv("HMK_DEBUG_P2")) {
+            unsigned long long tm[64];
+            CK(cudaMemcpy(tm, P.tim, sizeof(tm), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "p2 window [%d, %d) W %d grid %d: %d iterations; us: D0 %.0f", qa, qb, W, grid, iters, (tm[1] - tm[0]) * 1e-3);
+            for (int k = 1; k < iters && 2 * k + 1 < 62; k++) fprintf(stderr, " | R %.0f D %.0f", (tm[2 * k] - tm[2 * k - 1]) * 1e-3, (tm[2 * k + 1] - tm[2 * k]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
 #endif
         qa = qb;
         if (iters > 8) W = std::min(Wmax, std::max(256, W / 2));
@@ -1608,7 +1619,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
         {"p2_chunk", &o.p2_chunk, 1024, 1 << 24},   {"hit_cap", &o.hit_cap, 1024, (int64_t)1 << 30},
         {"force_generic", &o.force_generic, 0, 1},  {"profile", &o.profile, 0, 1},
         {"p2_window", &o.p2_window, 1, 1 << 24},
-        {"xhit_cap", &o.xhit_cap, 0, (int64_t)1 << 30},
+        {"xhit_cap", &o.xhit_cap, 0, (int64_t)1 << 30}, {"p2_first", &o.p2_first, 0, 1 << 24},
     };
     for (const Knob& k : knobs) {
         if (s != k.name) continue;

@@ -1769,7 +1769,7 @@ struct __align__(16) HmkDynEntry {
     int32_t qi;     // query index (into singles)
     int32_t ab;     // abundance
 };
-// per cluster, one 16-byte record: [0] offset into dyn / tent, [1] final phase-2 members, [2 + parity] tentative joiners
+// per cluster, one 16-byte record: [0] offset into dyn, [1] final phase-2 members, [2] tentative joiners, [3] unused
 #define HMK_CI 4
 // control words of a window (P.ctl): per parity [0..1] work-list entries, [2..3] entries consumed, [4..5] clusters on the
 // changed list, [6..7] "some assignment changed"; [8] iterations the window took (read by the host)
@@ -1789,10 +1789,9 @@ struct HmkP2 {
     const int32_t* cc_q;      // the pairs grouped by cluster: query indices, ascending inside a cluster
     int32_t* base_cl;         // per pair: static score with the first FINAL phase-2 member folded in; HMK_JMIN = some final member scores < T
     int32_t* cinfo;           // [ncl][HMK_CI]
-    HmkDynEntry* dyn;         // per cluster: final members (join order == query order), then the sorted tentative joiners
-    int32_t* tent;            // tentative joiners in arrival order (scratch, same offsets as the dyn tail)
-    int32_t* a;               // [2][ns] tentative assignment (-1 = none)
-    int32_t* dirty;           // [2][ncl] smallest query whose tentative assignment to/from c changed in the last iteration
+    HmkDynEntry* dyn;         // per cluster: final members (join order == query order), then the tentative joiners in query order
+    int32_t* a;               // [ns] tentative assignment (-1 = none)
+    int32_t* dirty;           // [ncl] smallest query whose tentative assignment to/from c changed in the last iteration
     int32_t* stamp;           // [ns] generation in which the query was last put on a work list
     int32_t* work;            // [2][wcap] queries to re-evaluate
     int32_t* chg;             // [2][HMK_P2_CHG] clusters whose tentative joiner list changed in the last iteration
@@ -1802,6 +1801,7 @@ struct HmkP2 {
     int32_t qa, qb;           // window = queries [qa, qb)
     int32_t gen0;             // generation of the window's first iteration (unique across windows)
     int32_t max_iters;
+    unsigned long long* tim;  // optional [64] phase boundaries in ns (profiling builds): start, base, then R / D ends per iteration
 };
 
 // candidate pairs per cluster (cq_c is grouped by query, so neighbours rarely collide)
@@ -1861,13 +1861,10 @@ template <bool FAST>
 __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_t* sM, int qi, int par, long long& npairs) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int32_t* a_cur = P.a + (size_t)par * P.ns;
-    int32_t* a_new = P.a + (size_t)(par ^ 1) * P.ns;
-    int32_t* dirty_nxt = P.dirty + (size_t)(par ^ 1) * P.ncl;
     const int32_t T = P.S.T;
     const int4* cinfo = reinterpret_cast<const int4*>(P.cinfo);
     const int e0 = P.qstart[qi], e1 = P.qstart[qi + 1];
-    const int32_t old = a_cur[qi];
+    const int32_t old = P.a[qi];
     const int32_t q = P.singles[qi];
     const HmkQueryScorer<FAST> scorer(P, sM, q);
     HmkBestCluster best;        // warp-uniform
@@ -1877,7 +1874,7 @@ __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_
         int32_t c = -1, st = HMK_JMIN, cl = HMK_JMIN, off = 0, nd = 0, tn = 0;
         if (e < e1) { cl = P.base_cl[e]; st = P.cq_s[e]; c = P.cq_c[e]; }
         const bool alive = cl != HMK_JMIN && !(best.slot >= 0 && st < best.score);
-        if (alive) { const int4 ci = cinfo[c]; off = ci.x; nd = ci.y; tn = par ? ci.w : ci.z; }
+        if (alive) { const int4 ci = cinfo[c]; off = ci.x; nd = ci.y; tn = ci.z; }
         const int start = nd > 0 ? 1 : 0;             // member 0 of the final members is in base_cl already
         const bool more = alive && nd + tn > start;
         {   // candidates without further members are decided: fold them into the warp's best (prunes the rest)
@@ -1918,7 +1915,7 @@ __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_
                 }
                 const unsigned badm = __ballot_sync(FULL, bad);
                 if (badm) { ok = false; final_fail = __any_sync(FULL, bad && i < pnd); break; }
-                if (__any_sync(FULL, behind)) break;                  // sorted: everything further is behind q as well
+                if (__any_sync(FULL, behind)) break;                  // in query order: everything further is behind q as well
             }
             mn = __reduce_min_sync(FULL, mn);
             sz = __reduce_add_sync(FULL, sz);
@@ -1935,18 +1932,16 @@ __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_
             todo &= ~(1u << pick);
         }
     }
-    if (lane == 0) {
-        a_new[qi] = best.slot;
-        if (best.slot != old) {
-            P.ctl[6 + par] = 1;
-            const int32_t two[2] = {old, best.slot};
-            for (int k = 0; k < 2; k++) {
-                const int32_t c = two[k];
-                if (c < 0) continue;
-                if (atomicMin(dirty_nxt + c, qi) == HMK_P2_CLEAN) {       // first change of this cluster in this iteration
-                    const int pos = atomicAdd(P.ctl + 4 + (par ^ 1), 1);
-                    if (pos < HMK_P2_CHG) P.chg[(size_t)(par ^ 1) * HMK_P2_CHG + pos] = c;
-                }
+    if (lane == 0 && best.slot != old) {
+        P.a[qi] = best.slot;
+        P.ctl[6 + par] = 1;
+        const int32_t two[2] = {old, best.slot};
+        for (int k = 0; k < 2; k++) {
+            const int32_t c = two[k];
+            if (c < 0) continue;
+            if (atomicMin(P.dirty + c, qi) == HMK_P2_CLEAN) {       // first change of this cluster in this iteration
+                const int pos = atomicAdd(P.ctl + 4 + par, 1);
+                if (pos < HMK_P2_CHG) P.chg[(size_t)par * HMK_P2_CHG + pos] = c;
             }
         }
     }
@@ -1955,18 +1950,16 @@ __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_
 
 // ONE cooperative launch resolves one window: setup, base pass, the fixed-point iterations and the commit are phases of
 // the same grid separated by grid-wide barriers, so an iteration that re-evaluates a handful of queries costs a few
-// microseconds instead of three launches and a host round trip.
+// microseconds instead of several launches and a host round trip.
 //   setup   per cluster: nobody joins
 //   base    one thread per candidate pair of the window: fold the FIRST final phase-2 member of the cluster into the
 //           pair's score (HMK_JMIN if it scores < T).  Unrelated candidates -- nearly all of them -- die here.
-//   iteration t (parity t & 1):
-//     A  every window query goes onto the tentative list of the cluster it currently joins and keeps its assignment
-//        by default; the queries that must be re-evaluated -- a candidate cluster changed (tentatively) at a position
-//        before them in iteration t-1 -- are put on the work list: from the clusters' side when few clusters changed
-//        (their candidate lists are sorted by query), else every query gathers dirty[] for its candidates
-//     B  one warp per cluster: rank sort of the tentative joiners into the dyn tail
-//     C  warps take queries off the work list (iteration 0: the whole window) and decide them
-//   until an iteration changes nothing; commit: the tentative joiners become final members, in query order.
+//   iteration t:
+//     R  (t > 0) one warp per cluster whose joiners changed in iteration t-1 walks the cluster's candidate queries of the
+//        window (grouped by cluster, ascending): those currently assigned to it become its tentative joiner list, in
+//        query order; those behind the first change are put on the work list (once: generation stamp)
+//     D  warps take queries off the work list (iteration 0: the whole window) and decide them
+//   until an iteration changes nothing; commit: the tentative joiners become final members.
 template <bool FAST>
 __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
     namespace cg = cooperative_groups;
@@ -1979,18 +1972,16 @@ __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
     const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
     long long npairs = 0;
     // ---- setup + base
-    for (int c = gtid; c < P.ncl; c += gthreads) {
-        P.cinfo[c * HMK_CI + 2] = 0; P.cinfo[c * HMK_CI + 3] = 0;
-        P.dirty[c] = HMK_P2_CLEAN; P.dirty[(size_t)P.ncl + c] = HMK_P2_CLEAN;
-    }
+    for (int c = gtid; c < P.ncl; c += gthreads) { P.cinfo[c * HMK_CI + 2] = 0; P.dirty[c] = HMK_P2_CLEAN; }
     if (gtid < HMK_P2_CTL) P.ctl[gtid] = 0;
     {
         const int e0 = P.qstart[P.qa], e1 = P.qstart[P.qb];
         for (int e = e0 + gtid; e < e1; e += gthreads) {
-            const int4 ci = reinterpret_cast<const int4*>(P.cinfo)[P.cq_c[e]];      // .x / .y only: not touched by the setup
+            const int32_t c = P.cq_c[e];
+            const int32_t nd = P.cinfo[c * HMK_CI + 1];
             int32_t cl = P.cq_s[e];
-            if (ci.y > 0) {                                // the cluster has final phase-2 members
-                const HmkDynEntry m = P.dyn[ci.x];
+            if (nd > 0) {                                  // the cluster has final phase-2 members
+                const HmkDynEntry m = P.dyn[P.cinfo[c * HMK_CI]];
                 const HmkQueryScorer<FAST> scorer(P, sM, P.singles[P.cq_q[e]]);
                 const int32_t s = scorer.score(m);
                 npairs++;
@@ -2000,70 +1991,56 @@ __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
         }
     }
     grid.sync();
+    int tslot = 0;
+    auto mark_time = [&]() {
+        if (P.tim && gtid == 0 && tslot < 64) { unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns)); P.tim[tslot] = ns; }
+        tslot++;
+    };
+    mark_time();
     int t = 0;
     for (;; t++) {
         const int par = t & 1;
-        // ---- A
-        for (int qi = P.qa + gtid; qi < P.qb; qi += gthreads) {
-            const int32_t old = P.a[(size_t)par * P.ns + qi];
-            if (old >= 0) {
-                int32_t* ci = P.cinfo + old * HMK_CI;
-                const int pos = atomicAdd(ci + 2 + par, 1);
-                P.tent[ci[0] + ci[1] + pos] = qi;
-            }
-            P.a[(size_t)(par ^ 1) * P.ns + qi] = old;
-        }
         if (t > 0) {
-            const int32_t* dirty_cur = P.dirty + (size_t)par * P.ncl;
-            const int nchg = P.ctl[4 + par];
+            // ---- R: rebuild the joiner lists of the clusters that changed, and collect the queries behind the changes
+            const int nchg = P.ctl[4 + (par ^ 1)];
             const int32_t gen = P.gen0 + t;
             int32_t* work = P.work + (size_t)par * P.wcap;
-            if (nchg <= HMK_P2_CHG) {
-                for (int k = gwarp; k < nchg; k += gwarps) {
-                    const int32_t c = P.chg[(size_t)par * HMK_P2_CHG + k];
-                    const int32_t from = max(P.qa, dirty_cur[c] + 1);
-                    int lo = P.cstart[c], hi = P.cstart[c + 1];
-                    const int end = hi;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.cc_q[mid] < from) lo = mid + 1; else hi = mid; }
-                    for (int i = lo + lane; i < end; i += 32) {
-                        const int32_t qi = P.cc_q[i];
-                        if (qi >= P.qb) break;
-                        if (atomicMax(P.stamp + qi, gen) < gen) work[atomicAdd(P.ctl + par, 1)] = qi;
+            const bool listed = nchg <= HMK_P2_CHG;
+            const int ncl_it = listed ? nchg : P.ncl;
+            for (int k = gwarp; k < ncl_it; k += gwarps) {
+                const int32_t c = listed ? P.chg[(size_t)(par ^ 1) * HMK_P2_CHG + k] : k;
+                const int32_t dpos = P.dirty[c];
+                if (dpos == HMK_P2_CLEAN) continue;
+                int32_t* ci = P.cinfo + c * HMK_CI;
+                HmkDynEntry* out = P.dyn + ci[0] + ci[1];
+                int lo = P.cstart[c], hi = P.cstart[c + 1];
+                const int end = hi;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.cc_q[mid] < P.qa) lo = mid + 1; else hi = mid; }
+                int n = 0;
+                for (int i0 = lo; i0 < end; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int32_t qi = i < end ? P.cc_q[i] : 0x7fffffff;
+                    const bool inw = qi < P.qb;
+                    const bool joins = inw && P.a[qi] == c;
+                    const unsigned jm = __ballot_sync(FULL, joins);
+                    if (joins) {
+                        const int32_t id = P.singles[qi];
+                        HmkDynEntry en;
+                        en.w = P.packed ? P.packed[id] : 0ull; en.qi = qi; en.ab = P.S.ab[id];
+                        out[n + __popc(jm & ((1u << lane) - 1u))] = en;
                     }
+                    n += __popc(jm);
+                    if (inw && qi > dpos && atomicMax(P.stamp + qi, gen) < gen) work[atomicAdd(P.ctl + par, 1)] = qi;
+                    if (!__all_sync(FULL, inw)) break;
                 }
-            } else {
-                for (int qi = P.qa + gwarp; qi < P.qb; qi += gwarps) {
-                    bool dirty = false;
-                    const int e1 = P.qstart[qi + 1];
-                    for (int e = P.qstart[qi] + lane; e < e1; e += 32) dirty |= dirty_cur[P.cq_c[e]] < qi;
-                    if (__any_sync(FULL, dirty) && lane == 0) work[atomicAdd(P.ctl + par, 1)] = qi;
-                }
+                __syncwarp();
+                if (lane == 0) { ci[2] = n; P.dirty[c] = HMK_P2_CLEAN; }
             }
+            if (gtid == 0) { P.ctl[4 + par] = 0; P.ctl[6 + par] = 0; P.ctl[2 + par] = 0; P.ctl[par ^ 1] = 0; }
+            grid.sync();
+            mark_time();
         }
-        grid.sync();
-        // ---- B
-        for (int c = gwarp; c < P.ncl; c += gwarps) {
-            int32_t* ci = P.cinfo + c * HMK_CI;
-            const int n = ci[2 + par];
-            const int base = ci[0] + ci[1];
-            __syncwarp();
-            if (lane == 0) { ci[2 + (par ^ 1)] = 0; P.dirty[(size_t)(par ^ 1) * P.ncl + c] = HMK_P2_CLEAN; }
-            if (n == 0) continue;
-            const int32_t* tl = P.tent + base;
-            HmkDynEntry* o = P.dyn + base;
-            for (int i = lane; i < n; i += 32) {
-                const int32_t v = tl[i];
-                int r = 0;
-                for (int j = 0; j < n; j++) r += tl[j] < v;
-                const int32_t id = P.singles[v];
-                HmkDynEntry en;
-                en.w = P.packed ? P.packed[id] : 0ull; en.qi = v; en.ab = P.S.ab[id];
-                o[r] = en;
-            }
-        }
-        if (gtid == 0) { P.ctl[par ^ 1] = 0; P.ctl[2 + (par ^ 1)] = 0; P.ctl[4 + (par ^ 1)] = 0; P.ctl[6 + (par ^ 1)] = 0; }
-        grid.sync();
-        // ---- C
+        // ---- D
         {
             const int nwork = t == 0 ? P.qb - P.qa : P.ctl[par];
             const int32_t* work = P.work + (size_t)par * P.wcap;
@@ -2078,28 +2055,27 @@ __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
             }
         }
         grid.sync();
+        mark_time();
+        if (gtid == 0 && P.tim && tslot < 62) { P.tim[62] = (unsigned long long)(t == 0 ? P.qb - P.qa : P.ctl[par]); }
         if (!P.ctl[6 + par] || t + 1 >= P.max_iters) break;
     }
-    // ---- commit (parity of the last iteration: its tentative lists are the final joiners)
-    {
-        const int par = t & 1;
-        for (int c = gtid; c < P.ncl; c += gthreads) {
-            int32_t* ci = P.cinfo + c * HMK_CI;
-            const int n = ci[2 + par];
-            if (n == 0) continue;
-            const int32_t nd = ci[1];
-            int32_t cnt = P.S.c_count[c], size = P.S.c_size[c];
-            const HmkDynEntry* tl = P.dyn + ci[0] + nd;
-            for (int i = 0; i < n; i++) {
-                const int32_t q = P.singles[tl[i].qi];
-                P.S.rank[q] = cnt++;
-                size = hmk_wadd(size, tl[i].ab);
-                P.S.slot[q] = c;
-            }
-            ci[1] = nd + n; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
+    // ---- commit: the tentative lists (rebuilt in R of the last iteration, unchanged since) are the final joiners
+    for (int c = gtid; c < P.ncl; c += gthreads) {
+        int32_t* ci = P.cinfo + c * HMK_CI;
+        const int n = ci[2];
+        if (n == 0) continue;
+        const int32_t nd = ci[1];
+        int32_t cnt = P.S.c_count[c], size = P.S.c_size[c];
+        const HmkDynEntry* tl = P.dyn + ci[0] + nd;
+        for (int i = 0; i < n; i++) {
+            const int32_t q = P.singles[tl[i].qi];
+            P.S.rank[q] = cnt++;
+            size = hmk_wadd(size, tl[i].ab);
+            P.S.slot[q] = c;
         }
-        if (gtid == 0) P.ctl[8] = t + 1;
+        ci[1] = nd + n; P.S.c_count[c] = cnt; P.S.c_size[c] = size;
     }
+    if (gtid == 0) P.ctl[8] = t + 1;
     for (int s = 16; s > 0; s >>= 1) npairs += __shfl_xor_sync(FULL, npairs, s);
     if (lane == 0) hmk_count_pairs(P.pair_parts, npairs);
 }
@@ -2186,6 +2162,16 @@ __global__ void hmk_segment_starts(const unsigned long long* __restrict__ keys, 
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if ((int64_t)(keys[mid] >> shift) < (int64_t)s) lo = mid + 1; else hi = mid;
+    }
+    start[s] = lo;
+}
+__global__ void hmk_segment_starts_i32(const int32_t* __restrict__ keys, int n, int nseg, int32_t* __restrict__ start) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nseg) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (keys[mid] < s) lo = mid + 1; else hi = mid;
     }
     start[s] = lo;
 }

@@ -148,6 +148,7 @@ int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n);
  *              symmetric (default), 0 = always run the separate founder pass
  *   qt, waves  profiles per shared-memory tile (0 = as many as fit), grid waves per launch
  *   p2_chunk, p2_window, hit_cap   phase-2 chunking / window size / initial hit-buffer size
+ *   p2_first   queries in the first phase-2 window (0 = automatic; later windows grow towards p2_window)
  *   xhit_cap   entries of the buffer that keeps the phase-1 hits for phase 2 (0 = automatic: what the last run on this
  *              context needed, else 96 per sequence); an overflow is reported in hmk_stats.flags
  *   force_generic  1 = scalar kernel for everything (correctness path)
