@@ -135,6 +135,7 @@ struct SmemConfig {
     }
 };
 
+enum { HMK_MAXTILES_PERSISTENT = 1024 };   // profile tiles a persistent bulk launch schedules (more: static grid)
 enum { HMK_NBATCHBUF = 3 };   // the batch being resolved + up to two prepared ahead
 enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_RESOLVE, SEC_P2_SETUP, SEC_P2_FILTER,
        SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
@@ -153,6 +154,8 @@ struct Options {
     int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
     int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
+    int64_t reserve = 4;          // SMs the look-ahead bulk launches leave to the main stream (resolver + small kernels)
+    int64_t persistent = 1;       // 1: filter kernel as one CTA per SM taking database chunks dynamically; 0: static grid
     int64_t p2_first = 0;         // queries in the first phase-2 window (0 = automatic)
     int64_t xhit_cap = 0;         // capacity of the kept-hit buffer (0 = automatic: the last run's need, else 96 per sequence)
 };
@@ -271,6 +274,12 @@ private:
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
         DevBuf<unsigned long long> gmin;   // per query: published lower bound of the kb-th best key (prunes top-k insertions)
         DevBuf<uint32_t> prof;
+        DevBuf<int32_t> sched, sched2;   // chunk / slot counters of the persistent partner-search / cluster-search launches
+        // cluster search, part 1: founder hits of the clusters that existed when the batch was prepared
+        DevBuf<int4> hits;
+        DevBuf<unsigned int> hcount;     // [0] founder hits (may exceed hit_cap: the resolver then asks for a bigger buffer)
+        size_t hit_cap = 0;
+        int ncl_ahead = 0;               // clusters [0, ncl_ahead) are covered by part 1
         DevBuf<uint32_t> prof_len[HMK_MAXLEN + 1], pcells[HMK_MAXLEN + 1], pops[HMK_MAXLEN + 1];   // mixed lengths: per thread-side length
         // state-independent inputs of the resolver: intra-batch scores (+ bit mask), partner candidate ids and
         // their scores against every batch query
@@ -283,11 +292,14 @@ private:
     };
     BatchBuf bb_[HMK_NBATCHBUF];
     cudaStream_t st2_ = nullptr;
-    void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s);
+    void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, int ncl_known, cudaStream_t s);
+    void founder_hits(BatchBuf& bb, int from, int to, cudaStream_t s, DevBuf<int32_t>& sched);
+    size_t hit_cap_ = 0;
     // ---- phase-1 scratch
     DevBuf<int32_t> d_qid_, d_nq_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_;
     DevBuf<int4> d_ac_full_, d_ac_best_;
+    DevBuf<int32_t> d_sched_;
     // phase-1 partner-search hits kept for phase 2 (opt.reuse): buffer, 64-bit counters [0] appended, [1] valid
     DevBuf<int4> d_xhits_;
     DevBuf<unsigned long long> d_xcount_;
@@ -337,10 +349,10 @@ private:
     HmkScheme scheme_for(int n) const;
     void launch_profiles(int mode, const int32_t* ids, int nq, uint32_t* prof, const HmkScheme& sc, cudaStream_t s,
                          uint32_t* cells = nullptr, uint32_t* ops = nullptr);
-    void plan_bulk(HmkBulkArgs& a, const HmkScheme* sch) const;
+    void plan_bulk(HmkBulkArgs& a, const HmkScheme* sch, int32_t* sched = nullptr) const;
     void launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const int32_t* prof_ids, int prof_is_query, cudaStream_t s);
     void launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s = nullptr,
-                     BatchBuf* bb = nullptr);
+                     BatchBuf* bb = nullptr, DevBuf<int32_t>* sched_buf = nullptr);
     cudaEvent_t next_event();
     // per-section device timers (only with opt.profile)
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> sections_;
@@ -544,7 +556,7 @@ int Engine::qt_max(const HmkScheme& sc) const {
     if (opt.qt > 0) return (int)opt.qt;
     const size_t pwb = (size_t)sc.prof_words * 4;
     const size_t per = pwb + (size_t)opt.kb * 8 + 8 + 12;
-    const size_t fixed = 64 + (HMK_BULK_THREADS / 32) * HMK_QCAP * 8 + (sc.filter ? 16 + (HMK_BULK_THREADS / 32) * HMK_CQCAP * 12 : 0);
+    const size_t fixed = 128 + (HMK_BULK_THREADS / 32) * HMK_QCAP * 8 + (sc.filter ? 16 + (HMK_BULK_THREADS / 32) * HMK_CQCAP * 12 : 0);
     return (int)std::min<size_t>(255, std::max<size_t>(1, (smem_optin_ - fixed) / per));
 }
 
@@ -615,12 +627,27 @@ static void launch_generic_mode(SmemConfig& cfg, const HmkGenericArgs& g, int gr
 // tiling of a bulk launch: nqt profile tiles x nstripes database stripes; the grid is an exact
 // multiple of the SM count whenever the database is large enough (one CTA per SM is resident:
 // the profile tile fills shared memory)
-void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch) const {
+void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch, int32_t* sched) const {
     const int threads = sch ? (sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS) : HMK_GENERIC_THREADS;
     const int qmax = sch ? qt_max(*sch) : 128;
     const int sms = plan_sms_ > 0 ? plan_sms_ : sm_count_;
     a.nqt = (a.nq + qmax - 1) / qmax;
     a.qt = (a.nq + a.nqt - 1) / a.nqt;
+    a.sched = nullptr; a.nchunks = 0;
+    if (sched && opt.persistent && sch && sch->filter && a.nqt <= HMK_MAXTILES_PERSISTENT) {
+        // filter kernel, persistent form: one CTA per SM, dynamic chunks (about 8 per CTA and tile, a multiple of the
+        // block size) -- no tail wave, and a CTA loads a profile tile once instead of once per stripe
+        const int64_t units = (int64_t)a.nqt * ((a.ndb + threads - 1) / threads);
+        const int G = (int)std::max<int64_t>(1, std::min<int64_t>(sms, units));
+        const int per_tile = std::max(1, G / a.nqt);
+        int chunk = (a.ndb / (per_tile * 8) + threads - 1) / threads * threads;
+        chunk = std::max(threads, std::min(chunk, 8 * threads));
+        a.chunk = chunk;
+        a.nchunks = (a.ndb + chunk - 1) / chunk;
+        a.nstripes = G;           // output slots per query: a CTA engages a tile at most once
+        a.sched = sched;
+        return;
+    }
     int want = (int)((sms * opt.waves + a.nqt - 1) / a.nqt);
     if (a.nqt <= sms * opt.waves && (sms * opt.waves) % a.nqt != 0) {
         // nqt does not divide waves*SMs: round the total up to the next multiple of the SM count
@@ -651,7 +678,8 @@ void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const
     a.sc = sch ? *sch : sc_;
     a.pair_counter = d_pairctr_.p;
     a.kb = (int)opt.kb;
-    const int grid = a.nqt * a.nstripes;
+    const int grid = a.sched ? a.nstripes : a.nqt * a.nstripes;
+    if (a.sched) CK(cudaMemsetAsync(a.sched, 0, sizeof(int32_t) * 2 * a.nqt, s));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (opt.profile) { e0 = next_event(); e1 = next_event(); CK(cudaEventRecord(e0, s)); }
     if (sch) {
@@ -679,11 +707,14 @@ void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const
 
 // one-launch convenience for everything that is not a (possibly multi-bucket) partner search:
 // the uniform packed kernel when the whole input has one length <= 12, else the generic kernel
-void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s, BatchBuf* bb) {
+void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int prof_is_query, cudaStream_t s, BatchBuf* bb,
+                         DevBuf<int32_t>* sched_buf) {
     if (a.nq <= 0 || a.ndb <= 0) return;
     if (!s) s = st_;
     const HmkScheme* sch = fast_ ? &sc_ : nullptr;
-    plan_bulk(a, sch);
+    DevBuf<int32_t>& sched = sched_buf ? *sched_buf : (bb ? bb->sched : d_sched_);      // launches on different streams overlap: one each
+    sched.reserve(2 * HMK_MAXTILES_PERSISTENT);
+    plan_bulk(a, sch, mode == HMK_MODE_DENSE ? nullptr : sched.p);
     if (mode == HMK_MODE_TOPK) {
         const size_t slots = (size_t)a.nstripes * a.nq;
         bb->tk_key.reserve(slots * opt.kb); bb->tk_cnt.reserve(slots); bb->tk_ovf.reserve(slots);
@@ -693,7 +724,8 @@ void Engine::launch_bulk(int mode, HmkBulkArgs a, const int32_t* prof_ids, int p
     launch_planned(mode, a, sch, prof_ids, prof_is_query, s);
     if (mode == HMK_MODE_TOPK) {
         hmk_topk_merge<<<(a.nq * 32 + 255) / 256, 256, 0, s>>>(a.nq, a.nstripes, (int)opt.kb, bb->tk_key.p, bb->tk_cnt.p,
-                                                               bb->tk_ovf.p, bb->bk_key.p, bb->bk_cnt.p, bb->bk_ovf.p);
+                                                               bb->tk_ovf.p, bb->bk_key.p, bb->bk_cnt.p, bb->bk_ovf.p,
+                                                               a.sched ? a.sched + a.nqt : nullptr, a.qt);
         CK(cudaGetLastError());
         launches_++;
     }
@@ -728,7 +760,17 @@ void Engine::sort_pairs(unsigned long long* keys, int32_t* vals, int n, int begi
 // ---------------------------------------------------------------- phase 1
 // select the next batch, build its query profiles and run the partner search (+ the multi-GPU
 // best-hit exchange) on stream `s`; bb.ready fires when the merged lists are in bb.bk_*
-void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, cudaStream_t s) {
+// founder filter of the cluster search for the clusters [from, to): appends (query index, founder id, score) to bb.hits
+void Engine::founder_hits(BatchBuf& bb, int from, int to, cudaStream_t s, DevBuf<int32_t>& sched) {
+    if (to <= from) return;
+    HmkBulkArgs a{};
+    a.prof = bb.prof.p; a.nq = bb.nq;
+    a.packed = d_packed_.p; a.db_ids = d_cf_.p + from; a.db_begin = 0; a.ndb = to - from;
+    a.hits = bb.hits.p; a.hit_count = bb.hcount.p; a.hit_cap = (unsigned int)bb.hit_cap;
+    launch_bulk(HMK_MODE_EMIT, a, bb.qid.p, 1, s, nullptr, &sched);
+}
+
+void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, int ncl_known, cudaStream_t s) {
     const int kb = (int)opt.kb;
     bb.qid.reserve(HMK_MAXBATCH); bb.nq_dev.reserve(1);
     bb.bk_key.reserve((size_t)HMK_MAXBATCH * kb); bb.bk_cnt.reserve(HMK_MAXBATCH); bb.bk_ovf.reserve(HMK_MAXBATCH);
@@ -842,9 +884,17 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         launch_bulk(HMK_MODE_DENSE, d, bb.qid.p, 1, s);
     }
     CK(cudaGetLastError());
+    // cluster search, part 1 (state independent as well: founders never change): the clusters that exist now.  The ones
+    // created until the batch is resolved are added on the main stream (phase1)
+    bb.nq = nq;
+    bb.hit_cap = hit_cap_;
+    bb.hits.reserve(bb.hit_cap); bb.hcount.reserve(4);
+    bb.sched2.reserve(2 * HMK_MAXTILES_PERSISTENT);
+    CK(cudaMemsetAsync(bb.hcount.p, 0, 4 * sizeof(unsigned int), s));
+    bb.ncl_ahead = ncl_known;
+    founder_hits(bb, 0, ncl_known, s, bb.sched2);
     CK(cudaEventRecord(bb.ready, s));
     bb.valid = true;
-    bb.nq = nq;
 }
 
 int Engine::phase1() {
@@ -874,36 +924,38 @@ int Engine::phase1() {
         CK(cudaMemsetAsync(d_xcount_.p, 0, 2 * sizeof(unsigned long long), st_));
         CK(cudaMemsetAsync(d_qbatch_.p, 0xff, sizeof(int32_t) * n_, st_));
     }
-    size_t hit_cap = (size_t)opt.hit_cap;
-    d_hits_.reserve(hit_cap);
+    hit_cap_ = (size_t)opt.hit_cap;
     for (auto& b : bb_) b.valid = false;
     const int depth = (int)std::max<int64_t>(0, std::min<int64_t>(opt.lookahead, HMK_NBATCHBUF - 1));
+    // SMs the side stream's bulk launches leave alone while the main stream works on a batch: one for the resolver,
+    // the others for the small kernels around it (new founders, member check), which then never wait for a CTA of a
+    // millisecond-long partner search to finish
+    const int reserve = depth > 0 ? (int)std::max<int64_t>(1, std::min<int64_t>(opt.reserve, sm_count_ / 2)) : 0;
     int head = 0;
     fetch_ctl();
     while (h_ctl_->ncl < K_ && h_ctl_->unproc_alive > 0) {
         BatchBuf& cb = bb_[head];
         const int cur = h_ctl_->cur, ncl = h_ctl_->ncl;
         sec(SEC_P1_PARTNER);
-        if (!cb.valid) stage_partner_search(cb, std::min(B, h_ctl_->unproc_alive), cur, nullptr, st_);   // not prepared ahead
+        if (!cb.valid) stage_partner_search(cb, std::min(B, h_ctl_->unproc_alive), cur, nullptr, ncl, st_);   // not prepared ahead
         else CK(cudaStreamWaitEvent(st_, cb.ready, 0));
         const int nq = cb.nq;
         const int32_t* d_qid = cb.qid.p;
-        const uint32_t* d_prof = cb.prof.p;
-        // A: clusters whose founder scores >= T, then complete linkage over their members
+        // A: clusters whose founder scores >= T (part 1 came with the batch; part 2 = the clusters created since), then
+        // complete linkage over their members
         sec(SEC_P1_CLUSTER);
-        CK(cudaMemsetAsync(d_counts_.p, 0, 4 * sizeof(unsigned int), st_));
         CK(cudaMemsetAsync(d_ac_cnt_.p, 0, sizeof(int32_t) * nq, st_));
         if (ncl > 0) {
-            HmkBulkArgs a{};
-            a.prof = d_prof; a.nq = nq;
-            a.packed = d_packed_.p; a.db_ids = d_cf_.p; a.db_begin = 0; a.ndb = ncl;
-            a.hits = d_hits_.p; a.hit_count = d_counts_.p; a.hit_cap = (unsigned int)hit_cap;
-            launch_bulk(HMK_MODE_EMIT, a, d_qid, 1);
+            if (ncl > cb.ncl_ahead) {
+                plan_sms_ = reserve > 1 ? reserve - 1 : 0;      // while a prepared partner search holds the other SMs
+                founder_hits(cb, cb.ncl_ahead, ncl, st_, d_sched_);
+                plan_sms_ = 0;
+            }
             HmkCheckArgs c{};
-            c.S = state(); c.hits = d_hits_.p; c.hit_count = d_counts_.p; c.hit_cap = (unsigned int)hit_cap;
+            c.S = state(); c.hits = cb.hits.p; c.hit_count = cb.hcount.p; c.hit_cap = (unsigned int)cb.hit_cap;
             c.hit_t_is_query = 1; c.qids = d_qid; c.sidx = nullptr;
             c.ac_cnt = d_ac_cnt_.p; c.ac_slot = d_ac_slot_.p; c.ac_score = d_ac_score_.p; c.capq = (int32_t)capq;
-            c.cand_count = d_counts_.p + 1; c.cand_cap = 0; c.linked = 1;
+            c.cand_count = cb.hcount.p + 1; c.cand_cap = 0; c.linked = 1;
             c.packed = fast_scalar_ ? d_packed_.p : nullptr; c.L = max_len_; c.pair_parts = d_pairparts_.p;
             if (scalar12x3()) hmk_member_check<true><<<sm_count_ * 2, 256, 0, st_>>>(c);
             else hmk_member_check<false><<<sm_count_ * 2, 256, 0, st_>>>(c);
@@ -920,7 +972,7 @@ int Engine::phase1() {
         pb.bk_key = cb.bk_key.p; pb.bk_cnt = cb.bk_cnt.p; pb.bk_ovf = cb.bk_ovf.p;
         pb.capq = (int32_t)capq; pb.ac_cnt = d_ac_cnt_.p; pb.ac_slot = d_ac_slot_.p; pb.ac_score = d_ac_score_.p;
         pb.ac_full = d_ac_full_.p; pb.best = d_ac_best_.p;
-        pb.hit_count = d_counts_.p; pb.hit_cap = (unsigned int)hit_cap;   // truncated hit lists: the resolver returns HMK_P1_GROWHITS
+        pb.hit_count = cb.hcount.p; pb.hit_cap = (unsigned int)cb.hit_cap;   // truncated hit lists: the resolver returns HMK_P1_GROWHITS
         pb.ib = cb.ib.p; pb.ib_stride = ib_stride; pb.ibm = cb.ibm.p; pb.ibm2 = cb.ibm2.p; pb.nw = nw;
         pb.pcand = cb.pcand.p;
         pb.pd = cb.pd.p; pb.pd_stride = pd_stride;
@@ -945,9 +997,9 @@ int Engine::phase1() {
             BatchBuf& nb = bb_[(head + d) % HMK_NBATCHBUF];
             if (nb.valid) continue;
             if (!prev.valid || prev.nq != B || h_ctl_->unproc_alive < nq + (2 + d) * B) break;
-            plan_sms_ = sm_count_ - 1;
+            plan_sms_ = sm_count_ - reserve;
             CK(cudaStreamWaitEvent(st2_, prev.ready, 0));      // prev.qid is written on the stream that staged prev
-            stage_partner_search(nb, B, cur, prev.qid.p + (prev.nq - 1), st2_);
+            stage_partner_search(nb, B, cur, prev.qid.p + (prev.nq - 1), ncl, st2_);
             plan_sms_ = 0;
         }
         sec(-1);
@@ -959,8 +1011,11 @@ int Engine::phase1() {
                     h_ctl_->unproc_alive, st, h_ctl_->steps);
 #endif
         if (st == HMK_P1_GROWHITS) {   // the state is untouched: redo the cluster search of this batch with a bigger buffer
-            hit_cap = (size_t)(uint32_t)h_ctl_->pad0 * 5 / 4 + 1024;
-            d_hits_.reserve(hit_cap);
+            hit_cap_ = std::max(hit_cap_, (size_t)(uint32_t)h_ctl_->pad0 * 5 / 4 + 1024);
+            cb.hit_cap = hit_cap_;
+            cb.hits.reserve(cb.hit_cap);
+            CK(cudaMemsetAsync(cb.hcount.p, 0, 4 * sizeof(unsigned int), st_));
+            cb.ncl_ahead = 0;           // every founder again, on the main stream
             h_ctl_->status = HMK_P1_CONTINUE;
             continue;       // cb (and the batches prepared behind it) stay valid
         }
@@ -1620,6 +1675,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
         {"force_generic", &o.force_generic, 0, 1},  {"profile", &o.profile, 0, 1},
         {"p2_window", &o.p2_window, 1, 1 << 24},
         {"xhit_cap", &o.xhit_cap, 0, (int64_t)1 << 30}, {"p2_first", &o.p2_first, 0, 1 << 24},
+        {"persistent", &o.persistent, 0, 1},        {"reserve", &o.reserve, 1, 64},
     };
     for (const Knob& k : knobs) {
         if (s != k.name) continue;

@@ -211,6 +211,11 @@ struct HmkBulkArgs {
     unsigned long long* pair_counter;   // [0] pairs, [1] cells, [2] int ops (the last two only with prof_cells)
     const uint32_t* prof_cells;         // per profile: cells of one pair against this launch's thread-side length
     const uint32_t* prof_ops;
+    // persistent mode (hmk_bulk_filter): one CTA per SM, the database is cut into nchunks chunks of `chunk` items per
+    // profile tile and CTAs take chunks dynamically -- sched[t] = next chunk of tile t, sched[nqt + t] = output slots
+    // (CTA x tile engagements) handed out for tile t; nstripes = slots per query in tk_* (>= CTAs)
+    int32_t* sched;
+    int32_t nchunks;
 };
 
 // ---------------------------------------------------------------- hit handling
@@ -379,7 +384,7 @@ __device__ __forceinline__ int32_t hmk_lane_max(const uint32_t* acc, int nw, int
 __device__ __forceinline__ void hmk_topk_init(const HmkTopkSmem& tk, int qn, int kb) {
     for (int i = threadIdx.x; i < qn; i += blockDim.x) { tk.cnt[i] = 0; tk.lock[i] = 0; tk.ovf[i] = 0; tk.minkey[i] = 0; }
 }
-__device__ __forceinline__ void hmk_topk_flush(const HmkBulkArgs& a, const HmkTopkSmem& tk, int q0, int qn, int stripe) {
+__device__ __forceinline__ void hmk_topk_flush(const HmkBulkArgs& a, const HmkTopkSmem& tk, int q0, int qn, int stripe) {   // stripe = output slot
     for (int t = threadIdx.x; t < qn; t += blockDim.x) {
         uint64_t* k = tk.key + (size_t)t * a.kb;
         int c = tk.cnt[t];
@@ -547,10 +552,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t PWB = HMK_FPW * 4;
     constexpr uint32_t SUB = HMK_MAXL1 * HMK_ROWB;   // bytes of one sub-table
-    const int qtile = blockIdx.x % a.nqt, stripe = blockIdx.x / a.nqt;
-    const int q0 = qtile * a.qt;
-    const int qn = min(a.qt, a.nq - q0);
-    if (qn <= 0) return;
+    __shared__ int s_next[3];                         // persistent mode: (tile, chunk, output slot) of the next piece of work
     const int L = LT ? LT : a.sc.L;
     size_t o = ((size_t)a.qt * PWB + 15) & ~(size_t)15;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + o);
@@ -566,31 +568,20 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
     int ccnt = 0;   // warp-uniform
 
     if (threadIdx.x == 0) hmk_mbar_init(bar, 1);
-    if (MODE == HMK_MODE_TOPK) hmk_topk_init(tk, qn, a.kb);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t total = (uint32_t)qn * PWB;
-        hmk_mbar_expect_tx(bar, total);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.prof) + (size_t)q0 * PWB;
-        uint32_t done = 0;
-        while (done < total) {
-            uint32_t n = min(total - done, 32768u);
-            hmk_bulk_g2s(smem_raw + done, src + done, n, bar);
-            done += n;
-        }
-    }
-    hmk_mbar_wait(bar, 0);
 
-    const int i_begin = stripe * a.chunk;
-    const int i_end = min(a.ndb, i_begin + a.chunk);
     unsigned long long scored = 0;
     const int32_t dec = a.sc.T - a.sc.half;
     const unsigned char* sbase = smem_raw;
     const int lane = threadIdx.x & 31;
     const unsigned ltmask = (1u << lane) - 1u;
+    const bool persistent = a.sched != nullptr;
+    int cur_tile = -1, slot = 0, q0 = 0, qn = 0, home = blockIdx.x % a.nqt;
+    uint32_t bar_phase = 0;
+    int i_begin = 0, i_end = 0;
 
     // exact re-scoring of up to 32 queued candidates, one per lane.  entry: bits 24..31 = t, bit 7 / bit 23 =
-    // "a filter byte of exact word 0 / word 1 passed", the other 22 bits = offset in the stripe.  Only the
+    // "a filter byte of exact word 0 / word 1 passed", the other 22 bits = offset in the chunk.  Only the
     // exact word(s) whose filter bytes passed are summed (both: rare, handled in a divergent tail)
     auto verify = [&]() {
         const int n = ccnt < 32 ? ccnt : 32, base = ccnt - n;
@@ -619,69 +610,128 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
         hmk_queue_push<MODE>(a, tk, q0, hq, hit, t, hit ? (int32_t)m1 + dec : 0, i);
     };
 
-    for (int ib = i_begin + (threadIdx.x & ~31); ib < i_end; ib += blockDim.x) {
-        const int i = ib + lane;
-        bool valid = i < i_end;
-        const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
-        if (valid && a.slot && a.slot[id] >= 0) valid = false;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        const uint64_t w = valid ? a.packed[id] : 0ull;
-        const unsigned char* rowp[HMK_MAXL1];   // &filter[0][j][residue_j]
-#pragma unroll
-        for (int j = 0; j < HMK_MAXL1; j++)
-            rowp[j] = sbase + 2 * SUB + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u;
-        if (valid) scored += qn;
-        const uint32_t ilocal = (uint32_t)(i - i_begin);
-        uint32_t tI = (ilocal & 0x7fu) | ((ilocal >> 7) << 8);
+    for (;;) {
+        // ---- next piece of work: (tile, chunk).  Static mode: exactly one, named by the block index.  Persistent mode:
+        // chunks of the home tile first; when it runs dry, the CTA moves on to the next tile that still has chunks left
+        int tile, chunk_idx;
+        if (!persistent) {
+            if (cur_tile >= 0) break;
+            tile = blockIdx.x % a.nqt; chunk_idx = blockIdx.x / a.nqt;
+            slot = chunk_idx;
+        } else {
+            __syncthreads();            // everybody is done with s_next (and with the previous chunk)
+            if (threadIdx.x == 0) {
+                int t = home, ch = atomicAdd(a.sched + t, 1);
+                for (int k = 1; ch >= a.nchunks && k < a.nqt; k++) {
+                    t = (home + k) % a.nqt;
+                    ch = __ldcg(a.sched + t) < a.nchunks ? atomicAdd(a.sched + t, 1) : a.nchunks;
+                }
+                if (ch >= a.nchunks) t = -1;
+                else if (t != cur_tile) s_next[2] = atomicAdd(a.sched + a.nqt + t, 1);
+                s_next[0] = t; s_next[1] = ch;
+            }
+            __syncthreads();
+            tile = s_next[0]; chunk_idx = s_next[1];
+            if (tile < 0) break;
+        }
+        if (tile != cur_tile) {
+            if (cur_tile >= 0) {        // leave the previous tile: everything queued belongs to it
+                while (ccnt > 0) verify();
+                if (hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
+                if (MODE == HMK_MODE_TOPK) { __syncthreads(); hmk_topk_flush(a, tk, q0, qn, slot); }
+                __syncthreads();
+            }
+            if (persistent) { slot = s_next[2]; home = tile; }
+            cur_tile = tile;
+            q0 = tile * a.qt;
+            qn = min(a.qt, a.nq - q0);
+            if (qn <= 0) { if (persistent) continue; else return; }
+            // ---- stage the profile tile with the TMA bulk-copy engine
+            if (MODE == HMK_MODE_TOPK) hmk_topk_init(tk, qn, a.kb);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint32_t total = (uint32_t)qn * PWB;
+                hmk_mbar_expect_tx(bar, total);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.prof) + (size_t)q0 * PWB;
+                uint32_t done = 0;
+                while (done < total) {
+                    uint32_t n = min(total - done, 32768u);
+                    hmk_bulk_g2s(smem_raw + done, src + done, n, bar);
+                    done += n;
+                }
+            }
+            hmk_mbar_wait(bar, bar_phase);
+            bar_phase ^= 1u;
+        }
+        i_begin = chunk_idx * a.chunk;
+        i_end = min(a.ndb, i_begin + a.chunk);
 
-        auto bound = [&](const int tu) -> uint32_t {
-            uint32_t f = 0;
+        for (int ib = i_begin + (threadIdx.x & ~31); ib < i_end; ib += blockDim.x) {
+            const int i = ib + lane;
+            bool valid = i < i_end;
+            const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
+            if (valid && a.slot && a.slot[id] >= 0) valid = false;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            const uint64_t w = valid ? a.packed[id] : 0ull;
+            const unsigned char* rowp[HMK_MAXL1];   // &filter[0][j][residue_j]
 #pragma unroll
             for (int j = 0; j < HMK_MAXL1; j++)
-                if (j < L) f += *reinterpret_cast<const uint32_t*>(rowp[j] + tu * PWB);
-            return f;
-        };
-        auto enqueue = [&](const uint32_t tu, const uint32_t f) {
-            // lanes without an item look up residue 0 (same row as everybody else: no bank conflict) and are masked here
-            const uint32_t top = valid ? f & 0x80808080u : 0u;
-            const unsigned m = __ballot_sync(0xffffffffu, top != 0);
-            if (m) {
-                if (top) {
-                    const int slot = ccnt + __popc(m & ltmask);
-                    cq[slot] = (tI + (tu << 24)) | ((top | (top >> 8)) & 0x00800080u);
-                    cqw[slot] = w;
-                }
-                ccnt += __popc(m);
-                __syncwarp();
-                if (ccnt >= 32) verify();
-            }
-        };
+                rowp[j] = sbase + 2 * SUB + j * HMK_ROWB + (uint32_t)((w >> (5 * j)) & 31u) * 4u;
+            if (valid) scored += qn;
+            const uint32_t ilocal = (uint32_t)(i - i_begin);
+            uint32_t tI = (ilocal & 0x7fu) | ((ilocal >> 7) << 8);
 
-        int t = 0;
-        for (; t + 4 <= qn; t += 4) {
-            const uint32_t f0 = bound(0), f1 = bound(1), f2 = bound(2), f3 = bound(3);
-            enqueue(0, f0); enqueue(1, f1); enqueue(2, f2); enqueue(3, f3);
-            tI += 4u << 24;
+            auto bound = [&](const int tu) -> uint32_t {
+                uint32_t f = 0;
 #pragma unroll
-            for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += 4 * PWB;
+                for (int j = 0; j < HMK_MAXL1; j++)
+                    if (j < L) f += *reinterpret_cast<const uint32_t*>(rowp[j] + tu * PWB);
+                return f;
+            };
+            auto enqueue = [&](const uint32_t tu, const uint32_t f) {
+                // lanes without an item look up residue 0 (same row as everybody else: no bank conflict) and are masked here
+                const uint32_t top = valid ? f & 0x80808080u : 0u;
+                const unsigned m = __ballot_sync(0xffffffffu, top != 0);
+                if (m) {
+                    if (top) {
+                        const int sl = ccnt + __popc(m & ltmask);
+                        cq[sl] = (tI + (tu << 24)) | ((top | (top >> 8)) & 0x00800080u);
+                        cqw[sl] = w;
+                    }
+                    ccnt += __popc(m);
+                    __syncwarp();
+                    if (ccnt >= 32) verify();
+                }
+            };
+
+            int t = 0;
+            for (; t + 4 <= qn; t += 4) {
+                const uint32_t f0 = bound(0), f1 = bound(1), f2 = bound(2), f3 = bound(3);
+                enqueue(0, f0); enqueue(1, f1); enqueue(2, f2); enqueue(3, f3);
+                tI += 4u << 24;
+#pragma unroll
+                for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += 4 * PWB;
+            }
+            for (; t < qn; t++) {
+                const uint32_t f0 = bound(0);
+                enqueue(0, f0);
+                tI += 1u << 24;
+#pragma unroll
+                for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += PWB;
+            }
         }
-        for (; t < qn; t++) {
-            const uint32_t f0 = bound(0);
-            enqueue(0, f0);
-            tI += 1u << 24;
-#pragma unroll
-            for (int j = 0; j < HMK_MAXL1; j++) rowp[j] += PWB;
+        while (ccnt > 0) verify();      // the queued offsets are relative to this chunk
+    }
+    if (cur_tile >= 0 && qn > 0) {
+        if (hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
+        if (MODE == HMK_MODE_TOPK) {
+            __syncthreads();
+            hmk_topk_flush(a, tk, q0, qn, slot);
         }
     }
-    while (ccnt > 0) verify();
-    if (hq.cnt) hmk_queue_drain<MODE>(a, tk, q0, hq);
     if (a.pair_counter) {
         for (int s = 16; s > 0; s >>= 1) scored += __shfl_xor_sync(0xffffffffu, scored, s);
         if ((threadIdx.x & 31) == 0 && scored) atomicAdd(a.pair_counter, scored);
-    }
-    if (MODE == HMK_MODE_TOPK) {
-        __syncthreads();
-        hmk_topk_flush(a, tk, q0, qn, stripe);
     }
 }
 
@@ -871,12 +921,14 @@ __global__ void __launch_bounds__(HMK_GENERIC_THREADS) hmk_bulk_generic(const __
 
 // ---------------------------------------------------------------- top-k merge across stripes
 // one warp per query: kb rounds of "largest key below the previous pick" (keys are distinct)
+// `slots_of_tile` (persistent launches): the number of lists tile t / qt really got, instead of nstripes
 __global__ void hmk_topk_merge(int nq, int nstripes, int kb, const uint64_t* __restrict__ tk_key,
                                const int32_t* __restrict__ tk_cnt, const int32_t* __restrict__ tk_ovf,
                                uint64_t* __restrict__ out_key, int32_t* __restrict__ out_cnt,
-                               int32_t* __restrict__ out_ovf) {
+                               int32_t* __restrict__ out_ovf, const int32_t* __restrict__ slots_of_tile = nullptr, int qt = 1) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= nq) return;
+    if (slots_of_tile) nstripes = min(nstripes, slots_of_tile[t / qt]);
     int total = 0, ovf = 0;
     for (int s = lane; s < nstripes; s += 32) {
         total += tk_cnt[(size_t)s * nq + t];
@@ -1273,6 +1325,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
     __shared__ int32_t h_cons[HMK_HASH_SIZE];            // set: sequence ids consumed as partners in this batch
     __shared__ int32_t h_tkey[HMK_HASH_SIZE], h_trow[HMK_HASH_SIZE];   // map: cluster slot -> row
     __shared__ int32_t s_wb[32];                         // window scratch: partner taken by each lane
+    __shared__ int32_t s_wpick[32];                      //   ... and which entry of its list that is
     __shared__ int s_ncached;                            // queries [0, s_ncached) have their candidates cached
 
     // the cluster search must have seen every founder hit (nothing below has touched the state yet)
@@ -1455,25 +1508,40 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             __syncwarp();
             HMK_TICK(7);   // window: partner pick
             HMK_TRACE(1, 2);
-            // clusters born in this batch (before the window, or by earlier lanes of it) whose founder scores >= T
+            // Clusters born in this batch (before the window, or by earlier lanes of it): such a cluster is {founder b2,
+            // the partner b2 picked, ...}, so min(S(founder, q), S(partner, q)) bounds its complete-linkage score from
+            // above (further members only lower it).  A lane stays trusted if no such cluster can reach what the lane
+            // is about to do: for a new pair, a bound >= T that also reaches the partner's score would make the reference
+            // join instead; an orphan joins any valid cluster.  The bit masks pre-select the founders worth a look
+            // (ibm2: founder score >= T and >= the lowest listed partner score; ibm: founder score >= T); the two
+            // scores themselves come from the dense tables ib / pd.
             const unsigned cm0 = __ballot_sync(FULL, kind == 1);
             const unsigned lt = (1u << lane) - 1u;
+            s_wpick[lane] = bpick;
+            __syncwarp();
             {
                 const int w0 = b >> 5, sh = b & 31;
                 const unsigned mine = cm0 & lt;
-                // a new pair only has to fear founders scoring at least its lowest listed partner (ibm2);
-                // an orphan joins whatever valid cluster there is (ibm)
                 const uint32_t* hmrow = kind == 1 ? s_ibm2 + bi * nw : s_ibm + bi * nw;
-                uint32_t any = 0;
+                const int32_t need = kind == 1 ? (bscore > S.T ? bscore : S.T) : S.T;
+                bool threat = false;
                 if (kind == 1 || kind == 2) {
-                    for (int w = 0; w < nw; w++) {
+                    for (int w = 0; w < nw && !threat; w++) {
                         uint32_t m = s_fmask[w];
                         m |= w == w0 ? mine << sh : 0u;
                         m |= (w == w0 + 1 && sh) ? mine >> (32 - sh) : 0u;
-                        any |= m & hmrow[w];
+                        m &= hmrow[w];
+                        while (m && !threat) {
+                            const int b2 = w * 32 + __ffs(m) - 1;
+                            m &= m - 1;
+                            const int pk = b2 >= b ? s_wpick[b2 - b] : f_pick[b2];      // founded by an earlier lane of this window?
+                            const int32_t sf = __ldcg(B.ib + (size_t)bi * B.ib_stride + b2);
+                            const int32_t sp = __ldcg(B.pd + (size_t)bi * B.pd_stride + b2 * kb + pk);
+                            threat = (sf < sp ? sf : sp) >= need;
+                        }
                     }
                 }
-                if (any) kind = 3;
+                if (threat) kind = 3;
             }
             __syncwarp();
             HMK_TICK(6);   // window: founder bounds
