@@ -377,6 +377,14 @@ def test_cpp_host_driver_end_to_end(tmp_path, golden_dir, blosum62):
     for fn in ("initial_clusters_sequences.tsv", "initial_clusters_sequences_original_order.tsv", "initial_clusters.tsv",
                "input_statistics.tsv"):
         assert (out / fn).read_text() == (ref / fn).read_text(), fn
+    # ... and against the oracle's restatement of the reference writers (oracle/pyref_writers.py)
+    from oracle import pyref_writers as W
+    tup = lambda s: (s.get_sequence_string(), dict(s.labels_map))
+    ct = [(c.get_id(), [tup(s) for s in c.get_sequences()]) for c in clusters]
+    assert (out / "initial_clusters_sequences.tsv").read_text() == W.cluster_sequences_tsv(ct, labels)
+    assert (out / "initial_clusters_sequences_original_order.tsv").read_text() == W.cluster_sequences_tsv_ordered(ct, labels, [tup(s) for s in seqs])
+    assert (out / "initial_clusters.tsv").read_text() == W.clusters_tsv(ct, labels)
+    assert (out / "input_statistics.tsv").read_text() == W.input_statistics([tup(s) for s in seqs], labels)
     # all abundances are 1 in MUSI and the clustering order is (abundance, string) -> same order as the golden
     got = {}
     for line in (out / "initial_clusters_sequences.tsv").read_text().splitlines()[1:]:

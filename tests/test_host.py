@@ -299,3 +299,56 @@ def test_committed_bench_line_keeps_the_contract():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     w = d["work"]
     assert w["bulk_pairs"] + w["scalar_pairs"] + w["pairs_served_by_phase1_hits"] >= w["reference_min_pairs"]
+
+
+def _labelled_musi(golden_dir):
+    """MUSI with three labels and varied counts + its golden clustering as host Cluster objects and as the oracle's tuples"""
+    z = np.load(os.path.join(golden_dir, "musi.npz"))
+    strs = synth.to_strings(z["residues"], z["offsets"])
+    rng = np.random.default_rng(9)
+    labs = ["rep1", "rep2", "ctrl"]
+    maps = []
+    for i in range(len(strs)):
+        k = int(rng.integers(1, 4))
+        maps.append({labs[j]: int(rng.integers(1, 60)) for j in rng.choice(3, k, replace=False)})
+    seqs = [hb.UniqueSequence(strs[i], maps[i]) for i in range(len(strs))]
+    r = hb.GreedyResult(z["cluster_id"], z["member_rank"], z["result_order"], int(z["n_multi"]), {})
+    clusters = hb.rebuild_clusters(seqs, r)
+    tuples = [(c.get_id(), [(s.get_sequence_string(), dict(s.labels_map)) for s in c.get_sequences()]) for c in clusters]
+    return seqs, clusters, tuples, labs
+
+
+def test_result_file_writers_against_the_oracle_writers(tmp_path, golden_dir):
+    """the four files of the greedy stage, host writers vs the oracle's restatement of
+    FileIOManager (oracle/pyref_writers.py), byte for byte, on the MUSI golden clustering with labels"""
+    from oracle import pyref_writers as W
+    seqs, clusters, tuples, labs = _labelled_musi(golden_dir)
+    rng = np.random.default_rng(2)
+    for labels in (labs, ["ctrl", "rep1"], ["rep2", "absent", "rep1", "ctrl"]):
+        order = [int(i) for i in rng.permutation(len(seqs))]
+        ordered = [seqs[i] for i in order]
+        ordered_t = [(seqs[i].get_sequence_string(), dict(seqs[i].labels_map)) for i in order]
+        # plus a sequence that is in no cluster: the reference writes NA for it (FileIOManager.java:625-627)
+        extra = hb.UniqueSequence("WWWWWWWWWWWW", {"rep1": 2})
+        ordered.append(extra)
+        ordered_t.append(("WWWWWWWWWWWW", {"rep1": 2}))
+        p = tmp_path / "a.tsv"
+        hb.save_cluster_sequences_to_csv(clusters, str(p), labels)
+        assert p.read_text() == W.cluster_sequences_tsv(tuples, labels)
+        hb.save_cluster_sequences_to_csv_ordered(clusters, str(p), labels, ordered)
+        assert p.read_text() == W.cluster_sequences_tsv_ordered(tuples, labels, ordered_t)
+        hb.save_clusters_to_csv(clusters, str(p), labels)
+        assert p.read_text() == W.clusters_tsv(tuples, labels)
+        hb.save_input_statistics(seqs, labels, str(p))
+        assert p.read_text() == W.input_statistics([(s.get_sequence_string(), dict(s.labels_map)) for s in seqs], labels)
+    # known answers: descending cluster size then id; members by abundance then string, both descending
+    lines = W.cluster_sequences_tsv(tuples, labs).splitlines()
+    assert lines[0] == "cluster_id\tsequence\talignment\tsum\trep1\trep2\tctrl"
+    sizes = {}
+    for ln in lines[1:]:
+        f = ln.split("\t")
+        sizes.setdefault(int(f[0]), []).append((int(f[3]), f[1]))
+    tot = [(sum(v for v, _ in m), cid) for cid, m in sizes.items()]
+    assert tot == sorted(tot, reverse=True)
+    for m in sizes.values():
+        assert m == sorted(m, reverse=True)
