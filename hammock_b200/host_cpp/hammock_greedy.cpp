@@ -20,7 +20,7 @@ static void usage() {
 
 int main(int argc, char** argv) {
     std::string input, outdir, format = "fasta", matrixPath, order = "size";
-    bool haveT = false, haveX = false, haveK = false, dump = false, haveLabels = false;
+    bool haveT = false, haveX = false, haveK = false, dump = false, haveLabels = false, timeHost = false, hostOnly = false;
     int32_t threshold = 0, maxShift = 0, shiftPenalty = 0, limit = 0;   // shiftPenalty default 0 (Hammock.java:82)
     int64_t seed = 42;                                                   // Hammock.java:67
     int device = 0;
@@ -46,6 +46,8 @@ int main(int argc, char** argv) {
             else if (a == "-t" || a == "--threads") next();   // accepted for compatibility; the GPU does the work
             else if (a == "--device") device = decode_int(next());
             else if (a == "--dump-prepared") dump = true;
+            else if (a == "--time-host") timeHost = true;       // stage timings of the host side on stderr
+            else if (a == "--host-only") hostOnly = true;       // stop before the GPU call (with --time-host: SURVEY.md 8f N4)
             else if (a == "-l" || a == "--labels") {
                 std::string v = next(), cur;
                 for (char c : v) { if (c == ',') { labels.push_back(cur); cur.clear(); } else cur.push_back(c); }
@@ -58,8 +60,15 @@ int main(int argc, char** argv) {
         if (matrixPath.empty() && !dump) throw CLIException("Error. Parameter matrix (-m) missing (e.g. matrices/blosum62.txt of the Hammock distribution).");
         if (format != "fasta" && format != "tab") throw CLIException("Error. Wrong input file format. Use \"fasta\" or \"tab\"");
 
+        auto tick = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            auto now = std::chrono::steady_clock::now();
+            if (timeHost) std::cerr << "host time " << what << ": " << std::chrono::duration<double, std::milli>(now - tick).count() << " ms\n";
+            tick = now;
+        };
         // loadInputSequences (Hammock.java:749-787)
         std::vector<UniqueSequence> sequences = format == "fasta" ? loadUniqueSequencesFromFasta(input) : loadUniqueSequencesFromTable(input);
+        lap("load + de-duplicate");
         if (haveLabels) {   // filterSequencesForLabels (Hammock.java:1661-1675): keep sequences having any listed label
             std::vector<UniqueSequence> kept;
             for (auto& s : sequences) {
@@ -76,7 +85,10 @@ int main(int argc, char** argv) {
         if (!haveX) maxShift = getMaxShift(sequences); else maxShift = checkMaxShift(sequences, maxShift);
         if (!haveT) threshold = setGreedyThreshold(sequences);            // Hammock.java:394-397
         if (!haveK) limit = initialClustersLimit(sequences);              // :398-401
+        lap("labels + automatic parameters");
         sortSequences(sequences, order, labels, seed);                     // :407
+        lap("sortSequences");
+        if (hostOnly) return 0;
 
         if (dump) {   // host-side state right before clusterer.cluster(sequences): used by the CPU tests
             std::cout << "threshold\t" << threshold << "\nmax_shift\t" << maxShift << "\nlimit\t" << limit << "\nlabels";
