@@ -211,6 +211,7 @@ public:
     int run();
     void download(hmk_greedy_out* out);
     void score_block(const int32_t* first, int32_t nf, const int32_t* second, int32_t ns, int32_t* scores);
+    int clinkage(const hmk_greedy_in* in, hmk_greedy_out* out);
     hmk_stats stats{};
     int error_step = -1;
     void timer_begin() { CK(cudaSetDevice(device_)); CK(cudaEventRecord(ev_t0_, st_)); }
@@ -299,7 +300,7 @@ private:
     DevBuf<int32_t> d_qid_, d_nq_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_;
     DevBuf<int4> d_ac_full_, d_ac_best_;
-    DevBuf<int32_t> d_sched_;
+    DevBuf<int32_t> d_sched_, d_clD_, d_cli_;
     // phase-1 partner-search hits kept for phase 2 (opt.reuse): buffer, 64-bit counters [0] appended, [1] valid
     DevBuf<int4> d_xhits_;
     DevBuf<unsigned long long> d_xcount_;
@@ -1454,6 +1455,86 @@ void Engine::score_block(const int32_t* first, int32_t nf, const int32_t* second
     }
 }
 
+// ---------------------------------------------------------------- exact complete-linkage clustering
+// ClinkageSequenceClusterer.cluster (ClinkageSequenceClusterer.java:43-124): dense pair scores from the bulk kernel,
+// nearest-neighbour chain in hmk_clinkage_chain.  Returns the status; fills `out` on success.
+int Engine::clinkage(const hmk_greedy_in* in, hmk_greedy_out* out) {
+    upload(in);
+    stats = hmk_stats{};
+    stats.error_step = -1;
+    launches_ = bulk_launches_ = 0;
+    ev_used_ = 0; bulk_events_.clear(); sections_.clear(); sec_open_ = -1;
+    if (!out || (n_ > 0 && (!out->cluster_id || !out->member_rank || !out->result_order)))
+        throw std::invalid_argument("hmk_clinkage_cluster: null output array");
+    out->n_result = 0; out->n_multi = 0; out->error_step = -1;
+    if (n_ == 0)      // activeClusters.iterator().next() on an empty set (ClinkageSequenceClusterer.java:116)
+        throw std::invalid_argument("hmk_clinkage_cluster: no sequences (the reference throws NoSuchElementException)");
+    if (bad_residue_) return HMK_ERR_BAD_RESIDUE;
+    if (!sym_) return HMK_STATUS_UNSUPPORTED;          // CachedClusterScorer keeps one value per unordered pair of clusters
+    if (n_ > 32768) return HMK_STATUS_UNSUPPORTED;     // n x n int32 scores; the reference switches to greedy above 10 000
+    if (n_ >= 2 && X_ >= min_len_) return HMK_ERR_SHIFT_TOO_BIG;
+    const size_t n = (size_t)n_;
+    d_clD_.reserve(n * n);
+    CK(cudaEventRecord(ev_a_, st_));
+    {   // D[q][i] = sequenceScore(seq i, seq q) (symmetric), one batch of profiles at a time
+        std::vector<int32_t> ids(n_);
+        std::iota(ids.begin(), ids.end(), 0);
+        CK(cudaMemcpyAsync(d_sidx_.p, ids.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st_));
+        CK(cudaStreamSynchronize(st_));
+        const int chunk = HMK_MAXBATCH;
+        if (fast_) d_prof_.reserve((size_t)chunk * sc_.prof_words);
+        for (int q0 = 0; q0 < n_; q0 += chunk) {
+            const int sn = std::min(chunk, n_ - q0);
+            if (fast_) launch_profiles(HMK_PROF_QUERY, d_sidx_.p + q0, sn, d_prof_.p, sc_, st_);
+            HmkBulkArgs a{};
+            a.prof = d_prof_.p; a.nq = sn;
+            a.packed = d_packed_.p; a.db_ids = nullptr; a.db_begin = 0; a.ndb = n_;
+            a.dense = d_clD_.p + (size_t)q0 * n; a.dense_stride = n_;
+            launch_bulk(HMK_MODE_DENSE, a, d_sidx_.p + q0, 1);
+        }
+    }
+    hmk_clinkage_threshold<<<sm_count_ * 8, 256, 0, st_>>>(d_clD_.p, n * n, T_);
+    int acap = 16;
+    while (n_ > (int)(acap * 0.75f)) acap *= 2;          // java.util.HashMap: doubled whenever size > 0.75 x capacity
+    int rcap = 16;
+    while ((int)(rcap * 0.75f) < n_) rcap *= 2;
+    const size_t maxid = 2 * n + 3;
+    d_cli_.reserve((size_t)acap * 2 + maxid * 4 + n * 8 + 1 + (size_t)rcap * 4 + 8);
+    HmkClinkage C{};
+    int32_t* p = d_cli_.p;
+    C.n = n_; C.T = T_; C.D = d_clD_.p; C.ab = d_ab_.p; C.acap = acap;
+    C.a_head = p; p += acap; C.a_tail = p; p += acap;
+    C.a_next = p; p += maxid; C.a_prev = p; p += maxid; C.slot_of = p; p += maxid; C.r_next = p; p += maxid;
+    C.id_of = p; p += n; C.size_of = p; p += n; C.mhead = p; p += n; C.mtail = p; p += n; C.mnext = p; p += n;
+    C.stack = p; p += n + 1; C.ready = p; p += n; C.result_order = p; p += n;
+    C.r_head = p; p += (size_t)rcap * 4; C.rcap_max = rcap;
+    C.out_scalars = p; p += 8;
+    C.cluster_id = d_cluster_id_.p; C.member_rank = d_member_rank_.p;
+    hmk_clinkage_chain<<<1, HMK_CL_THREADS, 0, st_>>>(C);
+    CK(cudaGetLastError());
+    launches_ += 2;
+    CK(cudaEventRecord(ev_c_, st_));
+    int32_t sc[8];
+    CK(cudaMemcpyAsync(sc, C.out_scalars, sizeof(sc), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev_a_, ev_c_));
+    stats.total_ms = ms; stats.phase1_ms = ms;
+    stats.bulk_launches = bulk_launches_; stats.total_launches = launches_;
+    stats.bulk_pairs = (int64_t)n * (int64_t)n;
+    stats.p1_steps = sc[3];                          // nearest-neighbour searches
+    stats.fast_path = fast_ ? 1 : 0;
+    stats.lane_bits = fast_ ? (sc_.lane16 ? 16 : 8) : 32;
+    if (sc[2]) return HMK_STATUS_UNSUPPORTED;         // a HashMap bin reached the tree threshold
+    CK(cudaMemcpyAsync(out->cluster_id, d_cluster_id_.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(out->member_rank, d_member_rank_.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(out->result_order, C.result_order, sizeof(int32_t) * sc[0], cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    out->n_result = sc[0];
+    out->n_multi = sc[1];
+    return HMK_OK;
+}
+
 void Engine::init_distributed(int rank, int world, const void* id128) {
     CK(cudaSetDevice(device_));
     if (world < 1 || rank < 0 || rank >= world || !id128) throw std::invalid_argument("hmk_init_distributed: bad rank/world/id");
@@ -1564,6 +1645,8 @@ static const char* status_text(int rc) {
         case HMK_STATUS_SHIFT_TOO_BIG: return "DataException: Shift too big (max_shift >= length of the shortest sequence)";
         case HMK_STATUS_NULL_CLUSTER: return "NullPointerException: nearest cluster object without a cluster (see error_step)";
         case HMK_STATUS_BAD_RESIDUE: return "FileFormatException: residue code outside 0..23";
+        case HMK_STATUS_UNSUPPORTED: return "unsupported input for the exact complete-linkage clusterer: asymmetric substitution matrix, "
+                                            "more than 32768 sequences, or a java.util.HashMap bin that would be treeified";
         default: return "";
     }
 }
@@ -1714,6 +1797,19 @@ int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device,
     });
 }
 
+
+int hmk_clinkage_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen) {
+    if (!in || !out) return HMK_STATUS_BAD_ARG;
+    std::lock_guard<std::mutex> lock(cache_mutex());
+    return guarded(errbuf, errlen, [&] {
+        if (!cached_group().empty()) clear_cached();
+        auto& slot = cached_ctx()[device];
+        if (!slot) slot.reset(new hmk_ctx(device));
+        int rc = slot->engine.clinkage(in, out);
+        if (rc) set_err(errbuf, errlen, status_text(rc));
+        return rc;
+    });
+}
 
 int hmk_greedy_cluster_multi(const hmk_greedy_in* in, hmk_greedy_out* out, const int32_t* devices, int32_t n_gpus,
                              char* errbuf, size_t errlen) {

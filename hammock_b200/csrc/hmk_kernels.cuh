@@ -2324,3 +2324,236 @@ __global__ void __launch_bounds__(1024) hmk_peak_lds(int iters, int32_t* out) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = (int32_t)(acc0 ^ acc1 ^ acc2 ^ acc3);
 }
+
+// ---------------------------------------------------------------- exact complete-linkage clustering (NN chain)
+// ClinkageSequenceClusterer.cluster (reference ClinkageSequenceClusterer.java:43-124), Hammock's default
+// initial stage for <= 10 000 unique sequences (Hammock.java:371-373), on the same pair scorer: the dense matrix of
+// sequence-pair scores comes from the bulk kernel (MODE_DENSE), this kernel runs the nearest-neighbour chain on it.
+//   D[a][b]   complete-linkage score of the clusters in slots a, b (ClinkageClusterScorer.java:30-49): min over the
+//             member pairs, HMK_CL_BELOW as soon as one pair scores < T; merging two clusters takes the element-wise
+//             minimum of their rows -- what CachedClusterScorer.join does (CachedClusterScorer.java:96-125)
+//   nearest   arg-max over the other active clusters under NearestClusterRunner's order (score, Cluster.size(), smaller
+//             id; ClinkageSequenceClusterer.java:258-293) -- a strict total order, so the scan order does not matter
+//   HashSets  the chain restarts from activeClusters.iterator().next() (:70) and the result is new ArrayList(readyClusters)
+//             (:119-123): both are java.util.HashSet<Cluster>, iterated in bucket order.  Emulated for OpenJDK 8+:
+//             bucket = (h ^ h >>> 16) & (capacity - 1) with h = Cluster.hashCode() = 79 * 7 + id (Cluster.java:179-183),
+//             chains in insertion order.  The table of activeClusters only grows while the n singletons are added, and a
+//             resize keeps the relative order inside a bin, so inserting into the final table directly gives the same
+//             chains; the same holds for readyClusters (insert only).  A bin that reaches 8 entries would be turned into
+//             a tree by the JDK (different order): reported as unsupported -- it cannot happen with these consecutive
+//             hash codes unless n is tiny.
+// One CTA: a chain step is a row scan + a block reduction; steps are inherently sequential (about 3 n of them).
+#define HMK_CL_BELOW (HMK_JMIN + 1)
+#define HMK_CL_THREADS 1024
+
+struct HmkClinkage {
+    int32_t n, T;
+    int32_t* D;            // [n][n]
+    const int32_t* ab;
+    int32_t acap;          // capacity of the activeClusters table
+    int32_t* a_head;       // [acap] -1 = empty bin
+    int32_t* a_tail;       // [acap]
+    int32_t* a_next;       // [2n + 3] chain links by cluster id
+    int32_t* a_prev;
+    int32_t* slot_of;      // [2n + 3] cluster id -> slot
+    int32_t* id_of;        // [n] slot -> cluster id, -1 = slot not active
+    int32_t* size_of;      // [n] Cluster.size() (abundance weighted, Java int)
+    int32_t* mhead;        // [n] member list of the slot's cluster
+    int32_t* mtail;
+    int32_t* mnext;
+    int32_t* stack;        // [n + 1] cluster ids
+    int32_t* ready;        // [n] ready clusters in insertion order
+    int32_t* r_head;       // [4][rcap_max] scratch: two (head, tail) tables of the growing readyClusters set
+    int32_t rcap_max;
+    int32_t* r_next;       // [2n + 3]
+    int32_t* cluster_id;   // outputs
+    int32_t* member_rank;
+    int32_t* result_order;
+    int32_t* out_scalars;  // [0] n_result, [1] n_multi, [2] status (0 ok, 1 a bin reached the tree threshold), [3] nearest searches
+};
+
+__device__ __forceinline__ uint32_t hmk_cluster_hash(int32_t id) {
+    const uint32_t h = (uint32_t)(79 * 7 + id);
+    return h ^ (h >> 16);
+}
+
+__global__ void hmk_clinkage_threshold(int32_t* D, size_t total, int32_t T) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        if (D[i] < T) D[i] = HMK_CL_BELOW;
+}
+
+__global__ void __launch_bounds__(HMK_CL_THREADS) hmk_clinkage_chain(const HmkClinkage C) {
+    __shared__ int32_t r_score[32], r_size[32], r_id[32];
+    __shared__ int32_t s_top, s_best, s_bscore, s_action, s_ts, s_bs;     // action: 0 ready, 1 merge, 2 push, 3 finished
+    __shared__ int32_t s_first[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = C.n;
+    const unsigned FULL = 0xffffffffu;
+    // ---- the n singleton clusters, ids 1..n (:48-54)
+    for (int b = tid; b < C.acap; b += blockDim.x) { C.a_head[b] = -1; C.a_tail[b] = -1; }
+    for (int i = tid; i < n; i += blockDim.x) {
+        C.id_of[i] = i + 1; C.slot_of[i + 1] = i; C.size_of[i] = C.ab[i];
+        C.mhead[i] = i; C.mtail[i] = i; C.mnext[i] = -1;
+    }
+    __syncthreads();
+    __shared__ int32_t sp, nr, nactive, cur_id, treeified, searches;
+    if (tid == 0) {
+        treeified = 0;
+        for (int id = 1; id <= n; id++) {            // insertion order = id order; chains are short (consecutive hash codes)
+            const int b = (int)(hmk_cluster_hash(id) & (uint32_t)(C.acap - 1));
+            int len = 0;
+            for (int k = C.a_head[b]; k >= 0; k = C.a_next[k]) len++;
+            if (len >= 7) treeified = 1;
+            C.a_next[id] = -1; C.a_prev[id] = C.a_tail[b];
+            if (C.a_tail[b] >= 0) C.a_next[C.a_tail[b]] = id; else C.a_head[b] = id;
+            C.a_tail[b] = id;
+        }
+        sp = 0; nr = 0; nactive = n; cur_id = n + 1; searches = 0;
+    }
+    __syncthreads();
+    auto set_remove = [&](int32_t id) {               // thread 0
+        const int b = (int)(hmk_cluster_hash(id) & (uint32_t)(C.acap - 1));
+        const int32_t p = C.a_prev[id], nx = C.a_next[id];
+        if (p >= 0) C.a_next[p] = nx; else C.a_head[b] = nx;
+        if (nx >= 0) C.a_prev[nx] = p; else C.a_tail[b] = p;
+        nactive--;
+    };
+    auto set_add = [&](int32_t id) {                  // thread 0
+        const int b = (int)(hmk_cluster_hash(id) & (uint32_t)(C.acap - 1));
+        int len = 0;
+        for (int k = C.a_head[b]; k >= 0; k = C.a_next[k]) len++;
+        if (len >= 7) treeified = 1;
+        C.a_next[id] = -1; C.a_prev[id] = C.a_tail[b];
+        if (C.a_tail[b] >= 0) C.a_next[C.a_tail[b]] = id; else C.a_head[b] = id;
+        C.a_tail[b] = id;
+        nactive++;
+    };
+    for (;;) {
+        // ---- empty stack: activeClusters.iterator().next() -- the head of the first non-empty bin (:62-70)
+        if (sp == 0) {
+            if (nactive <= 1) break;                  // (uniform: shared variables, read after a barrier)
+            int first = 0x7fffffff;
+            for (int b = tid; b < C.acap; b += blockDim.x)
+                if (C.a_head[b] >= 0) { first = b; break; }
+            first = __reduce_min_sync(FULL, first);
+            if (lane == 0) s_first[wid] = first;
+            __syncthreads();
+            if (tid == 0) {
+                int f = 0x7fffffff;
+                for (int w = 0; w < (int)(blockDim.x >> 5); w++) f = min(f, s_first[w]);
+                C.stack[0] = C.a_head[f];
+                sp = 1;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { s_top = C.stack[sp - 1]; s_ts = C.slot_of[s_top]; searches++; }
+        __syncthreads();
+        const int32_t top = s_top, ts = s_ts;
+        // ---- nearest neighbour of `top` (:75-82)
+        HmkBestCluster bb;
+        bb.score = HMK_JMIN; bb.size = 0; bb.fid = 0; bb.slot = -1;
+        for (int k = tid; k < n; k += blockDim.x) {
+            const int32_t id = C.id_of[k];
+            if (id < 0 || k == ts) continue;
+            hmk_consider(bb, C.D[(size_t)ts * n + k], C.size_of[k], id, k);
+        }
+        hmk_best_reduce(bb);
+        if (lane == 0) { r_score[wid] = bb.slot >= 0 ? bb.score : HMK_JMIN; r_size[wid] = bb.size; r_id[wid] = bb.slot >= 0 ? bb.fid : -1; }
+        __syncthreads();
+        if (tid == 0) {
+            HmkBestCluster g;
+            g.score = HMK_JMIN; g.size = 0; g.fid = 0; g.slot = -1;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++)
+                if (r_id[w] >= 0) hmk_consider(g, r_score[w], r_size[w], r_id[w], w);
+            const int32_t best = g.slot >= 0 ? g.fid : -1, bscore = g.slot >= 0 ? g.score : HMK_JMIN;
+            s_best = best; s_bscore = bscore;
+            if (bscore < C.T) {                                           // :85-91
+                sp--;
+                C.ready[nr++] = top;
+                set_remove(top);
+                C.id_of[ts] = -1;
+                s_action = 0;
+            } else if (sp > 1 && C.stack[sp - 2] == best) {               // :95-109
+                s_bs = C.slot_of[best];
+                s_action = 1;
+            } else {
+                C.stack[sp++] = best;                                     // :111
+                s_action = 2;
+            }
+        }
+        __syncthreads();
+        if (s_action == 1) {
+            const int32_t bs = s_bs;
+            // CachedClusterScorer.join: the merged cluster's scores are the element-wise minimum of the two rows
+            for (int k = tid; k < n; k += blockDim.x) {
+                const int32_t a = C.D[(size_t)ts * n + k], b2 = C.D[(size_t)bs * n + k], m = a < b2 ? a : b2;
+                C.D[(size_t)ts * n + k] = m;
+                C.D[(size_t)k * n + ts] = m;
+            }
+            if (tid == 0) {
+                cur_id++;
+                sp -= 2;
+                set_remove(top);
+                set_remove(s_best);
+                // new Cluster(top.getSequences() ++ nearest.getSequences(), currentId) (:104-106)
+                C.mnext[C.mtail[ts]] = C.mhead[bs];
+                C.mtail[ts] = C.mtail[bs];
+                C.size_of[ts] = hmk_wadd(C.size_of[ts], C.size_of[bs]);
+                C.id_of[ts] = cur_id; C.id_of[bs] = -1;
+                C.slot_of[cur_id] = ts;
+                set_add(cur_id);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- the last cluster is ready too (:116); then new ArrayList(readyClusters): bucket order of a table that grew with
+    // the set (capacity 16, doubled whenever the size exceeded 0.75 x capacity)
+    if (tid == 0) {
+        for (int b = 0; b < C.acap; b++)
+            if (C.a_head[b] >= 0) { C.ready[nr++] = C.a_head[b]; break; }
+        // the set as HashMap builds it: append at the bin's tail, double the table (bins split in order) whenever the size
+        // exceeds 0.75 x capacity
+        int rcap = 16, rsize = 0;
+        int32_t* head = C.r_head;                     // two (head, tail) table pairs, used alternately across resizes
+        int32_t* tail = C.r_head + C.rcap_max;
+        int32_t* head2 = C.r_head + 2 * C.rcap_max;
+        int32_t* tail2 = C.r_head + 3 * C.rcap_max;
+        for (int b = 0; b < rcap; b++) { head[b] = -1; tail[b] = -1; }
+        for (int i = 0; i < nr; i++) {
+            const int32_t id = C.ready[i];
+            const int b = (int)(hmk_cluster_hash(id) & (uint32_t)(rcap - 1));
+            int len = 0;
+            for (int32_t k = head[b]; k >= 0; k = C.r_next[k]) len++;
+            if (len >= 7) treeified = 1;
+            C.r_next[id] = -1;
+            if (tail[b] >= 0) C.r_next[tail[b]] = id; else head[b] = id;
+            tail[b] = id;
+            if (++rsize > (int)(rcap * 0.75f)) {
+                const int ncap = rcap * 2;
+                for (int b2 = 0; b2 < ncap; b2++) { head2[b2] = -1; tail2[b2] = -1; }
+                for (int b2 = 0; b2 < rcap; b2++)
+                    for (int32_t k = head[b2], nx; k >= 0; k = nx) {
+                        nx = C.r_next[k];
+                        const int nb = (int)(hmk_cluster_hash(k) & (uint32_t)(ncap - 1));
+                        C.r_next[k] = -1;
+                        if (tail2[nb] >= 0) C.r_next[tail2[nb]] = k; else head2[nb] = k;
+                        tail2[nb] = k;
+                    }
+                int32_t* t1 = head; head = head2; head2 = t1;
+                t1 = tail; tail = tail2; tail2 = t1;
+                rcap = ncap;
+            }
+        }
+        int o = 0, multi = 0;
+        for (int b = 0; b < rcap; b++)
+            for (int32_t id = head[b]; id >= 0; id = C.r_next[id]) C.result_order[o++] = id;
+        for (int i = 0; i < nr; i++) { const int s = C.slot_of[C.result_order[i]]; multi += C.mhead[s] != C.mtail[s]; }
+        C.out_scalars[0] = nr; C.out_scalars[1] = multi; C.out_scalars[2] = treeified; C.out_scalars[3] = searches;
+    }
+    __syncthreads();
+    for (int i = tid; i < nr; i += blockDim.x) {
+        const int32_t id = C.result_order[i];
+        int32_t rank = 0;
+        for (int32_t m = C.mhead[C.slot_of[id]]; m >= 0; m = C.mnext[m]) { C.cluster_id[m] = id; C.member_rank[m] = rank++; }
+    }
+}

@@ -693,6 +693,28 @@ def greedy_cluster_arrays(residues, offsets, abundance, matrix, threshold, max_s
     return 0, GreedyResult(cid[:n], rank[:n], order[:out.n_result].copy(), int(out.n_multi), {}), -1, b""
 
 
+def clinkage_cluster_arrays(residues, offsets, abundance, matrix, threshold, max_shift, shift_penalty, device: int = 0):
+    """One blocking hmk_clinkage_cluster call on host arrays (sequences in the caller's order)
+    -> (status, GreedyResult | None, message).  cluster_id holds Cluster.getId() (1-based, merged clusters n + 2, ...)."""
+    L = _lib.load()
+    residues = np.ascontiguousarray(residues, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    abundance = np.ascontiguousarray(abundance, dtype=np.int32)
+    matrix = np.ascontiguousarray(matrix, dtype=np.int32).reshape(-1)
+    n = len(abundance)
+    cid = np.empty(max(n, 1), dtype=np.int32)
+    rank = np.empty(max(n, 1), dtype=np.int32)
+    order = np.empty(max(n, 1), dtype=np.int32)
+    gin = _lib.GreedyIn(n, _ptr(residues, C.c_uint8), _ptr(offsets, C.c_int32), _ptr(abundance, C.c_int32),
+                        _ptr(matrix, C.c_int32), int(threshold), int(max_shift), int(shift_penalty), 0)
+    out = _lib.GreedyOut(_ptr(cid, C.c_int32), _ptr(rank, C.c_int32), _ptr(order, C.c_int32), 0, 0, -1)
+    err = C.create_string_buffer(512)
+    rc = L.hmk_clinkage_cluster(C.byref(gin), C.byref(out), device, err, 512)
+    if rc:
+        return rc, None, err.value
+    return 0, GreedyResult(cid[:n], rank[:n], order[:out.n_result].copy(), int(out.n_multi), {}), b""
+
+
 # ---------------------------------------------------------------- scorer / clusterer seam
 class ShiftedScorer:
     """ShiftedScorer.java:12-32 (constructor arguments) -- the scoring itself runs on the GPU."""
@@ -735,6 +757,48 @@ class LimitedGreedySequenceClusterer:
         if rc:
             _raise_status(rc, err, step)
         return rebuild_clusters(sequences, r)
+
+
+class UnsupportedInput(HammockException):
+    """hmk_clinkage_cluster: asymmetric matrix, too many sequences, or a treeified java.util.HashMap bin"""
+
+
+class ClinkageSequenceClusterer:
+    """ClinkageSequenceClusterer.java:22-39 + SequenceClusterer.java:15-26 -- the exact complete-linkage clusterer
+    (nearest-neighbour chain), Hammock's default initial stage for up to 10 000 unique sequences (Hammock.java:371-373)."""
+
+    def __init__(self, sequence_scorer: ShiftedScorer, threshold: int, size_limit: int = 1):
+        # size_limit only decides which cluster scores the reference caches (CachedClusterScorer.java:38-41); the
+        # cached values equal the recomputed ones, so it does not change the result
+        self.sequence_scorer, self.threshold, self.size_limit = sequence_scorer, int(threshold), int(size_limit)
+
+    def cluster(self, sequences: List[UniqueSequence]) -> List[Cluster]:
+        """cluster(List<UniqueSequence>) -> List<Cluster> (ClinkageSequenceClusterer.java:43-124), in the order of the
+        list the reference returns (java.util.HashSet iteration order, OpenJDK 8+)."""
+        sc = self.sequence_scorer
+        res, offs, ab = pack_sequences(sequences)
+        rc, r, err = clinkage_cluster_arrays(res, offs, ab, sc.scoring_matrix, self.threshold, sc.max_shift, sc.shift_penalty, sc.device)
+        if rc == _lib.STATUS_UNSUPPORTED:
+            raise UnsupportedInput(err.decode(errors="replace"))
+        if rc:
+            _raise_status(rc, err)
+        return rebuild_clusters(sequences, r)
+
+
+def set_clinkage_threshold(sequences: Sequence[UniqueSequence]) -> int:
+    """Hammock.setClinkageThreshold (Hammock.java:1415-1419)"""
+    return _java_round(get_mean_sequence_length(sequences) * 1.7)
+
+
+def run_clinkage_clustering(sequences: List[UniqueSequence], scoring_matrix, threshold: Optional[int] = None,
+                            max_shift: Optional[int] = None, shift_penalty: int = 0, device: int = 0) -> List[Cluster]:
+    """The clustering part of Hammock.runClinkageClustering (Hammock.java:449-462): automatic parameters, NO sorting."""
+    if not sequences:
+        raise FileFormatException("Error. No sequences (with specified labels) to cluster.")   # Hammock.java:783-785
+    max_shift = get_max_shift(sequences) if max_shift is None else check_max_shift(sequences, max_shift)
+    if threshold is None:
+        threshold = set_clinkage_threshold(sequences)
+    return ClinkageSequenceClusterer(ShiftedScorer(scoring_matrix, shift_penalty, max_shift, device), threshold).cluster(list(sequences))
 
 
 def rebuild_clusters(sequences: Sequence[UniqueSequence], r: GreedyResult) -> List[Cluster]:

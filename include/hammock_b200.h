@@ -37,6 +37,7 @@ extern "C" {
 #define HMK_STATUS_BAD_RESIDUE 3   /* residue code >= 24                  UniqueSequence.java:51-54 */
 #define HMK_STATUS_CUDA 4          /* CUDA / NCCL failure (no CPU fallback) */
 #define HMK_STATUS_BAD_ARG 5
+#define HMK_STATUS_UNSUPPORTED 6   /* hmk_clinkage_cluster only, see there */
 
 typedef struct {
     int32_t n;                /* sequences, ALREADY in clustering order                              */
@@ -103,6 +104,18 @@ int hmk_greedy_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device,
  * with the same device list.  The result is identical to the one-GPU result. */
 int hmk_greedy_cluster_multi(const hmk_greedy_in* in, hmk_greedy_out* out, const int32_t* devices, int32_t n_gpus,
                              char* errbuf, size_t errlen);
+/* SURVEY.md 8(f) N1 -- the EXACT complete-linkage initial clustering, Hammock's default initial stage for up to 10 000
+ * unique sequences (Hammock.java:371-373):  new ClinkageSequenceClusterer(scorer, threshold).cluster(sequences)
+ * (Hammock.java:457-462, ClinkageSequenceClusterer.java:43-124; nearest-neighbour chain over complete-linkage scores with
+ * CachedClusterScorer.java:38-125).  Same input struct (max_clusters is ignored; the sequences come in the caller's order --
+ * runClinkageClustering does not sort).  Outputs: cluster_id[i] = Cluster.getId() of sequence i's cluster (i + 1 for
+ * singletons, n + 2, n + 3, ... for merged clusters, in merge order), member_rank[i] = position in getSequences(),
+ * result_order[0 .. n_result) = the ids of the returned list IN ITS ORDER, n_multi = clusters with more than one member.
+ * The chain start and the order of the returned list come from java.util.HashSet iteration; they are reproduced for the
+ * OpenJDK 8+ HashMap.  HMK_STATUS_UNSUPPORTED: asymmetric matrix (the reference's cached scores then depend on the thread
+ * schedule), more than 32768 sequences, or a hash bin that the JDK would turn into a tree.  An empty input (the reference
+ * throws NoSuchElementException) returns HMK_STATUS_BAD_ARG. */
+int hmk_clinkage_cluster(const hmk_greedy_in* in, hmk_greedy_out* out, int device, char* errbuf, size_t errlen);
 /* Frees the contexts the two calls above keep.  Call it before the process unloads CUDA if the memory
  * matters; the library never tears them down from a static destructor. */
 void hmk_release_cached(void);

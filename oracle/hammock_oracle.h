@@ -34,7 +34,10 @@ enum {
     HMKO_ERR_NULL_CLUSTER = 2,    /* NullPointerException, LimitedGreedy...java:104,108 */
     HMKO_ERR_BAD_RESIDUE = 3,     /* FileFormatException, UniqueSequence.java:51-54     */
     HMKO_ERR_FILE_FORMAT = 6,     /* FileFormatException in the loaders                 */
-    HMKO_ERR_IO = 7
+    HMKO_ERR_IO = 7,
+    HMKO_ERR_EMPTY = 8,           /* clinkage: NoSuchElementException on an empty input (ClinkageSequenceClusterer.java:116) */
+    HMKO_ERR_ASYMMETRIC = 9,      /* clinkage: asymmetric substitution matrix (the reference's cached scores become schedule dependent) */
+    HMKO_ERR_TREEIFIED = 10       /* clinkage: a HashMap bin reached the tree threshold; the bucket-order emulation is not exact */
 };
 
 /* work counters */
@@ -100,6 +103,16 @@ int hmko_greedy_cluster_bounded(int32_t n, const uint8_t* residues, const int32_
                                 int32_t* cluster_id, int32_t* member_rank,
                                 int32_t* result_order, int32_t* n_result, int32_t* n_multi,
                                 hmko_counters* counters);
+
+/* SURVEY.md 8(f) N1 -- ClinkageSequenceClusterer.cluster (ClinkageSequenceClusterer.java:43-124 with
+ * CachedClusterScorer.java:38-125 and the java.util.HashSet iteration order, see clinkage_oracle.c).  Sequences in the
+ * order the caller hands them over (Hammock.runClinkageClustering does NOT sort, Hammock.java:449-462).
+ * cluster_id[i] = Cluster.getId() of sequence i's cluster (singletons keep i + 1, merged clusters get n + 2, n + 3, ...),
+ * member_rank[i] = position in Cluster.getSequences(), result_order[0..*n_result) = ids of the returned list. */
+int hmko_clinkage_cluster(int32_t n, const uint8_t* residues, const int32_t* offsets, const int32_t* abundance,
+                          const int32_t* matrix576, int32_t threshold, int32_t max_shift, int32_t shift_penalty,
+                          int32_t* cluster_id, int32_t* member_rank, int32_t* result_order, int32_t* n_result,
+                          int64_t* nearest_searches);
 
 /* FileIOManager.java:159-216 -- fasta reader.  Returns a malloc'ed table; free with
  * hmko_fasta_free.  Sequences in first-occurrence order; abundance = sum over labels. */

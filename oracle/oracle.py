@@ -19,6 +19,7 @@ ALPHABET = "ARNDCQEGHILKMFPSTWYVBZX*"
 
 OK, ERR_SHIFT_TOO_BIG, ERR_NULL_CLUSTER, ERR_BAD_RESIDUE = 0, 1, 2, 3
 ERR_FILE_FORMAT, ERR_IO = 6, 7
+ERR_EMPTY, ERR_ASYMMETRIC, ERR_TREEIFIED = 8, 9, 10
 
 
 class Counters(C.Structure):
@@ -39,8 +40,8 @@ class _Fasta(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "hammock_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("hammock_oracle.c", "clinkage_oracle.c", "hammock_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -74,6 +75,9 @@ def lib():
         L.hmko_greedy_cluster_bounded.argtypes = [C.c_int32, u8p, i32p, i32p, i32p, C.c_int32, C.c_int32,
                                                   C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                                   i32p, i32p, i32p, i32p, i32p, C.POINTER(Counters)]
+        L.hmko_clinkage_cluster.restype = C.c_int
+        L.hmko_clinkage_cluster.argtypes = [C.c_int32, u8p, i32p, i32p, i32p, C.c_int32, C.c_int32, C.c_int32,
+                                            i32p, i32p, i32p, i32p, C.POINTER(C.c_int64)]
         L.hmko_load_fasta.restype = C.c_int
         L.hmko_load_fasta.argtypes = [C.c_char_p, C.POINTER(_Fasta), C.c_char_p, C.c_size_t]
         L.hmko_fasta_free.restype = None
@@ -190,6 +194,32 @@ def greedy_cluster(residues, offsets, abundance, matrix, threshold, max_shift, s
         int(max_p1_steps), int(max_p2_queries),
         _p(cid, C.c_int32), _p(rank, C.c_int32), _p(order, C.c_int32), C.byref(nres), C.byref(nmulti), C.byref(ctr))
     return GreedyResult(rc, cid, rank, order[:nres.value].copy(), int(nmulti.value), ctr.as_dict())
+
+
+@dataclass
+class ClinkageResult:
+    status: int
+    cluster_id: np.ndarray
+    member_rank: np.ndarray
+    result_order: np.ndarray
+    nearest_searches: int
+
+
+def clinkage_cluster(residues, offsets, abundance, matrix, threshold, max_shift, shift_penalty) -> ClinkageResult:
+    """ClinkageSequenceClusterer.cluster (clinkage_oracle.c); sequences in the caller's order"""
+    residues = np.ascontiguousarray(residues, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    abundance = np.ascontiguousarray(abundance, dtype=np.int32)
+    M = np.ascontiguousarray(matrix, dtype=np.int32).reshape(-1)
+    n = len(abundance)
+    cid = np.zeros(max(n, 1), dtype=np.int32)
+    rank = np.zeros(max(n, 1), dtype=np.int32)
+    order = np.zeros(max(n, 1), dtype=np.int32)
+    nres, ns = C.c_int32(0), C.c_int64(0)
+    rc = lib().hmko_clinkage_cluster(n, _p(residues, C.c_uint8), _p(offsets, C.c_int32), _p(abundance, C.c_int32),
+                                     _p(M, C.c_int32), int(threshold), int(max_shift), int(shift_penalty),
+                                     _p(cid, C.c_int32), _p(rank, C.c_int32), _p(order, C.c_int32), C.byref(nres), C.byref(ns))
+    return ClinkageResult(rc, cid[:n], rank[:n], order[:nres.value].copy(), int(ns.value))
 
 
 def load_fasta(path: str):
