@@ -136,6 +136,8 @@ struct SmemConfig {
 };
 
 enum { HMK_MAXTILES_PERSISTENT = 1024 };   // profile tiles a persistent bulk launch schedules (more: static grid)
+enum { HMK_FB_STRIDE = 1 << 16 };   // founders per slice of the per-length split of the cluster search
+enum { HMK_NAUX = 6 };         // auxiliary streams for launches that are independent of each other (length buckets)
 enum { HMK_NBATCHBUF = 3 };   // the batch being resolved + up to two prepared ahead
 enum { SEC_P1_SELECT = 0, SEC_P1_PARTNER, SEC_P1_CLUSTER, SEC_P1_INTRA, SEC_P1_RESOLVE, SEC_P2_SETUP, SEC_P2_FILTER,
        SEC_P2_CHECK, SEC_P2_SORT, SEC_P2_BASE, SEC_P2_ITERATE, SEC_P2_COMMIT, SEC_FINAL };
@@ -179,6 +181,9 @@ public:
         CK(cudaStreamCreateWithPriority(&st_, cudaStreamNonBlocking, prio_hi));    // resolvers, small kernels
         CK(cudaStreamCreateWithPriority(&st2_, cudaStreamNonBlocking, prio_lo));   // look-ahead partner search
         for (auto& b : bb_) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
+        for (auto& a : aux_) CK(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, prio_lo));
+        CK(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
+        for (auto& e : join_ev_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaMallocHost(&h_ctl_, sizeof(HmkCtl)));
         CK(cudaMallocHost(&h_scalars_, 16 * sizeof(int32_t)));
         CK(cudaMallocHost(&h_p2flags_, HMK_P2_CTL * sizeof(int32_t)));
@@ -201,6 +206,9 @@ public:
         if (h_p2flags_) cudaFreeHost(h_p2flags_);
         if (comm_) NcclApi::get().CommDestroy(comm_);
         for (auto& b : bb_) if (b.ready) cudaEventDestroy(b.ready);
+        for (auto& e : join_ev_) if (e) cudaEventDestroy(e);
+        if (fork_ev_) cudaEventDestroy(fork_ev_);
+        for (auto& a : aux_) if (a) cudaStreamDestroy(a);
         if (st2_) cudaStreamDestroy(st2_);
         if (st_) cudaStreamDestroy(st_);
     }
@@ -255,7 +263,7 @@ private:
     DevBuf<int32_t> d_bucket_[HMK_MAXLEN + 1];
     DevBuf<int32_t> d_sidx_, d_sb_ids_, d_sb_cnt_;
     DevBuf<uint32_t> d_pcells_, d_pops_;
-    bool fast_scalar_ = false;   // uniform length <= 12: packed scalar scorer usable
+    bool fast_scalar_ = false;   // every length <= 12: the one-at-a-time scorer works on the packed words (which carry the lengths)
     HmkScheme sc_{};
     std::vector<int32_t> h_off_;
     DevBuf<uint8_t> d_res_;
@@ -275,6 +283,8 @@ private:
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
         DevBuf<unsigned long long> gmin;   // per query: published lower bound of the kb-th best key (prunes top-k insertions)
         DevBuf<uint32_t> prof;
+        int prof_len_batch[HMK_MAXLEN + 1] = {0};   // batch for which prof_len[L] was built
+        DevBuf<int32_t> fb_ids, fb_cnt;             // founders of the cluster search split by length (mixed lengths)
         DevBuf<int32_t> sched, sched2;   // chunk / slot counters of the persistent partner-search / cluster-search launches
         // cluster search, part 1: founder hits of the clusters that existed when the batch was prepared
         DevBuf<int4> hits;
@@ -293,6 +303,8 @@ private:
     };
     BatchBuf bb_[HMK_NBATCHBUF];
     cudaStream_t st2_ = nullptr;
+    cudaStream_t aux_[HMK_NAUX] = {nullptr};
+    cudaEvent_t fork_ev_ = nullptr, join_ev_[HMK_NAUX] = {nullptr};
     void stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, int ncl_known, cudaStream_t s);
     void founder_hits(BatchBuf& bb, int from, int to, cudaStream_t s, DevBuf<int32_t>& sched);
     size_t hit_cap_ = 0;
@@ -392,7 +404,7 @@ private:
         CK(cudaStreamSynchronize(st_));
     }
     // the unrolled one-at-a-time pair scorer applies: uniform length 12, max shift 3, lane-sized matrix entries
-    bool scalar12x3() const { return fast_scalar_ && fast_ && max_len_ == HMK_MAXL1 && X_ == 3; }
+    bool scalar12x3() const { return fast_scalar_ && fast_ && min_len_ == HMK_MAXL1 && max_len_ == HMK_MAXL1 && X_ == 3; }
     int phase1();
     void phase2();
     int compact_unassigned(int32_t* out);
@@ -519,7 +531,7 @@ void Engine::upload(const hmk_greedy_in* in) {
         }
         CK(cudaStreamSynchronize(st_));
     }
-    fast_scalar_ = n_ > 0 && min_len_ == max_len_ && max_len_ >= 1 && max_len_ <= HMK_MAXL1 && X_ >= 0 && X_ < max_len_;
+    fast_scalar_ = n_ > 0 && min_len_ >= 1 && max_len_ <= HMK_MAXL1 && X_ >= 0 && X_ < min_len_;
     // validate residues + pack 5 bits/residue on the device
     words_ = max_len_ <= HMK_MAXLEN ? std::max(1, (max_len_ + HMK_MAXL1 - 1) / HMK_MAXL1) : 1;
     d_packed_.reserve((size_t)std::max(n_, 1) * words_);
@@ -655,7 +667,8 @@ void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch, int32_t* sched) con
         int total = (int)((((int64_t)want * a.nqt + sms - 1) / sms) * sms);
         want = std::max(1, total / a.nqt);
     }
-    int max_stripes = (a.ndb + threads - 1) / threads;
+    // a CTA stages a whole profile tile (up to 190 KB) before it scores anything: at least 8 block iterations per stripe
+    int max_stripes = std::max(1, a.ndb / (8 * threads));
     if (a.nqt > sms * opt.waves) {
         // more profile tiles than resident CTAs: take the stripe count (<= 8, stripes of >= 16 K items) that
         // fills the last wave best
@@ -768,7 +781,34 @@ void Engine::founder_hits(BatchBuf& bb, int from, int to, cudaStream_t s, DevBuf
     a.prof = bb.prof.p; a.nq = bb.nq;
     a.packed = d_packed_.p; a.db_ids = d_cf_.p + from; a.db_begin = 0; a.ndb = to - from;
     a.hits = bb.hits.p; a.hit_count = bb.hcount.p; a.hit_cap = (unsigned int)bb.hit_cap;
-    launch_bulk(HMK_MODE_EMIT, a, bb.qid.p, 1, s, nullptr, &sched);
+    if (!mixed_ || max_len_ > HMK_MAXL1) { launch_bulk(HMK_MODE_EMIT, a, bb.qid.p, 1, s, nullptr, &sched); return; }
+    // mixed lengths <= 12: the founders are split by length on the device (no host round trip: every bucket is launched
+    // for the upper bound `to - from` and reads its real size on the device) and each bucket runs the packed kernel on
+    // the profiles of that thread-side length -- built by the partner search of this batch, or here
+    const int cnt = to - from;
+    bb.fb_ids.reserve((size_t)(HMK_MAXL1 + 1) * HMK_FB_STRIDE); bb.fb_cnt.reserve(HMK_MAXLEN + 1);
+    for (int f0 = 0; f0 < cnt; f0 += HMK_FB_STRIDE) {       // (more founders than the bucket arrays hold: in slices)
+        const int fn = std::min<int>(HMK_FB_STRIDE, cnt - f0);
+        CK(cudaMemsetAsync(bb.fb_cnt.p, 0, sizeof(int32_t) * (HMK_MAXLEN + 1), s));
+        hmk_bucket_by_length<<<(fn + 255) / 256, 256, 0, s>>>(d_cf_.p + from + f0, fn, d_off_.p, HMK_FB_STRIDE, bb.fb_ids.p, bb.fb_cnt.p);
+        launches_++;
+        for (int L = min_len_; L <= max_len_; L++) {
+            if (h_bucket_[L].empty()) continue;
+            const HmkScheme sch = scheme_for(L);
+            auto& pf = bb.prof_len[L];
+            if (bb.prof_len_batch[L] != bb.batch_id) {      // no later singleton of this length: the partner search skipped it
+                pf.reserve((size_t)HMK_MAXBATCH * sch.prof_words);
+                bb.pcells[L].reserve(HMK_MAXBATCH); bb.pops[L].reserve(HMK_MAXBATCH);
+                launch_profiles(HMK_PROF_QUERY, bb.qid.p, bb.nq, pf.p, sch, s, bb.pcells[L].p, bb.pops[L].p);
+                bb.prof_len_batch[L] = bb.batch_id;
+            }
+            HmkBulkArgs b = a;
+            b.prof = pf.p; b.prof_cells = bb.pcells[L].p; b.prof_ops = bb.pops[L].p;
+            b.db_ids = bb.fb_ids.p + (size_t)L * HMK_FB_STRIDE; b.ndb = fn; b.ndb_dev = bb.fb_cnt.p + L;
+            plan_bulk(b, &sch);
+            launch_planned(HMK_MODE_EMIT, b, &sch, bb.qid.p, 1, s);
+        }
+    }
 }
 
 void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32_t* start_after, int ncl_known, cudaStream_t s) {
@@ -829,14 +869,26 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         } else {
             const size_t slots = (size_t)total_stripes * nq;
             bb.tk_key.reserve(slots * kb); bb.tk_cnt.reserve(slots); bb.tk_ovf.reserve(slots);
+            // the buckets are independent (own profiles, own output slots): fork them over the auxiliary streams so
+            // that the small launches of a 100 k-sequence input fill the GPU together, then join
+            CK(cudaEventRecord(fork_ev_, s));
+            int k = 0;
             for (auto& p : plans) {
+                cudaStream_t as = aux_[k % HMK_NAUX];
+                if (k < HMK_NAUX) CK(cudaStreamWaitEvent(as, fork_ev_, 0));
                 auto& pf = bb.prof_len[p.L];
                 pf.reserve((size_t)HMK_MAXBATCH * p.sc.prof_words);
                 bb.pcells[p.L].reserve(HMK_MAXBATCH); bb.pops[p.L].reserve(HMK_MAXBATCH);
-                launch_profiles(HMK_PROF_QUERY, bb.qid.p, nq, pf.p, p.sc, s, bb.pcells[p.L].p, bb.pops[p.L].p);
+                launch_profiles(HMK_PROF_QUERY, bb.qid.p, nq, pf.p, p.sc, as, bb.pcells[p.L].p, bb.pops[p.L].p);
+                bb.prof_len_batch[p.L] = bb.batch_id;
                 p.a.prof = pf.p; p.a.prof_cells = bb.pcells[p.L].p; p.a.prof_ops = bb.pops[p.L].p;
                 p.a.tk_key = bb.tk_key.p; p.a.tk_cnt = bb.tk_cnt.p; p.a.tk_ovf = bb.tk_ovf.p;
-                launch_planned(HMK_MODE_TOPK, p.a, &p.sc, bb.qid.p, 1, s);
+                launch_planned(HMK_MODE_TOPK, p.a, &p.sc, bb.qid.p, 1, as);
+                k++;
+            }
+            for (int j = 0; j < std::min(k, (int)HMK_NAUX); j++) {
+                CK(cudaEventRecord(join_ev_[j], aux_[j]));
+                CK(cudaStreamWaitEvent(s, join_ev_[j], 0));
             }
             hmk_topk_merge<<<(nq * 32 + 255) / 256, 256, 0, s>>>(nq, total_stripes, kb, bb.tk_key.p, bb.tk_cnt.p, bb.tk_ovf.p,
                                                                  bb.bk_key.p, bb.bk_cnt.p, bb.bk_ovf.p);

@@ -216,6 +216,7 @@ struct HmkBulkArgs {
     // (CTA x tile engagements) handed out for tile t; nstripes = slots per query in tk_* (>= CTAs)
     int32_t* sched;
     int32_t nchunks;
+    const int32_t* ndb_dev;   // optional: the real number of thread-side items (<= ndb, which then only sizes the grid)
 };
 
 // ---------------------------------------------------------------- hit handling
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_fast(const __gri
     hmk_mbar_wait(bar, 0);
 
     const int i_begin = stripe * a.chunk;
-    const int i_end = min(a.ndb, i_begin + a.chunk);
+    const int i_end = min(a.ndb_dev ? min(a.ndb, __ldg(a.ndb_dev)) : a.ndb, i_begin + a.chunk);
     unsigned long long scored = 0;
     const uint32_t topmask = a.sc.lane16 ? 0x80008000u : 0x80808080u;
     const int32_t dec = a.sc.T - a.sc.half;
@@ -1000,22 +1001,35 @@ __device__ __forceinline__ void hmk_load_matrix_smem(int32_t* sM, const int32_t*
     __syncthreads();
 }
 
-__device__ __forceinline__ int32_t hmk_scalar_score(const HmkState& S, const HmkScalar& sc, int32_t member, int32_t query) {
-    if (!sc.packed) return hmk_state_score(S, member, query);
-    const uint64_t wm = sc.packed[member], wq = sc.packed[query];
-    const int L = sc.L;
+// S(seq1 = member, seq2 = query) from two packed words that carry their lengths (<= 12 residues each): the reference's
+// roles (ShiftedScorer.java:51-57: the shorter sequence slides, equal lengths make seq2 the shorter one) and orientation
+// M[shorter][longer] (:71,75,110), Java-int arithmetic.
+__device__ __forceinline__ int32_t hmk_packed_pair_score(uint64_t w1, uint64_t w2, const int32_t* sM, int X, int P) {
+    const int len1 = (int)(w1 >> 60), len2 = (int)(w2 >> 60);
+    uint64_t ws, wl;
+    int ls, ll;
+    if (len1 >= len2) { ws = w2; ls = len2; wl = w1; ll = len1; }
+    else              { ws = w1; ls = len1; wl = w2; ll = len2; }
+    const int d = ll - ls;
     int32_t best = HMK_JMIN;
-    for (int k = -S.X; k <= S.X; k++) {       // equal lengths: shorter = query (second argument)
-        const int j0 = k > 0 ? k : 0, j1 = k < 0 ? L + k : L;
+    for (int k = -X; k <= X + d; k++) {
+        const int j0 = k > 0 ? k : 0, j1 = ls + k < ll ? ls + k : ll;      // longer index j pairs with shorter index j - k
         int32_t v = 0;
         for (int j = j0; j < j1; j++) {
-            const uint32_t rq = (uint32_t)(wq >> (5 * (j - k))) & 31u, rm = (uint32_t)(wm >> (5 * j)) & 31u;
-            v = hmk_wadd(v, sc.sM[rq * HMK_NRES + rm]);
+            const uint32_t rs = (uint32_t)(ws >> (5 * (j - k))) & 31u, rl = (uint32_t)(wl >> (5 * j)) & 31u;
+            v = hmk_wadd(v, sM[rs * HMK_NRES + rl]);
         }
-        v = hmk_wadd(v, hmk_wmul(2 * (k < 0 ? -k : k), S.P));
+        v = hmk_wadd(v, hmk_wmul(d, P));
+        if (k < 0) v = hmk_wadd(v, hmk_wmul(-2 * k, P));
+        if (k > d) v = hmk_wadd(v, hmk_wmul(2 * (k - d), P));
         if (v > best) best = v;
     }
     return best;
+}
+
+__device__ __forceinline__ int32_t hmk_scalar_score(const HmkState& S, const HmkScalar& sc, int32_t member, int32_t query) {
+    if (!sc.packed) return hmk_state_score(S, member, query);
+    return hmk_packed_pair_score(sc.packed[member], sc.packed[query], sc.sM, S.X, S.P);
 }
 
 // S(member, query) with both sequences given as packed words: uniform length 12, max shift 3, matrix in shared memory.
@@ -2166,6 +2180,9 @@ __global__ void hmk_pack_sequences(int n, int words, const uint8_t* __restrict__
         if (r >= HMK_NRES) { atomicExch(bad, 1); r = 0; }
         if (j < HMK_MAXL1 * words) w[j / HMK_MAXL1] |= (uint64_t)r << (5 * (j % HMK_MAXL1));
     }
+    // one-word sequences (<= 12 residues use bits 0..59) carry their length in bits 60..63: the one-at-a-time scorer
+    // then needs nothing but the two words (the bulk kernels only ever look at the residue fields)
+    if (words == 1) w[0] |= (uint64_t)(len <= HMK_MAXL1 ? len : 0) << 60;
     for (int k = 0; k < words; k++) packed[(size_t)i * words + k] = w[k];
 }
 

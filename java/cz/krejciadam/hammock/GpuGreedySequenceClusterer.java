@@ -48,26 +48,38 @@ public class GpuGreedySequenceClusterer implements SequenceClusterer {
             JAVA_INT.withName("n_result"), JAVA_INT.withName("n_multi"), JAVA_INT.withName("error_step"),
             MemoryLayout.paddingLayout(4));
 
-    private static final MethodHandle HMK_GREEDY_CLUSTER;
+    private static final MethodHandle HMK_GREEDY_CLUSTER, HMK_GREEDY_CLUSTER_MULTI;
 
     static {
         System.loadLibrary("hammock_b200");          // libhammock_b200.so on java.library.path
         HMK_GREEDY_CLUSTER = Linker.nativeLinker().downcallHandle(
                 SymbolLookup.loaderLookup().find("hmk_greedy_cluster").orElseThrow(),
                 FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
+        /* int hmk_greedy_cluster_multi(in, out, const int32_t* devices, int32_t n_gpus, errbuf, errlen): the same call
+         * on several GPUs of this JVM -- worker threads and the NCCL communicator live inside the library */
+        HMK_GREEDY_CLUSTER_MULTI = Linker.nativeLinker().downcallHandle(
+                SymbolLookup.loaderLookup().find("hmk_greedy_cluster_multi").orElseThrow(),
+                FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
     }
 
     private final int[][] scoringMatrix;
-    private final int shiftPenalty, maxShift, threshold, maxClusters, device;
+    private final int shiftPenalty, maxShift, threshold, maxClusters;
+    private final int[] devices;
 
     public GpuGreedySequenceClusterer(int[][] scoringMatrix, int shiftPenalty, int maxShift,
                                       int threshold, int maxClusters, int device) {
+        this(scoringMatrix, shiftPenalty, maxShift, threshold, maxClusters, new int[]{device});
+    }
+
+    /** several GPUs of this machine, e.g. {0, 1, 2, 3, 4, 5, 6, 7}: identical result, the partner search is sharded */
+    public GpuGreedySequenceClusterer(int[][] scoringMatrix, int shiftPenalty, int maxShift,
+                                      int threshold, int maxClusters, int[] devices) {
         this.scoringMatrix = scoringMatrix;
         this.shiftPenalty = shiftPenalty;
         this.maxShift = maxShift;
         this.threshold = threshold;
         this.maxClusters = maxClusters;
-        this.device = device;
+        this.devices = devices.clone();
     }
 
     @Override
@@ -113,7 +125,13 @@ public class GpuGreedySequenceClusterer implements SequenceClusterer {
 
             int rc;
             try {
-                rc = (int) HMK_GREEDY_CLUSTER.invokeExact(in, out, device, err, 512L);
+                if (devices.length == 1) {
+                    rc = (int) HMK_GREEDY_CLUSTER.invokeExact(in, out, devices[0], err, 512L);
+                } else {
+                    MemorySegment devs = arena.allocate(JAVA_INT, devices.length);
+                    for (int i = 0; i < devices.length; i++) devs.setAtIndex(JAVA_INT, i, devices[i]);
+                    rc = (int) HMK_GREEDY_CLUSTER_MULTI.invokeExact(in, out, devs, devices.length, err, 512L);
+                }
             } catch (Throwable t) {
                 throw new ExecutionException(t);
             }
