@@ -119,15 +119,19 @@ struct DevBuf {
     }
 };
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: the sizes already
-// configured are tracked per Engine (one Engine = one device), never in process-wide statics, so a host
-// that drives device 0 and then device 1 from one process configures both.
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel, and setting it REPLACES the value:
+// the largest size configured so far is tracked per (device, kernel) for the whole process, under a mutex -- not in
+// per-kernel statics (a second device would never be configured) and not per context (a context that needs less would
+// lower the limit under another context of the same device).
 struct SmemConfig {
-    std::map<const void*, size_t> done;
+    int device = 0;
     template <class K>
     void ensure(K kernel, size_t smem) {
+        static std::mutex mu;
+        static std::map<std::pair<int, const void*>, size_t> done;
         const void* f = reinterpret_cast<const void*>(kernel);
-        size_t& have = done[f];
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = done[{device, f}];
         if (smem > have) {
             CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             have = smem;
@@ -156,6 +160,8 @@ struct Options {
     int64_t force_generic = 0;  // 1: never use the packed SWAR kernel
     int64_t profile = 0;        // 1: time every bulk launch with CUDA events
     int64_t p2_window = 1 << 16;  // phase-2 queries resolved per window
+    int64_t min_iters = 1;        // static grids: block iterations a stripe must at least have
+    int64_t bucket_aux = 1;       // mixed lengths: run the per-length launches of a batch on separate streams
     int64_t reserve = 4;          // SMs the look-ahead bulk launches leave to the main stream (resolver + small kernels)
     int64_t persistent = 1;       // 1: filter kernel as one CTA per SM taking database chunks dynamically; 0: static grid
     int64_t p2_first = 0;         // queries in the first phase-2 window (0 = automatic)
@@ -172,6 +178,7 @@ public:
                             "); libhammock_b200 has no CPU fallback");
         if (device < 0 || device >= count) throw CudaError("invalid CUDA device index");
         CK(cudaSetDevice(device_));
+        smem_cfg_.device = device_;
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device_));
         sm_count_ = prop.multiProcessorCount;
@@ -668,7 +675,7 @@ void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch, int32_t* sched) con
         want = std::max(1, total / a.nqt);
     }
     // a CTA stages a whole profile tile (up to 190 KB) before it scores anything: at least 8 block iterations per stripe
-    int max_stripes = std::max(1, a.ndb / (8 * threads));
+    int max_stripes = std::max<int64_t>(1, a.ndb / (std::max<int64_t>(1, opt.min_iters) * threads));
     if (a.nqt > sms * opt.waves) {
         // more profile tiles than resident CTAs: take the stripe count (<= 8, stripes of >= 16 K items) that
         // fills the last wave best
@@ -874,8 +881,8 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
             CK(cudaEventRecord(fork_ev_, s));
             int k = 0;
             for (auto& p : plans) {
-                cudaStream_t as = aux_[k % HMK_NAUX];
-                if (k < HMK_NAUX) CK(cudaStreamWaitEvent(as, fork_ev_, 0));
+                cudaStream_t as = opt.bucket_aux ? aux_[k % HMK_NAUX] : s;
+                if (opt.bucket_aux && k < HMK_NAUX) CK(cudaStreamWaitEvent(as, fork_ev_, 0));
                 auto& pf = bb.prof_len[p.L];
                 pf.reserve((size_t)HMK_MAXBATCH * p.sc.prof_words);
                 bb.pcells[p.L].reserve(HMK_MAXBATCH); bb.pops[p.L].reserve(HMK_MAXBATCH);
@@ -886,7 +893,7 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
                 launch_planned(HMK_MODE_TOPK, p.a, &p.sc, bb.qid.p, 1, as);
                 k++;
             }
-            for (int j = 0; j < std::min(k, (int)HMK_NAUX); j++) {
+            for (int j = 0; opt.bucket_aux && j < std::min(k, (int)HMK_NAUX); j++) {
                 CK(cudaEventRecord(join_ev_[j], aux_[j]));
                 CK(cudaStreamWaitEvent(s, join_ev_[j], 0));
             }
@@ -914,7 +921,12 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
     const int ib_stride = (nq + 3) & ~3, pd_stride = (nq * kb + 3) & ~3, nw = (nq + 31) / 32;
     bb.ib.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH + 4)); bb.ibm.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH / 32)); bb.ibm2.reserve((size_t)HMK_MAXBATCH * (HMK_MAXBATCH / 32));
     bb.pcand.reserve((size_t)nq * kb); bb.pd.reserve((size_t)nq * (pd_stride + 4));
-    {
+    const bool dense_packed = mixed_ && fast_scalar_;      // mixed lengths <= 12: one thread per pair on the packed words
+    if (dense_packed) {
+        hmk_dense_packed<<<std::min(sm_count_ * 8, (nq * nq + 255) / 256), 256, 0, s>>>(d_packed_.p, bb.qid.p, nq, bb.qid.p, nq, d_M_.p, X_, P_,
+                                                                                       bb.ib.p, ib_stride, d_pairctr_.p);
+        launches_++;
+    } else {
         HmkBulkArgs d{};
         d.prof = bb.prof.p; d.nq = nq;
         d.packed = d_packed_.p; d.db_ids = bb.qid.p; d.db_begin = 0; d.ndb = nq;
@@ -930,11 +942,17 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         hmk_partner_ids<<<(npc + 127) / 128, 128, 0, s>>>(nq, kb, bb.bk_key.p, bb.bk_cnt.p,
                                                           identity_rank_ ? nullptr : d_id_of_rank_.p, bb.qid.p, bb.pcand.p);
         launches_++;
-        HmkBulkArgs d{};
-        d.prof = bb.prof.p; d.nq = nq;
-        d.packed = d_packed_.p; d.db_ids = bb.pcand.p; d.db_begin = 0; d.ndb = npc;
-        d.dense = bb.pd.p; d.dense_stride = pd_stride;
-        launch_bulk(HMK_MODE_DENSE, d, bb.qid.p, 1, s);
+        if (dense_packed) {
+            hmk_dense_packed<<<std::min(sm_count_ * 8, (nq * npc + 255) / 256), 256, 0, s>>>(d_packed_.p, bb.qid.p, nq, bb.pcand.p, npc, d_M_.p, X_,
+                                                                                            P_, bb.pd.p, pd_stride, d_pairctr_.p);
+            launches_++;
+        } else {
+            HmkBulkArgs d{};
+            d.prof = bb.prof.p; d.nq = nq;
+            d.packed = d_packed_.p; d.db_ids = bb.pcand.p; d.db_begin = 0; d.ndb = npc;
+            d.dense = bb.pd.p; d.dense_stride = pd_stride;
+            launch_bulk(HMK_MODE_DENSE, d, bb.qid.p, 1, s);
+        }
     }
     CK(cudaGetLastError());
     // cluster search, part 1 (state independent as well: founders never change): the clusters that exist now.  The ones
@@ -1811,6 +1829,7 @@ int hmk_set_option(hmk_ctx* ctx, const char* name, int64_t value) {
         {"p2_window", &o.p2_window, 1, 1 << 24},
         {"xhit_cap", &o.xhit_cap, 0, (int64_t)1 << 30}, {"p2_first", &o.p2_first, 0, 1 << 24},
         {"persistent", &o.persistent, 0, 1},        {"reserve", &o.reserve, 1, 64},
+        {"min_iters", &o.min_iters, 1, 64},         {"bucket_aux", &o.bucket_aux, 0, 1},
     };
     for (const Knob& k : knobs) {
         if (s != k.name) continue;

@@ -1055,6 +1055,24 @@ __device__ __forceinline__ void hmk_qrow12(uint64_t wq, int32_t (&qrow)[HMK_MAXL
     for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
 }
 
+// Dense table of pair scores for sequences of mixed lengths <= 12 straight from the packed words (which carry their
+// lengths): dense[t * stride + i] = S(seq1 = db item i, seq2 = profile-side sequence t).  One thread per pair; used for
+// the small intra-batch tables of mixed-length inputs, where the per-length packed kernel would need one launch per
+// (length, table) and the generic byte kernel is several times slower.
+__global__ void __launch_bounds__(256) hmk_dense_packed(const uint64_t* __restrict__ packed, const int32_t* __restrict__ prof_ids, int nq,
+                                                        const int32_t* __restrict__ db_ids, int ndb, const int32_t* __restrict__ M,
+                                                        int X, int P, int32_t* __restrict__ dense, int stride,
+                                                        unsigned long long* pair_counter) {
+    __shared__ int32_t sM[HMK_NRES * HMK_NRES];
+    hmk_load_matrix_smem(sM, M);
+    const size_t total = (size_t)nq * ndb;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e / ndb), i = (int)(e % ndb);
+        dense[(size_t)t * stride + i] = hmk_packed_pair_score(packed[db_ids[i]], packed[prof_ids[t]], sM, X, P);
+    }
+    if (pair_counter && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pair_counter, (unsigned long long)total);
+}
+
 // ---------------------------------------------------------------- member check (complete linkage)
 // One thread per founder hit: does the query also score >= T against every other current
 // member of that cluster?  (ClinkageClusterScorer.java:30-49; early exit keeps it cheap.)

@@ -114,6 +114,29 @@ def test_two_contexts_from_two_threads_on_one_device(blosum62):
     assert not errs, errs
 
 
+def test_a_small_context_does_not_lower_another_contexts_shared_memory_limit(blosum62):
+    """cudaFuncSetAttribute REPLACES the opt-in shared-memory size of a kernel on the device: a context that needs little
+    must not undercut a context that configured a full tile before (the limit is tracked per device, process-wide)"""
+    big, (T, X, K) = _workload(30000, 12, 12, seed=61)
+    small, (Ts, Xs, Ks) = _workload(40, 12, 12, seed=62)
+    Rb, Rs = _oracle(big, blosum62, T, X, 0, K), _oracle(small, blosum62, Ts, Xs, 0, Ks)
+    a = hb.GreedyContext(0)
+    b = hb.GreedyContext(0)
+    try:
+        for _ in range(2):
+            a.upload(big["residues"], big["offsets"], big["abundance"], blosum62, T, X, 0, K)
+            a.run()
+            assert _same(Rb, a.download())
+            b.upload(small["residues"], small["offsets"], small["abundance"], blosum62, Ts, Xs, 0, Ks)
+            rc, _ = b.run_status()
+            assert rc == Rs.status
+            if rc == 0:
+                assert _same(Rs, b.download())
+    finally:
+        a.close()
+        b.close()
+
+
 def test_kept_hit_overflow_is_reported_and_repaired(blosum62):
     """an overflow of the buffer that keeps the phase-1 hits for phase 2 must show in hmk_stats.flags, give the same
     result through the separate founder pass, and the next run on the context must size the buffer right"""
