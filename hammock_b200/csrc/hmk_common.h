@@ -24,13 +24,15 @@ HMK_HD int32_t hmk_wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (
 // (ClinkageClusterScorer.java:38).  Formulated per diagonal k = (position in longer) -
 // (position in shorter); equal lengths make the SECOND argument the "shorter" one.
 // Requires max_shift < shorter length (checked by the caller -> status 1).
-HMK_HD int32_t hmk_pair_score(const uint8_t* seq1, int len1, const uint8_t* seq2, int len2,
-                              const int32_t* M, int X, int P) {
+// `st1` / `st2`: element strides of the two residue arrays (1 = contiguous; the generic bulk kernel keeps the thread-side
+// sequences position-major in shared memory, stride = block size).
+HMK_HD int32_t hmk_pair_score_strided(const uint8_t* seq1, int st1, int len1, const uint8_t* seq2, int st2, int len2,
+                                      const int32_t* M, int X, int P) {
     const uint8_t* s;
     const uint8_t* l;
-    int ls, ll;
-    if (len1 >= len2) { s = seq2; ls = len2; l = seq1; ll = len1; }
-    else              { s = seq1; ls = len1; l = seq2; ll = len2; }
+    int ls, ll, ss, sl;
+    if (len1 >= len2) { s = seq2; ls = len2; ss = st2; l = seq1; ll = len1; sl = st1; }
+    else              { s = seq1; ls = len1; ss = st1; l = seq2; ll = len2; sl = st2; }
     const int d = ll - ls;
     int32_t best = HMK_JMIN;
     for (int k = -X; k <= X + d; k++) {
@@ -38,13 +40,17 @@ HMK_HD int32_t hmk_pair_score(const uint8_t* seq1, int len1, const uint8_t* seq2
         int j0 = k > 0 ? k : 0;
         int j1 = ls + k < ll ? ls + k : ll;
         int32_t sc = 0;
-        for (int j = j0; j < j1; j++) sc = hmk_wadd(sc, M[s[j - k] * HMK_NRES + l[j]]);
+        for (int j = j0; j < j1; j++) sc = hmk_wadd(sc, M[s[(j - k) * ss] * HMK_NRES + l[j * sl]]);
         sc = hmk_wadd(sc, hmk_wmul(d, P));
         if (k < 0) sc = hmk_wadd(sc, hmk_wmul(-2 * k, P));
         if (k > d) sc = hmk_wadd(sc, hmk_wmul(2 * (k - d), P));
         if (sc > best) best = sc;
     }
     return best;
+}
+HMK_HD int32_t hmk_pair_score(const uint8_t* seq1, int len1, const uint8_t* seq2, int len2,
+                              const int32_t* M, int X, int P) {
+    return hmk_pair_score_strided(seq1, 1, len1, seq2, 1, len2, M, X, P);
 }
 
 // cells / shifts summed by one pair score -- work accounting only

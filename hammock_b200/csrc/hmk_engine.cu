@@ -319,7 +319,8 @@ private:
     DevBuf<int32_t> d_qid_, d_nq_,
         d_ac_cnt_, d_ac_slot_, d_ac_score_, d_dirty_a_;
     DevBuf<int4> d_ac_full_, d_ac_best_;
-    DevBuf<int32_t> d_sched_, d_clD_, d_cli_;
+    DevBuf<int32_t> d_sched_, d_clD_, d_cli_, d_lsort_;
+    bool lsort_ = false;
     // phase-1 partner-search hits kept for phase 2 (opt.reuse): buffer, 64-bit counters [0] appended, [1] valid
     DevBuf<int4> d_xhits_;
     DevBuf<unsigned long long> d_xcount_;
@@ -538,6 +539,18 @@ void Engine::upload(const hmk_greedy_in* in) {
         }
         CK(cudaStreamSynchronize(st_));
     }
+    // generic kernel on lengths that differ: the thread side is walked in (length, id) order, so that the lanes of a warp
+    // run the same loop bounds
+    lsort_ = !fast_ && !mixed_ && n_ > 0 && min_len_ != max_len_;
+    if (lsort_) {
+        std::vector<int32_t> ids(n_);
+        std::iota(ids.begin(), ids.end(), 0);
+        const int32_t* o = h_off_.data();
+        std::stable_sort(ids.begin(), ids.end(), [o](int32_t a, int32_t b) { return o[a + 1] - o[a] < o[b + 1] - o[b]; });
+        d_lsort_.reserve(n_);
+        CK(cudaMemcpyAsync(d_lsort_.p, ids.data(), sizeof(int32_t) * n_, cudaMemcpyHostToDevice, st_));
+        CK(cudaStreamSynchronize(st_));
+    }
     fast_scalar_ = n_ > 0 && min_len_ >= 1 && max_len_ <= HMK_MAXL1 && X_ >= 0 && X_ < min_len_;
     // validate residues + pack 5 bits/residue on the device
     words_ = max_len_ <= HMK_MAXLEN ? std::max(1, (max_len_ + HMK_MAXL1 - 1) / HMK_MAXL1) : 1;
@@ -649,8 +662,13 @@ static void launch_generic_mode(SmemConfig& cfg, const HmkGenericArgs& g, int gr
 // the profile tile fills shared memory)
 void Engine::plan_bulk(HmkBulkArgs& a, const HmkScheme* sch, int32_t* sched) const {
     const int threads = sch ? (sch->long_layout ? HMK_LONG_THREADS : HMK_BULK_THREADS) : HMK_GENERIC_THREADS;
-    const int qmax = sch ? qt_max(*sch) : 128;
     const int sms = plan_sms_ > 0 ? plan_sms_ : sm_count_;
+    int qmax = sch ? qt_max(*sch) : 128;
+    if (!sch) {     // generic kernel: a thread scores its item against the whole tile, one pair after the other -- small
+                    // databases get small tiles, so that there are about two CTAs per SM instead of a few long threads
+        const int64_t blocks = (a.ndb + threads - 1) / threads;
+        qmax = (int)std::max<int64_t>(8, std::min<int64_t>(128, (int64_t)a.nq * blocks / (2 * sms)));
+    }
     a.nqt = (a.nq + qmax - 1) / qmax;
     a.qt = (a.nq + a.nqt - 1) / a.nqt;
     a.sched = nullptr; a.nchunks = 0;
@@ -714,8 +732,10 @@ void Engine::launch_planned(int mode, HmkBulkArgs a, const HmkScheme* sch, const
         HmkGenericArgs g;
         g.b = a; g.prof_ids = prof_ids; g.prof_is_query = prof_is_query;
         g.res = d_res_.p; g.off = d_off_.p; g.M = d_M_.p; g.maxlen = std::max(max_len_, 1);
+        g.db_smem = g.maxlen <= 128 ? 1 : 0;
         size_t smem = HMK_NRES * HMK_NRES * 4 + hmk_carve_bytes(a.qt, a.kb, HMK_GENERIC_THREADS, true) +
-                      (size_t)a.qt * 4 + (size_t)a.qt * g.maxlen + 16;
+                      (size_t)a.qt * 4 + (((size_t)a.qt * g.maxlen + 15) & ~(size_t)15) +
+                      (g.db_smem ? (size_t)g.maxlen * HMK_GENERIC_THREADS : 0) + 16;
         if (mode == HMK_MODE_TOPK) launch_generic_mode<HMK_MODE_TOPK>(smem_cfg_, g, grid, smem, s);
         else if (mode == HMK_MODE_EMIT) launch_generic_mode<HMK_MODE_EMIT>(smem_cfg_, g, grid, smem, s);
         else launch_generic_mode<HMK_MODE_DENSE>(smem_cfg_, g, grid, smem, s);
@@ -842,8 +862,12 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
         a.prof = bb.prof.p;
         // this rank's stripe of the later singletons (the whole range on one GPU)
         const int64_t span = (int64_t)n_ - db_from;
-        const int lo = db_from + (int)(span * rank_ / world_), hi = db_from + (int)(span * (rank_ + 1) / world_);
+        int lo = db_from + (int)(span * rank_ / world_), hi = db_from + (int)(span * (rank_ + 1) / world_);
         a.db_ids = nullptr; a.db_begin = lo; a.ndb = hi - lo;
+        if (lsort_) {       // the whole (length, id)-ordered list, striped across the ranks; ids before db_from are skipped
+            lo = (int)((int64_t)n_ * rank_ / world_); hi = (int)((int64_t)n_ * (rank_ + 1) / world_);
+            a.db_ids = d_lsort_.p + lo; a.db_begin = 0; a.ndb = hi - lo; a.db_min_id = db_from;
+        }
         if (a.ndb > 0) launch_bulk(HMK_MODE_TOPK, a, bb.qid.p, 1, s, &bb);
         else {
             CK(cudaMemsetAsync(bb.bk_cnt.p, 0, sizeof(int32_t) * nq, s));
@@ -1018,7 +1042,7 @@ int Engine::phase1() {
         CK(cudaMemsetAsync(d_ac_cnt_.p, 0, sizeof(int32_t) * nq, st_));
         if (ncl > 0) {
             if (ncl > cb.ncl_ahead) {
-                plan_sms_ = reserve > 1 ? reserve - 1 : 0;      // while a prepared partner search holds the other SMs
+                plan_sms_ = (fast_ && reserve > 1) ? reserve - 1 : 0;      // while a prepared partner search holds the other SMs
                 founder_hits(cb, cb.ncl_ahead, ncl, st_, d_sched_);
                 plan_sms_ = 0;
             }

@@ -217,6 +217,7 @@ struct HmkBulkArgs {
     int32_t* sched;
     int32_t nchunks;
     const int32_t* ndb_dev;   // optional: the real number of thread-side items (<= ndb, which then only sizes the grid)
+    int32_t db_min_id;        // generic kernel with a length-sorted id list: ids below this are not scored at all
 };
 
 // ---------------------------------------------------------------- hit handling
@@ -857,6 +858,7 @@ struct HmkGenericArgs {
     const int32_t* off;
     const int32_t* M;
     int32_t maxlen;
+    int32_t db_smem;      // 1: the thread-side residues are staged in shared memory ([maxlen][threads] fits)
 };
 
 #define HMK_GENERIC_THREADS 256
@@ -877,6 +879,10 @@ __global__ void __launch_bounds__(HMK_GENERIC_THREADS) hmk_bulk_generic(const __
     o += hmk_carve_bytes(a.qt, a.kb, HMK_GENERIC_THREADS, true);
     int32_t* slen = reinterpret_cast<int32_t*>(smem_raw + o); o += (size_t)a.qt * 4;
     uint8_t* sres = smem_raw + o;   // [qt][maxlen]
+    o += (((size_t)a.qt * g.maxlen + 15) & ~(size_t)15);
+    // the thread-side sequences of the current iteration, position-major ([j][thread]): the inner loops then read shared
+    // memory only, conflict free, instead of one global byte per cell and lane
+    uint8_t* sdb = smem_raw + o;    // [maxlen][HMK_GENERIC_THREADS]
     for (int i = threadIdx.x; i < HMK_NRES * HMK_NRES; i += blockDim.x) sM[i] = g.M[i];
     for (int t = threadIdx.x; t < qn; t += blockDim.x) {
         int32_t id = g.prof_ids[q0 + t];
@@ -893,17 +899,24 @@ __global__ void __launch_bounds__(HMK_GENERIC_THREADS) hmk_bulk_generic(const __
         const int i = ib + (threadIdx.x & 31);
         bool valid = i < i_end;
         const int32_t id = valid ? (a.db_ids ? a.db_ids[i] : a.db_begin + i) : 0;
-        if (valid && a.slot && a.slot[id] >= 0) valid = false;
+        if (valid && (id < a.db_min_id || (a.slot && a.slot[id] >= 0))) valid = false;
         if (!__any_sync(0xffffffffu, valid)) continue;
         const uint8_t* dres = g.res + g.off[id];
         const int dlen = valid ? g.off[id + 1] - g.off[id] : 0;
+        uint8_t* mine = sdb + threadIdx.x;
+        if (g.db_smem) {
+            for (int j = 0; j < dlen; j++) mine[(size_t)j * HMK_GENERIC_THREADS] = dres[j];
+            __syncwarp();
+        }
+        const uint8_t* dseq = g.db_smem ? mine : dres;
+        const int dst = g.db_smem ? HMK_GENERIC_THREADS : 1;
         if (valid) scored += qn;
         for (int t = 0; t < qn; t++) {
             const uint8_t* pres = sres + (size_t)t * g.maxlen;
             int32_t s = 0;
             if (valid)
-                s = g.prof_is_query ? hmk_pair_score(dres, dlen, pres, slen[t], sM, a.sc.X, a.sc.P)
-                                    : hmk_pair_score(pres, slen[t], dres, dlen, sM, a.sc.X, a.sc.P);
+                s = g.prof_is_query ? hmk_pair_score_strided(dseq, dst, dlen, pres, 1, slen[t], sM, a.sc.X, a.sc.P)
+                                    : hmk_pair_score_strided(pres, 1, slen[t], dseq, dst, dlen, sM, a.sc.X, a.sc.P);
             __syncwarp();
             if (MODE == HMK_MODE_DENSE) { if (valid) a.dense[(size_t)(q0 + t) * a.dense_stride + i] = s; }
             else hmk_queue_push<MODE>(a, tk, q0, hq, valid && s >= a.sc.T, t, s, i);

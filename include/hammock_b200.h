@@ -162,7 +162,7 @@ int hmk_get_section_ms(hmk_ctx* ctx, double* out, int n);
  *   qt, waves  profiles per shared-memory tile (0 = as many as fit), grid waves per launch
  *   reserve    SMs the look-ahead bulk launches leave free for the main stream (resolver + small kernels; default 4)
  *   min_iters, bucket_aux   static grids: block iterations per stripe at least; mixed lengths: per-length launches on separate streams
- *   persistent 1 = the filter kernel runs as one CTA per SM taking database chunks dynamically (default), 0 = static grid
+ *   persistent  1 = the filter kernel runs as one CTA per SM taking database chunks dynamically (default), 0 = static grid
  *   p2_chunk, p2_window, hit_cap   phase-2 chunking / window size / initial hit-buffer size
  *   p2_first   queries in the first phase-2 window (0 = automatic; later windows grow towards p2_window)
  *   xhit_cap   entries of the buffer that keeps the phase-1 hits for phase 2 (0 = automatic: what the last run on this
