@@ -286,7 +286,7 @@ private:
     // ---- phase-1 per-batch buffers, double buffered: while batch i is resolved on the main stream the
     // partner search of batch i+1 already runs on the side stream
     struct BatchBuf {
-        DevBuf<int32_t> qid, nq_dev, tk_cnt, tk_ovf, bk_cnt, bk_ovf, gk_cnt, gk_ovf;
+        DevBuf<int32_t> qid, gqid, nq_dev, tk_cnt, tk_ovf, bk_cnt, bk_ovf, gk_cnt, gk_ovf;
         DevBuf<uint64_t> tk_key, bk_key, gk_key;
         DevBuf<unsigned long long> gmin;   // per query: published lower bound of the kb-th best key (prunes top-k insertions)
         DevBuf<uint32_t> prof;
@@ -846,6 +846,15 @@ void Engine::stage_partner_search(BatchBuf& bb, int nq, int db_from, const int32
     hmk_select_queries<<<1, 1024, 0, s>>>(d_slot_.p, n_, d_ctl_.p, start_after, nq, bb.qid.p, bb.nq_dev.p);
     CK(cudaGetLastError());
     launches_++;
+    if (world_ > 1) {
+        // A batch prepared ahead is selected while the resolver of an earlier batch is still turning singletons into
+        // members, so WHICH ids it picks depends on timing.  On one GPU that is harmless (the resolver skips what has
+        // been consumed in the meantime); across ranks every rank must score the SAME queries, or the best-hit exchange
+        // below would merge lists of different queries position by position.  Rank 0's selection wins.
+        bb.gqid.reserve((size_t)world_ * HMK_MAXBATCH);
+        allgather(bb.qid.p, bb.gqid.p, sizeof(int32_t) * nq, s);
+        CK(cudaMemcpyAsync(bb.qid.p, bb.gqid.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToDevice, s));
+    }
     HmkBulkArgs a{};
     a.nq = nq;
     a.packed = d_packed_.p; a.slot = d_slot_.p; a.q_minid = bb.qid.p;

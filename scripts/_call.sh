@@ -1,8 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python scripts/gpu_case2.py mix730:50000:7:30:blosum62 '{}' '{"batch":448}' '{"batch":96}' > gpurun_out/c25_cases.log 2>&1
-timeout 600 python scripts/gpu_case2.py l30:50000:30:30:blosum62 '{}' >> gpurun_out/c25_cases.log 2>&1
-cat gpurun_out/c25_cases.log
-timeout 1200 python -m pytest tests -m gpu -q --maxfail=8 -p no:cacheprovider > gpurun_out/c25_pytest.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/c25_pytest.log
-tail -4 gpurun_out/c25_pytest.log
+timeout 80 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/c29_bench2.json 2> gpurun_out/c29_bench2.err
+echo "bench rc=$?" >> gpurun_out/c29_bench2.err
+tail -2 gpurun_out/c29_bench2.err
