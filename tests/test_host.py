@@ -281,10 +281,10 @@ def test_tuning_options_documented_in_header():
 
 
 def test_committed_bench_line_keeps_the_contract():
-    """profiles/r01_bench_n1.json is the line bench.py printed on the B200: the keys the driver reads must be there"""
+    """profiles/r02_bench_n1.json is the line bench.py printed on the B200: the keys the driver reads must be there"""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    d = json.loads(open(os.path.join(root, "profiles", "r01_bench_n1.json")).read().strip().splitlines()[-1])
+    d = json.loads(open(os.path.join(root, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert k in d, k
@@ -299,6 +299,16 @@ def test_committed_bench_line_keeps_the_contract():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     w = d["work"]
     assert w["bulk_pairs"] + w["scalar_pairs"] + w["pairs_served_by_phase1_hits"] >= w["reference_min_pairs"]
+    # the roofline fraction is a utilisation of the binding pipe (shared-memory loads), not the algorithmic-ops figure
+    assert 0 < d["roofline"]["frac"] <= 1.0 and d["roofline"]["bound"] == "smem" and "algorithmic_int_alu" in d["roofline"]
+    # bit-exactness evidence travels with the line: digest of the result == digest of the full oracle run
+    gold = json.load(open(os.path.join(root, "tests", "golden", "s1m_digest.json")))
+    assert d["result_digest"] == gold["sha256"] and d["digest_matches_golden"] is True
+    assert d["cpu_baseline"]["extrapolated"] is True and "EXTRAPOLATED C PORT" in d["cpu_baseline"]["sample"]
+    assert all(o["digest_matches_oracle"] for o in d["other_configs"]) and len(d["other_configs"]) >= 3
+    for n in (2, 4, 8):      # the multi-GPU lines carry the same digest
+        dn = json.loads(open(os.path.join(root, "profiles", f"r02_bench_n{n}.json")).read().strip().splitlines()[-1])
+        assert dn["n_gpus"] == n and dn["result_digest"] == gold["sha256"] and dn["digests_agree_across_ranks"] is True
 
 
 def _labelled_musi(golden_dir):
