@@ -2432,7 +2432,7 @@ __global__ void hmk_clinkage_threshold(int32_t* D, size_t total, int32_t T) {
 
 __global__ void __launch_bounds__(HMK_CL_THREADS) hmk_clinkage_chain(const HmkClinkage C) {
     __shared__ int32_t r_score[32], r_size[32], r_id[32];
-    __shared__ int32_t s_top, s_best, s_bscore, s_action, s_ts, s_bs;     // action: 0 ready, 1 merge, 2 push, 3 finished
+    __shared__ int32_t s_top, s_best, s_action, s_ts, s_bs;     // action: 0 ready, 1 merge, 2 push
     __shared__ int32_t s_first[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = C.n;
@@ -2514,7 +2514,7 @@ __global__ void __launch_bounds__(HMK_CL_THREADS) hmk_clinkage_chain(const HmkCl
             for (int w = 0; w < (int)(blockDim.x >> 5); w++)
                 if (r_id[w] >= 0) hmk_consider(g, r_score[w], r_size[w], r_id[w], w);
             const int32_t best = g.slot >= 0 ? g.fid : -1, bscore = g.slot >= 0 ? g.score : HMK_JMIN;
-            s_best = best; s_bscore = bscore;
+            s_best = best;
             if (bscore < C.T) {                                           // :85-91
                 sp--;
                 C.ready[nr++] = top;
