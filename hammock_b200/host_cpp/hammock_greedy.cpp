@@ -81,12 +81,12 @@ int main(int argc, char** argv) {
         if (sequences.empty()) throw FileFormatException("Error. No sequences (with specified labels) to cluster.");
         // prepareSequenceClustering (Hammock.java:795-817)
         if (!haveLabels) labels = getSortedLabels(sequences);
-        const std::vector<UniqueSequence> initialSequences = sequences;   // input order, for the *_original_order file
         if (!haveX) maxShift = getMaxShift(sequences); else maxShift = checkMaxShift(sequences, maxShift);
         if (!haveT) threshold = setGreedyThreshold(sequences);            // Hammock.java:394-397
         if (!haveK) limit = initialClustersLimit(sequences);              // :398-401
         lap("labels + automatic parameters");
-        sortSequences(sequences, order, labels, seed);                     // :407
+        std::vector<int> cameFrom;                                        // input position of every sorted sequence
+        sortSequences(sequences, order, labels, seed, &cameFrom);         // :407 (the reference copies the list instead, :800)
         lap("sortSequences");
         if (hostOnly) return 0;
 
@@ -109,12 +109,9 @@ int main(int argc, char** argv) {
         if (!outdir.empty()) {
             std::string d = outdir;
             if (d.back() != '/') d.push_back('/');
-            // map input-order sequences to their index in clustering order
-            std::unordered_map<std::string, int> where;
-            for (size_t i = 0; i < sequences.size(); i++) where.emplace(sequences[i].sequence, (int)i);
-            std::vector<int> inputOrder;
-            for (auto& s : initialSequences) inputOrder.push_back(where.at(s.sequence));
-            saveInputStatistics(initialSequences, labels, d + "input_statistics.tsv");
+            std::vector<int> inputOrder(sequences.size());   // clustering-order index of every input-order sequence
+            for (size_t i = 0; i < cameFrom.size(); i++) inputOrder[cameFrom[i]] = (int)i;
+            saveInputStatistics(sequences, labels, d + "input_statistics.tsv");   // sums: the order does not matter
             saveClusterSequencesToCsv(clusters, sequences, d + "initial_clusters_sequences.tsv", labels);
             saveClusterSequencesToCsvOrdered(clusters, sequences, inputOrder, d + "initial_clusters_sequences_original_order.tsv", labels);
             SaveClustersToCsv(clusters, sequences, d + "initial_clusters.tsv", labels);

@@ -18,6 +18,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <vector>
 
@@ -79,21 +80,34 @@ struct JavaRandom {   // java.util.Random
 };
 
 // ---------------------------------------------------------------- data model
-struct UniqueSequence {   // UniqueSequence.java:19-57, 81-109
-    std::string sequence;                                  // upper-case letters (getSequenceString)
-    std::vector<uint8_t> codes;                            // getSequence()
-    std::vector<std::pair<std::string, int32_t>> labels;   // labelsMap (insertion order kept for determinism)
-
-    UniqueSequence(const std::string& s, std::vector<std::pair<std::string, int32_t>> lab) : labels(std::move(lab)) {
-        for (char c : s) {
-            char u = (char)std::toupper((unsigned char)c);
-            const char* p = u ? std::strchr(ALPHABET, u) : nullptr;
-            if (!p) throw FileFormatException(std::string("Error, character ") + c +
-                                              " is not a valid letter from the amino acid alphabet code.");   // :51-54
-            codes.push_back((uint8_t)(p - ALPHABET));
-            sequence.push_back(u);
+// letter -> code 0..23, -1 = not in the alphabet (lower case folds to upper case, UniqueSequence.java:44)
+struct ResidueTable {
+    int8_t code[256];
+    ResidueTable() {
+        std::memset(code, -1, sizeof code);
+        for (int i = 0; ALPHABET[i]; i++) {
+            code[(unsigned char)ALPHABET[i]] = (int8_t)i;
+            code[(unsigned char)std::tolower((unsigned char)ALPHABET[i])] = (int8_t)i;
         }
     }
+};
+inline const ResidueTable& residue_table() { static const ResidueTable t; return t; }
+
+struct UniqueSequence {   // UniqueSequence.java:19-57, 81-109
+    std::string sequence;                                  // upper-case letters (getSequenceString)
+    std::vector<std::pair<std::string, int32_t>> labels;   // labelsMap (insertion order kept for determinism)
+
+    UniqueSequence(std::string s, std::vector<std::pair<std::string, int32_t>> lab) : sequence(std::move(s)), labels(std::move(lab)) {
+        const ResidueTable& t = residue_table();
+        for (char& c : sequence) {
+            const int8_t k = t.code[(unsigned char)c];
+            if (k < 0) throw FileFormatException(std::string("Error, character ") + c +
+                                                 " is not a valid letter from the amino acid alphabet code.");   // :51-54
+            c = ALPHABET[k];
+        }
+    }
+    size_t length() const { return sequence.size(); }
+    uint8_t code(size_t i) const { return (uint8_t)residue_table().code[(unsigned char)sequence[i]]; }   // getSequence()[i]
     int32_t size() const {   // :81-88
         int32_t s = 0;
         for (auto& kv : labels) s = wrap_add(s, kv.second);
@@ -121,22 +135,39 @@ struct Cluster {   // Cluster.java:21-74, 113-123, 156-158
 // ---------------------------------------------------------------- loaders
 inline bool java_ws(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == 0x0B || c == '\f' || c == '\r'; }
 
-inline std::vector<std::string> read_lines(const std::string& path) {   // BufferedReader.readLine
-    std::ifstream f(path, std::ios::binary);
+inline std::string read_file(const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) throw HammockException("cannot open " + path);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    std::string text = ss.str();
-    std::vector<std::string> lines;
+    std::string text;
+    char buf[1 << 16];
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long n = std::ftell(f);
+        if (n > 0) text.reserve((size_t)n);
+        std::rewind(f);
+    }
+    for (size_t got; (got = std::fread(buf, 1, sizeof buf, f)) > 0;) text.append(buf, got);
+    std::fclose(f);
+    return text;
+}
+
+// BufferedReader.readLine over a whole file held in memory: fn(line) per line, terminator (and a '\r' before it) stripped
+template <class Fn>
+inline void for_each_line(const std::string& text, Fn&& fn) {
     size_t i = 0;
     while (i < text.size()) {
-        size_t j = text.find('\n', i);
-        if (j == std::string::npos) j = text.size();
-        std::string l = text.substr(i, j - i);
-        if (!l.empty() && l.back() == '\r') l.pop_back();
-        lines.push_back(l);
+        const void* nl = std::memchr(text.data() + i, '\n', text.size() - i);
+        size_t j = nl ? (size_t)((const char*)nl - text.data()) : text.size();
+        size_t e = j;
+        if (e > i && text[e - 1] == '\r') e--;
+        fn(std::string_view(text.data() + i, e - i));
         i = j + 1;
     }
+}
+
+inline std::vector<std::string> read_lines(const std::string& path) {
+    const std::string text = read_file(path);
+    std::vector<std::string> lines;
+    for_each_line(text, [&](std::string_view l) { lines.emplace_back(l); });
     return lines;
 }
 
@@ -177,11 +208,35 @@ inline int32_t decode_int(const std::string& tok) {   // Integer.decode
     return (int32_t)v;
 }
 
-inline std::string java_trim(const std::string& s) {   // String.trim
+inline std::string_view java_trim(std::string_view s) {   // String.trim
     size_t i = 0, j = s.size();
     while (i < j && (unsigned char)s[i] <= ' ') i++;
     while (j > i && (unsigned char)s[j - 1] <= ' ') j--;
     return s.substr(i, j - i);
+}
+
+inline int32_t decode_int(std::string_view tok) {   // Integer.decode; plain short decimals (no sign, no radix prefix) directly
+    if (!tok.empty() && tok.size() <= 9 && tok[0] >= '1' && tok[0] <= '9') {
+        int32_t v = 0;
+        size_t i = 0;
+        for (; i < tok.size() && tok[i] >= '0' && tok[i] <= '9'; i++) v = v * 10 + (tok[i] - '0');
+        if (i == tok.size()) return v;
+    }
+    return decode_int(std::string(tok));
+}
+inline int32_t decode_int(const char* tok) { return decode_int(std::string(tok)); }
+
+// String.split(sep) for a one-character separator: trailing empty strings are dropped (an all-empty result keeps one)
+inline void java_split(std::string_view s, char sep, std::vector<std::string_view>& parts) {
+    parts.clear();
+    size_t i = 0;
+    for (;;) {
+        const size_t j = s.find(sep, i);
+        parts.push_back(s.substr(i, j == std::string_view::npos ? std::string_view::npos : j - i));
+        if (j == std::string_view::npos) break;
+        i = j + 1;
+    }
+    while (parts.size() > 1 && parts.back().empty()) parts.pop_back();
 }
 
 // FileIOManager.loadScoringMatrix (FileIOManager.java:46-81), quirks included (rows in file order,
@@ -217,80 +272,101 @@ inline std::vector<int32_t> loadScoringMatrix(const std::string& path) {
     return M;
 }
 
+// LinkedHashMap<String, Map<String, Integer>> of the fasta loader: first-occurrence order of the sequences, an open-
+// addressing index over the entries (no node per key)
+struct SequenceTable {
+    struct Entry { std::string sequence; std::vector<std::pair<std::string, int32_t>> labels; };
+    std::vector<Entry> entries;
+    std::vector<uint32_t> slots;    // entry index + 1, 0 = free
+    std::vector<uint64_t> hashes;   // per entry
+    explicit SequenceTable(size_t expected) {
+        size_t cap = 1024;
+        while (cap < 2 * expected) cap *= 2;
+        slots.assign(cap, 0);
+        entries.reserve(expected);
+        hashes.reserve(expected);
+    }
+    static uint64_t hash(std::string_view s) {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
+        return h ^ (h >> 29);
+    }
+    void grow() {
+        std::vector<uint32_t> bigger(slots.size() * 2, 0);
+        for (size_t e = 0; e < entries.size(); e++) {
+            size_t i = hashes[e] & (bigger.size() - 1);
+            while (bigger[i]) i = (i + 1) & (bigger.size() - 1);
+            bigger[i] = (uint32_t)e + 1;
+        }
+        slots.swap(bigger);
+    }
+    void add(std::string_view sequence, std::string_view label, int32_t count) {
+        const uint64_t h = hash(sequence);
+        size_t i = h & (slots.size() - 1);
+        for (; slots[i]; i = (i + 1) & (slots.size() - 1)) {
+            const uint32_t e = slots[i] - 1;
+            if (hashes[e] != h || entries[e].sequence != sequence) continue;
+            for (auto& kv : entries[e].labels)
+                if (kv.first == label) { kv.second = wrap_add(kv.second, count); return; }
+            entries[e].labels.emplace_back(std::string(label), count);
+            return;
+        }
+        slots[i] = (uint32_t)entries.size() + 1;
+        entries.push_back(Entry{std::string(sequence), {{std::string(label), count}}});
+        hashes.push_back(h);
+        if (2 * entries.size() > slots.size()) grow();
+    }
+};
+
 // FileIOManager.loadUniqueSequencesFromFasta (FileIOManager.java:159-216)
 inline std::vector<UniqueSequence> loadUniqueSequencesFromFasta(const std::string& path) {
-    std::vector<std::string> order;                                       // LinkedHashMap: first-occurrence order
-    std::unordered_map<std::string, std::vector<std::pair<std::string, int32_t>>> map;
+    const std::string text = read_file(path);
+    SequenceTable table(text.size() / 24);
     std::string sequence, label;
+    std::vector<std::string_view> parts;
     int32_t count = 0;
     bool have = false;
-    auto flush = [&]() {
-        auto it = map.find(sequence);
-        if (it == map.end()) { order.push_back(sequence); map[sequence] = {{label, count}}; }
-        else {
-            bool found = false;
-            for (auto& kv : it->second) if (kv.first == label) { kv.second = wrap_add(kv.second, count); found = true; }
-            if (!found) it->second.push_back({label, count});
-        }
-    };
-    for (const std::string& line : read_lines(path)) {
+    for_each_line(text, [&](std::string_view line) {
         if (!line.empty() && line[0] == '>') {
-            if (!sequence.empty()) { flush(); sequence.clear(); }
-            std::string h = java_trim(line).substr(1);
-            std::vector<std::string> parts;
-            size_t i = 0;
-            for (;;) {
-                size_t j = h.find('|', i);
-                parts.push_back(h.substr(i, j == std::string::npos ? std::string::npos : j - i));
-                if (j == std::string::npos) break;
-                i = j + 1;
-            }
-            while (parts.size() > 1 && parts.back().empty()) parts.pop_back();   // String.split drops trailing empties
+            if (!sequence.empty()) { table.add(sequence, label, count); sequence.clear(); }
+            java_split(java_trim(line).substr(1), '|', parts);
             if (parts.size() >= 2) {
                 count = decode_int(java_trim(parts[1]));
                 if (count < 1) throw FileFormatException("Error while loading input file. Fasta header defines sequence count lower than 1.");
             } else count = 1;
-            label = parts.size() >= 3 ? parts[2] : "no_label";
+            if (parts.size() >= 3) label.assign(parts[2]); else label = "no_label";
             have = true;
         } else {
             if (!have) throw FileFormatException("Error. Incorrect fasta format. Maybe header or sequence line missing?");
             sequence += java_trim(line);
         }
-    }
+    });
     if (!have) throw FileFormatException("Error. Incorrect fasta format. Maybe header or sequence line missing?");
-    flush();
+    table.add(sequence, label, count);
     std::vector<UniqueSequence> out;
-    for (auto& s : order) out.emplace_back(s, map[s]);
+    out.reserve(table.entries.size());
+    for (auto& e : table.entries) out.emplace_back(std::move(e.sequence), std::move(e.labels));
     return out;
 }
 
 // FileIOManager.loadUniqueSequencesFromTable (FileIOManager.java:227-255)
 inline std::vector<UniqueSequence> loadUniqueSequencesFromTable(const std::string& path) {
-    auto split = [](const std::string& l) {
-        std::vector<std::string> p;
-        size_t i = 0;
-        for (;;) {
-            size_t j = l.find('\t', i);
-            p.push_back(l.substr(i, j == std::string::npos ? std::string::npos : j - i));
-            if (j == std::string::npos) break;
-            i = j + 1;
-        }
-        while (p.size() > 1 && p.back().empty()) p.pop_back();
-        return p;
-    };
-    auto lines = read_lines(path);
-    if (lines.empty()) throw FileFormatException("empty table");
-    auto header = split(lines[0]);
+    const std::string text = read_file(path);
+    std::vector<std::string> header;
+    std::vector<std::string_view> parts;
     std::vector<UniqueSequence> out;
-    for (size_t li = 1; li < lines.size(); li++) {
-        auto parts = split(lines[li]);
+    bool first = true;
+    for_each_line(text, [&](std::string_view line) {
+        java_split(line, '\t', parts);
+        if (first) { for (auto p : parts) header.emplace_back(p); first = false; return; }
         std::vector<std::pair<std::string, int32_t>> lab;
         for (size_t i = 1; i < parts.size(); i++) {
-            int32_t v = decode_int(parts[i]);
-            if (v != 0) lab.push_back({header.at(i), v});
+            const int32_t v = decode_int(parts[i]);
+            if (v != 0) lab.emplace_back(header.at(i), v);
         }
-        out.emplace_back(parts[0], lab);
-    }
+        out.emplace_back(std::string(parts[0]), std::move(lab));
+    });
+    if (first) throw FileFormatException("empty table");
     return out;
 }
 
@@ -315,45 +391,88 @@ inline std::vector<std::string> getSortedLabels(const std::vector<UniqueSequence
     return sorted;
 }
 
-// UniqueSequence.sortSequences (UniqueSequence.java:176-203)
+// UniqueSequence.sortSequences (UniqueSequence.java:176-203).  Sorted through an index array with the abundances computed
+// once and the first eight letters as an integer (most comparisons never touch the strings); `permutation`, if given,
+// receives for every new position the position the sequence had before (the reference keeps a copy of the list instead,
+// Hammock.java:800).
 inline void sortSequences(std::vector<UniqueSequence>& v, const std::string& order, const std::vector<std::string>& labels,
-                          int64_t seed) {
-    auto size_alpha_desc = [](const UniqueSequence& a, const UniqueSequence& b) {   // reverseOrder(SizeAlphabetic)
-        int32_t sa = a.size(), sb = b.size();
-        if (sa != sb) return sa > sb;
-        return a.sequence > b.sequence;
+                          int64_t seed, std::vector<int>* permutation = nullptr) {
+    struct Key { int32_t count, size; uint64_t prefix; int idx; };
+    std::vector<Key> keys(v.size());
+    for (size_t i = 0; i < v.size(); i++) {
+        uint64_t p = 0;
+        for (size_t k = 0; k < 8; k++) p = (p << 8) | (k < v[i].sequence.size() ? (unsigned char)v[i].sequence[k] : 0);
+        keys[i] = Key{0, v[i].size(), p, (int)i};
+    }
+    auto alpha_desc = [&](const Key& a, const Key& b) {       // reverseOrder(String.compareTo), strict
+        if (a.prefix != b.prefix) return a.prefix > b.prefix;
+        return v[a.idx].sequence > v[b.idx].sequence;
     };
-    if (order == "size") std::stable_sort(v.begin(), v.end(), size_alpha_desc);
-    else if (order == "alphabetic")
-        std::stable_sort(v.begin(), v.end(), [](const UniqueSequence& a, const UniqueSequence& b) { return a.sequence > b.sequence; });
+    auto size_alpha_desc = [&](const Key& a, const Key& b) {  // reverseOrder(SizeAlphabetic)
+        if (a.size != b.size) return a.size > b.size;
+        return alpha_desc(a, b);
+    };
+    if (order == "size") std::stable_sort(keys.begin(), keys.end(), size_alpha_desc);
+    else if (order == "alphabetic") std::stable_sort(keys.begin(), keys.end(), alpha_desc);
     else if (order == "random") {   // Collections.shuffle(list, new Random(seed))
         JavaRandom rnd(seed);
-        for (size_t i = v.size(); i > 1; i--) std::swap(v[i - 1], v[(size_t)rnd.nextInt((int32_t)i)]);
+        for (size_t i = keys.size(); i > 1; i--) std::swap(keys[i - 1], keys[(size_t)rnd.nextInt((int32_t)i)]);
     } else if (order == "input") {
-    } else {
+    } else {                        // two stable sorts in the reference: by size/alphabet, then by the label's count
         if (std::find(labels.begin(), labels.end(), order) == labels.end())
             throw DataException("Incorrect sequence order defined. Use one of: size, alphabetic, random, input, or a label");
-        std::stable_sort(v.begin(), v.end(), size_alpha_desc);
-        std::stable_sort(v.begin(), v.end(), [&](const UniqueSequence& a, const UniqueSequence& b) { return a.count(order) > b.count(order); });
+        for (auto& k : keys) k.count = v[k.idx].count(order);
+        std::stable_sort(keys.begin(), keys.end(), [&](const Key& a, const Key& b) {
+            if (a.count != b.count) return a.count > b.count;
+            return size_alpha_desc(a, b);
+        });
+    }
+    std::vector<UniqueSequence> sorted;
+    sorted.reserve(v.size());
+    for (auto& k : keys) sorted.push_back(std::move(v[k.idx]));
+    v.swap(sorted);
+    if (permutation) {
+        permutation->resize(keys.size());
+        for (size_t i = 0; i < keys.size(); i++) (*permutation)[i] = keys[i].idx;
     }
 }
 
 inline int32_t java_round(double x) { return (int32_t)std::floor(x + 0.5); }
 inline double getMeanSequenceLength(const std::vector<UniqueSequence>& s) {   // Hammock.java:1554-1563
     int64_t sum = 0;
-    for (auto& q : s) sum += (int64_t)q.codes.size();
+    for (auto& q : s) sum += (int64_t)q.length();
     return (double)sum / (double)s.size();
 }
 inline int32_t setGreedyThreshold(const std::vector<UniqueSequence>& s) { return java_round(getMeanSequenceLength(s) * 1.7); }   // :1409-1413
 inline int32_t checkMaxShift(const std::vector<UniqueSequence>& s, int32_t maxShift) {   // :1421-1427
     int32_t mn = INT32_MAX;
-    for (auto& q : s) mn = std::min<int32_t>(mn, (int32_t)q.codes.size());
+    for (auto& q : s) mn = std::min<int32_t>(mn, (int32_t)q.length());
     return std::min(maxShift, mn - 1);
 }
 inline int32_t getMaxShift(const std::vector<UniqueSequence>& s) { return checkMaxShift(s, java_round(getMeanSequenceLength(s) / 4)); }   // :1429-1434
 inline int32_t initialClustersLimit(const std::vector<UniqueSequence>& s) { return java_round((double)s.size() * 0.025); }   // :398-401
 
 // ---------------------------------------------------------------- the clusterer (SequenceClusterer seam)
+// List<Cluster> from the arrays of the C ABI: members by rank, clusters in result order
+inline std::vector<Cluster> rebuildClusters(int32_t n, const int32_t* cid, const int32_t* rank, const int32_t* order, int32_t nResult,
+                                            const int32_t* abundance) {
+    std::vector<int> start(n + 2, 0);
+    for (int32_t i = 0; i < n; i++) start[cid[i] + 1]++;
+    for (int32_t i = 0; i <= n; i++) start[i + 1] += start[i];
+    std::vector<int> byRank(n);
+    for (int32_t i = 0; i < n; i++) byRank[start[cid[i]] + rank[i]] = i;
+    std::vector<Cluster> result;
+    result.reserve(nResult);
+    for (int32_t k = 0; k < nResult; k++) {
+        Cluster c;
+        c.id = order[k];
+        c.members.assign(byRank.begin() + start[c.id], byRank.begin() + start[c.id + 1]);
+        for (int m : c.members) c.sizeSum = wrap_add(c.sizeSum, abundance[m]);
+        result.push_back(std::move(c));
+    }
+    return result;
+}
+
 // == new LimitedGreedySequenceClusterer(new ShiftedScorer(matrix, shiftPenalty, maxShift), threshold,
 //    maxClusters).cluster(sequences)   (Hammock.java:402-409)
 struct GpuGreedySequenceClusterer {
@@ -365,8 +484,11 @@ struct GpuGreedySequenceClusterer {
         const int32_t n = (int32_t)seqs.size();
         std::vector<int32_t> off(n + 1, 0), ab(n), cid(std::max(n, 1)), rank(std::max(n, 1)), order(std::max(n, 1));
         std::vector<uint8_t> res;
+        size_t total = 0;
+        for (auto& q : seqs) total += q.length();
+        res.reserve(total + 1);
         for (int32_t i = 0; i < n; i++) {
-            res.insert(res.end(), seqs[i].codes.begin(), seqs[i].codes.end());
+            for (size_t k = 0; k < seqs[i].length(); k++) res.push_back(seqs[i].code(k));
             off[i + 1] = (int32_t)res.size();
             ab[i] = seqs[i].size();
         }
@@ -379,24 +501,7 @@ struct GpuGreedySequenceClusterer {
         if (rc == HMK_STATUS_NULL_CLUSTER) throw NullPointerException(out.error_step);
         if (rc == HMK_STATUS_BAD_RESIDUE) throw FileFormatException(err);
         if (rc != HMK_STATUS_OK) throw CudaException(std::string("hammock_b200: ") + err);
-        // rebuild List<Cluster>: members by rank, clusters in result order
-        std::vector<int> start(n + 1, 0);
-        for (int32_t i = 0; i < n; i++) start[cid[i] + 1]++;
-        for (int32_t i = 0; i < n; i++) start[i + 1] += start[i];
-        std::vector<int> byRank(n);
-        for (int32_t i = 0; i < n; i++) byRank[start[cid[i]] + rank[i]] = i;
-        std::vector<Cluster> result;
-        result.reserve(out.n_result);
-        for (int32_t k = 0; k < out.n_result; k++) {
-            Cluster c;
-            c.id = order[k];
-            for (int m = start[c.id]; m < start[c.id + 1]; m++) {
-                c.members.push_back(byRank[m]);
-                c.sizeSum = wrap_add(c.sizeSum, ab[byRank[m]]);
-            }
-            result.push_back(std::move(c));
-        }
-        return result;
+        return rebuildClusters(n, cid.data(), rank.data(), order.data(), out.n_result, ab.data());
     }
 };
 
@@ -405,18 +510,67 @@ static const char SEP = '\t';   // Hammock.CSV_SEPARATOR (Hammock.java:35)
 
 // Cluster.compareTo reversed (Cluster.java:197-204): size descending, then id descending; stable
 inline std::vector<const Cluster*> clustersLargestFirst(const std::vector<Cluster>& clusters) {
-    std::vector<const Cluster*> v;
-    for (auto& c : clusters) v.push_back(&c);
-    std::stable_sort(v.begin(), v.end(), [](const Cluster* a, const Cluster* b) {
-        if (a->size() != b->size()) return a->size() > b->size();
-        return a->id > b->id;
+    struct Key { int32_t size, id; const Cluster* c; };
+    std::vector<Key> keys;
+    keys.reserve(clusters.size());
+    for (auto& c : clusters) keys.push_back(Key{c.size(), c.id, &c});
+    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+        if (a.size != b.size) return a.size > b.size;
+        return a.id > b.id;
     });
+    std::vector<const Cluster*> v;
+    v.reserve(keys.size());
+    for (auto& k : keys) v.push_back(k.c);
     return v;
 }
 
-inline void writeRow(std::ostream& w, const std::string& clusterId, const UniqueSequence& s, const std::string& alignment,
+// BufferedWriter: rows are formatted into one buffer and written in 1 MB pieces
+class TsvWriter {
+    std::FILE* f_;
+    std::string buf_;
+public:
+    explicit TsvWriter(const std::string& path) : f_(std::fopen(path.c_str(), "wb")) {
+        if (!f_) throw HammockException("cannot write " + path);
+        buf_.reserve((1 << 20) + 4096);
+    }
+    TsvWriter(const TsvWriter&) = delete;
+    TsvWriter& operator=(const TsvWriter&) = delete;
+    ~TsvWriter() { flush(); std::fclose(f_); }
+    void flush() { if (!buf_.empty()) { std::fwrite(buf_.data(), 1, buf_.size(), f_); buf_.clear(); } }
+    TsvWriter& operator<<(std::string_view s) { buf_.append(s); if (buf_.size() > (1u << 20)) flush(); return *this; }
+    TsvWriter& operator<<(const char* s) { return *this << std::string_view(s); }
+    TsvWriter& operator<<(const std::string& s) { return *this << std::string_view(s); }
+    TsvWriter& operator<<(char c) { buf_.push_back(c); return *this; }
+    TsvWriter& operator<<(int32_t v) {   // Integer.toString
+        char tmp[12];
+        int n = 0;
+        uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+        do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (v < 0) tmp[n++] = '-';
+        while (n) buf_.push_back(tmp[--n]);
+        return *this;
+    }
+};
+
+inline std::vector<int32_t> sequenceSizes(const std::vector<UniqueSequence>& seqs) {
+    std::vector<int32_t> sizes(seqs.size());
+    for (size_t i = 0; i < seqs.size(); i++) sizes[i] = seqs[i].size();
+    return sizes;
+}
+
+inline void writeHeader(TsvWriter& w, const char* second, const char* third, const std::vector<std::string>& labels) {
+    w << "cluster_id" << SEP << second << SEP;
+    if (third) w << third << SEP;
+    w << "sum";
+    for (auto& l : labels) w << SEP << l;
+    w << '\n';
+}
+
+// one row of the *_sequences files; clusterId < 0 = "NA"
+inline void writeRow(TsvWriter& w, int32_t clusterId, const UniqueSequence& s, int32_t size, bool alone,
                      const std::vector<std::string>& labels) {
-    w << clusterId << SEP << s.sequence << SEP << alignment << SEP << s.size();
+    if (clusterId < 0) w << "NA"; else w << clusterId;
+    w << SEP << s.sequence << SEP << (alone ? std::string_view(s.sequence) : std::string_view("NA")) << SEP << size;
     for (auto& l : labels) w << SEP << s.count(l);
     w << '\n';
 }
@@ -428,51 +582,45 @@ inline void writeRow(std::ostream& w, const std::string& clusterId, const Unique
 // this path; `cluster` mode accepts NA and rebuilds the MSAs (FileIOManager.java:351-357).
 inline void saveClusterSequencesToCsv(const std::vector<Cluster>& clusters, const std::vector<UniqueSequence>& seqs,
                                       const std::string& path, const std::vector<std::string>& labels) {
-    std::ofstream w(path);
-    w << "cluster_id" << SEP << "sequence" << SEP << "alignment" << SEP << "sum";
-    for (auto& l : labels) w << SEP << l;
-    w << '\n';
+    const std::vector<int32_t> sizes = sequenceSizes(seqs);
+    TsvWriter w(path);
+    writeHeader(w, "sequence", "alignment", labels);
+    std::vector<int> m;
     for (const Cluster* c : clustersLargestFirst(clusters)) {
-        std::vector<int> m = c->members;
+        m = c->members;
         std::stable_sort(m.begin(), m.end(), [&](int a, int b) {
-            int32_t sa = seqs[a].size(), sb = seqs[b].size();
-            if (sa != sb) return sa > sb;
+            if (sizes[a] != sizes[b]) return sizes[a] > sizes[b];
             return seqs[a].sequence > seqs[b].sequence;
         });
-        for (int i : m) writeRow(w, std::to_string(c->id), seqs[i], m.size() == 1 ? seqs[i].sequence : "NA", labels);
+        for (int i : m) writeRow(w, c->id, seqs[i], sizes[i], m.size() == 1, labels);
     }
 }
 
-// saveClusterSequencesToCsvOrdered (FileIOManager.java:371-374): same rows in the given sequence order
+// saveClusterSequencesToCsvOrdered (FileIOManager.java:371-374): same rows in the given sequence order; a sequence that
+// is in no cluster gets NA (:625-627)
 inline void saveClusterSequencesToCsvOrdered(const std::vector<Cluster>& clusters, const std::vector<UniqueSequence>& seqs,
                                              const std::vector<int>& sequenceOrder, const std::string& path,
                                              const std::vector<std::string>& labels) {
     std::vector<const Cluster*> of(seqs.size(), nullptr);
     for (auto& c : clusters) for (int i : c.members) of[i] = &c;
-    std::ofstream w(path);
-    w << "cluster_id" << SEP << "sequence" << SEP << "alignment" << SEP << "sum";
-    for (auto& l : labels) w << SEP << l;
-    w << '\n';
+    TsvWriter w(path);
+    writeHeader(w, "sequence", "alignment", labels);
     for (int i : sequenceOrder) {
         const Cluster* c = of[i];
-        if (c) writeRow(w, std::to_string(c->id), seqs[i], c->members.size() == 1 ? seqs[i].sequence : "NA", labels);
-        else writeRow(w, "NA", seqs[i], "NA", labels);
+        writeRow(w, c ? c->id : -1, seqs[i], seqs[i].size(), c && c->members.size() == 1, labels);
     }
 }
 
 // SaveClustersToCsv (FileIOManager.java:649-676): main_sequence = most abundant member, ties alphabetically FIRST
 inline void SaveClustersToCsv(const std::vector<Cluster>& clusters, const std::vector<UniqueSequence>& seqs,
                               const std::string& path, const std::vector<std::string>& labels) {
-    std::ofstream w(path);
-    w << "cluster_id" << SEP << "main_sequence" << SEP << "sum";
-    for (auto& l : labels) w << SEP << l;
-    w << '\n';
+    const std::vector<int32_t> sizes = sequenceSizes(seqs);
+    TsvWriter w(path);
+    writeHeader(w, "main_sequence", nullptr, labels);
     for (const Cluster* c : clustersLargestFirst(clusters)) {
         int best = c->members[0];
-        for (int i : c->members) {   // first element of sort(reverseOrder(UniqueSequence.compareTo)); stable
-            int32_t si = seqs[i].size(), sb = seqs[best].size();
-            if (si > sb || (si == sb && seqs[i].sequence < seqs[best].sequence)) best = i;
-        }
+        for (int i : c->members)   // first element of sort(reverseOrder(UniqueSequence.compareTo)); stable
+            if (sizes[i] > sizes[best] || (sizes[i] == sizes[best] && seqs[i].sequence < seqs[best].sequence)) best = i;
         w << c->id << SEP << seqs[best].sequence << SEP << c->size();
         for (auto& l : labels) {
             int32_t sum = 0;
@@ -485,7 +633,7 @@ inline void SaveClustersToCsv(const std::vector<Cluster>& clusters, const std::v
 
 // saveInputStatistics (FileIOManager.java:709-729); no newline after the last line
 inline void saveInputStatistics(const std::vector<UniqueSequence>& seqs, const std::vector<std::string>& labels, const std::string& path) {
-    std::ofstream w(path);
+    TsvWriter w(path);
     for (auto& l : labels) w << SEP << l;
     w << '\n' << "total_count";
     for (auto& l : labels) { int32_t t = 0; for (auto& s : seqs) t = wrap_add(t, s.count(l)); w << SEP << t; }

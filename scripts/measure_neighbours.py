@@ -3,6 +3,8 @@ CPU of whatever machine runs this script:
 
   N4  input side: the C++ host (hammock_greedy --time-host --host-only): fasta parsing + de-duplication, label order,
       automatic parameters, UniqueSequence.sortSequences (UniqueSequence.java:176-203, FileIOManager.java:159-255)
+  N2  output side of the host: the four result files of the greedy stage at 1 M, written by the C++ writers from the
+      oracle's S1M clustering (tests/cpp/writers_harness.cpp: the functions the driver runs after the GPU call)
   N3  output side: the reference's post-greedy MSA step (Hammock.java:414-426, ClustalRunner.java:113-160): one
       `clustalo -i <fa> -o <aln> --force --wrap=999999` process per multi-member cluster, timed on a sample of the
       clusters of the S1M result (the full oracle run kept by scripts/make_s1m_digest.py) and extrapolated to all of them
@@ -49,9 +51,31 @@ def main():
                 stages[k.strip()] = float(v.replace("ms", ""))
         out["N4_input_side_cpp_host"] = {"what": "hammock_greedy --time-host --host-only on a shuffled 1 M-sequence fasta (28 MB), one thread",
                                          "ms": stages, "total_ms": round(sum(stages.values()), 1), "rc": r.returncode}
-        # ---- N3
+        out["N4_input_side_cpp_host"]["before_round_2_rewrite_ms"] = {"load + de-duplicate": 3054.64, "labels + automatic parameters": 159.714,
+                                                                      "sortSequences": 1431.92, "total": 4646.3}
         z = np.load(os.path.join(ROOT, "scratch", "s1m_oracle_result.npz"))
         cid, rank = z["cluster_id"], z["member_rank"]
+        # ---- N2: the writers at 1 M
+        harness = os.path.join(tmp, "writers_harness")
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", harness, os.path.join(ROOT, "tests", "cpp", "writers_harness.cpp")])
+        rt = os.path.join(tmp, "result.txt")
+        with open(rt, "w") as f:
+            f.write(f"{len(cid)} {len(z['result_order'])}\n")
+            for a in (cid, rank, z["result_order"]):
+                f.write(" ".join(map(str, a.tolist())) + "\n")
+        os.mkdir(os.path.join(tmp, "out"))
+        r = subprocess.run([harness, fa, "size", "42", rt, os.path.join(tmp, "out") + "/"], capture_output=True, text=True,
+                           env=dict(os.environ, HARNESS_TIMES="1"))
+        stages = {}
+        for line in r.stderr.splitlines():
+            if line.startswith("host time "):
+                k, v = line[len("host time "):].rsplit(":", 1)
+                stages[k.strip()] = float(v.replace("ms", ""))
+        wr = {k: v for k, v in stages.items() if k.startswith(("rebuild", "save", "Save"))}
+        out["N2_output_side_cpp_host"] = {"what": "rebuildClusters + the four result files (86 MB) from the oracle's S1M clustering, one thread",
+                                          "ms": wr, "total_ms": round(sum(wr.values()), 1), "rc": r.returncode,
+                                          "before_round_2_rewrite_total_ms": 1857.5}
+        # ---- N3
         order = np.argsort(cid, kind="stable")
         cs = cid[order]
         starts = np.nonzero(np.r_[True, cs[1:] != cs[:-1]])[0]

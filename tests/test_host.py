@@ -362,3 +362,57 @@ def test_result_file_writers_against_the_oracle_writers(tmp_path, golden_dir):
     assert tot == sorted(tot, reverse=True)
     for m in sizes.values():
         assert m == sorted(m, reverse=True)
+
+
+# ---------------------------------------------------------------- C++ host side around the GPU call, on the oracle's clustering
+def _writers_harness(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "writers_harness")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "writers_harness.cpp")])
+    return exe
+
+
+@pytest.mark.parametrize("order", ["size", "random", "rep2", "input"])
+def test_cpp_host_files_from_the_oracle_clustering(tmp_path, blosum62, order):
+    """SURVEY.md 8(f) N2/N4 on the CPU: fasta (duplicates, several labels, wrapped and lower-case lines) through the C++
+    loader / label order / sortSequences, the ORACLE's clustering of that order in place of the GPU call, then the C++
+    rebuildClusters + writers -- against the oracle's restatement of FileIOManager, byte for byte.  tests/cpp/writers_harness.cpp
+    runs the functions the driver runs either side of hmk_greedy_cluster and never links the library."""
+    import subprocess
+    from oracle import pyref_writers as W
+    exe = _writers_harness(tmp_path)
+    d = synth.generate(900, 7, 12, seed=21)
+    strs = synth.to_strings(d["residues"], d["offsets"])
+    rng = np.random.default_rng(3)
+    labs = ["rep1", "rep2", "ctrl"]
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for k in range(1500):
+            i = int(rng.integers(0, len(strs)))
+            s = strs[i].lower() if i % 7 == 0 else strs[i]      # per sequence: the loader de-duplicates the RAW strings
+            body = s if k % 5 else s[:4] + "\n" + s[4:] + "  "
+            f.write(f">r{k}|{int(rng.integers(1, 40))}|{labs[int(rng.integers(0, 3))]}\r\n{body}\n")
+    seqs = hb.load_unique_sequences_from_fasta(str(fa))
+    labels = hb.get_sorted_labels(seqs)
+    ordered = hb.sort_sequences(seqs, order, labels, seed=11)
+    res, offs, ab = hb.pack_sequences(ordered)
+    T, X, K = hb.set_greedy_threshold(seqs), hb.get_max_shift(seqs), hb.initial_clusters_limit(seqs)
+    R = O.greedy_cluster(res, offs, ab, blosum62, T, X, 0, K)
+    assert R.status == 0
+    with open(tmp_path / "result.txt", "w") as f:
+        f.write(f"{len(ordered)} {len(R.result_order)}\n")
+        for a in (R.cluster_id, R.member_rank, R.result_order):
+            f.write(" ".join(str(int(v)) for v in a) + "\n")
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([exe, str(fa), order, "11", str(tmp_path / "result.txt"), str(out) + "/"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines() == [f"{s.get_sequence_string()}\t{s.size()}" for s in ordered]
+    clusters = hb.rebuild_clusters(ordered, hb.GreedyResult(R.cluster_id, R.member_rank, R.result_order, R.n_multi, {}))
+    tup = lambda s: (s.get_sequence_string(), dict(s.labels_map))
+    ct = [(c.get_id(), [tup(s) for s in c.get_sequences()]) for c in clusters]
+    assert (out / "initial_clusters_sequences.tsv").read_text() == W.cluster_sequences_tsv(ct, labels)
+    assert (out / "initial_clusters_sequences_original_order.tsv").read_text() == W.cluster_sequences_tsv_ordered(ct, labels, [tup(s) for s in seqs])
+    assert (out / "initial_clusters.tsv").read_text() == W.clusters_tsv(ct, labels)
+    assert (out / "input_statistics.tsv").read_text() == W.input_statistics([tup(s) for s in seqs], labels)
