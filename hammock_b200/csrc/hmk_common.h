@@ -10,6 +10,17 @@
 #define HMK_HD inline
 #endif
 
+// -DHMK_CHECKED (hammock_b200.build.build(defines=["HMK_CHECKED"], out=...)): in-kernel bounds assertions at every write
+// whose index comes from an atomic counter, a scheduler or decoded data.  A failing device assert prints file:line and
+// makes the launch fail (cudaErrorAssert -> HMK_STATUS_CUDA).  Compiled out otherwise: the default build's SASS is
+// identical with and without these lines.  (compute-sanitizer is not available on the target pool.)
+#if defined(HMK_CHECKED) && defined(__CUDACC__)
+#include <assert.h>
+#define HMK_CHECK(cond) assert(cond)
+#else
+#define HMK_CHECK(cond) ((void)0)
+#endif
+
 #define HMK_NRES 24
 #define HMK_JMIN ((int32_t)0x80000000)
 #define HMK_JMAX ((int32_t)0x7fffffff)

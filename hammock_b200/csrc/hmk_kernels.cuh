@@ -253,6 +253,7 @@ __device__ __forceinline__ void hmk_topk_insert_locked(const HmkTopkSmem& s, int
     while (atomicCAS(s.lock + t, 0, 1) != 0) {}
     __threadfence_block();
     int c = *cnt;
+    HMK_CHECK(t >= 0 && c >= 0 && c <= kb);
     if (c < kb) {
         keys[c] = key;
         c++;
@@ -285,6 +286,7 @@ template <int MODE>
 __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopkSmem& tk, int q0, HmkHitQueue& hq) {
     const int lane = threadIdx.x & 31;
     const int n = hq.cnt;
+    HMK_CHECK(n >= 0 && n <= HMK_QCAP);
     __syncwarp();
     if (MODE == HMK_MODE_EMIT) {
         unsigned int base = 0;
@@ -295,6 +297,7 @@ __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopk
             const unsigned int pos = base + e;
             const int32_t sc = hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32);
             const int32_t i = (int32_t)(uint32_t)v;
+            HMK_CHECK(i >= 0 && i < a.ndb && (int)(v >> 48) < a.qt);
             const int32_t id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
             if (pos < a.hit_cap) a.hits[pos] = make_int4(q0 + (int)(v >> 48), id, sc, 0);
         }
@@ -309,6 +312,7 @@ __device__ __noinline__ void hmk_queue_drain(const HmkBulkArgs& a, const HmkTopk
                 const uint64_t v = hq.q[e];
                 tl = (int)(v >> 48);
                 const int32_t i = (int32_t)(uint32_t)v;
+                HMK_CHECK(i >= 0 && i < a.ndb && tl < a.qt && q0 + tl < a.nq);
                 id = a.db_ids ? a.db_ids[i] : a.db_begin + i;
                 sc = hq.s32 ? hq.s32[e] : (int32_t)(int16_t)(uint16_t)(v >> 32);
                 pending = !(a.q_minid && id <= a.q_minid[q0 + tl]);   // initialList[index+1 ..] only
@@ -359,6 +363,7 @@ __device__ __forceinline__ void hmk_queue_push(const HmkBulkArgs& a, const HmkTo
         const int lane = threadIdx.x & 31;
         if (hit) {
             const int pos = hq.cnt + __popc(m & ((1u << lane) - 1u));
+            HMK_CHECK(pos >= 0 && pos < HMK_QCAP);
             hq.q[pos] = hmk_hit_pack(tl, score, i);
             if (hq.s32) hq.s32[pos] = score;
         }
@@ -387,6 +392,7 @@ __device__ __forceinline__ void hmk_topk_init(const HmkTopkSmem& tk, int qn, int
     for (int i = threadIdx.x; i < qn; i += blockDim.x) { tk.cnt[i] = 0; tk.lock[i] = 0; tk.ovf[i] = 0; tk.minkey[i] = 0; }
 }
 __device__ __forceinline__ void hmk_topk_flush(const HmkBulkArgs& a, const HmkTopkSmem& tk, int q0, int qn, int stripe) {   // stripe = output slot
+    HMK_CHECK(stripe >= 0 && stripe < a.nstripes && q0 >= 0 && q0 + qn <= a.nq);
     for (int t = threadIdx.x; t < qn; t += blockDim.x) {
         uint64_t* k = tk.key + (size_t)t * a.kb;
         int c = tk.cnt[t];
@@ -592,6 +598,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
         const int t = (int)(ent >> 24);
         const uint32_t halves = ((ent >> 7) & 1u) | ((ent >> 22) & 2u);
         const int32_t i = i_begin + (int32_t)((ent & 0x7fu) | ((ent & 0x7fff00u) >> 1));
+        HMK_CHECK(!have || (t < qn && i >= i_begin && i < i_end && halves != 0u));
         const uint64_t w = have ? cqw[base + lane] : 0ull;
         const unsigned char* pb = sbase + (uint32_t)t * PWB + ((halves & 1u) ? 0u : SUB);
         uint32_t acc0 = 0, acc1 = 0;
@@ -635,6 +642,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
             __syncthreads();
             tile = s_next[0]; chunk_idx = s_next[1];
             if (tile < 0) break;
+            HMK_CHECK(tile < a.nqt && chunk_idx >= 0 && chunk_idx < a.nchunks);
         }
         if (tile != cur_tile) {
             if (cur_tile >= 0) {        // leave the previous tile: everything queued belongs to it
@@ -697,6 +705,7 @@ __global__ void __launch_bounds__(HMK_BULK_THREADS, 1) hmk_bulk_filter(const __g
                 if (m) {
                     if (top) {
                         const int sl = ccnt + __popc(m & ltmask);
+                        HMK_CHECK(sl >= 0 && sl < HMK_CQCAP && ilocal < (1u << 22) && (tI >> 24) + tu < 256u);
                         cq[sl] = (tI + (tu << 24)) | ((top | (top >> 8)) & 0x00800080u);
                         cqw[sl] = w;
                     }
@@ -942,9 +951,10 @@ __global__ void hmk_topk_merge(int nq, int nstripes, int kb, const uint64_t* __r
                                int32_t* __restrict__ out_ovf, const int32_t* __restrict__ slots_of_tile = nullptr, int qt = 1) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= nq) return;
-    if (slots_of_tile) nstripes = min(nstripes, slots_of_tile[t / qt]);
+    if (slots_of_tile) { HMK_CHECK(slots_of_tile[t / qt] >= 0 && slots_of_tile[t / qt] <= nstripes); nstripes = min(nstripes, slots_of_tile[t / qt]); }
     int total = 0, ovf = 0;
     for (int s = lane; s < nstripes; s += 32) {
+        HMK_CHECK(tk_cnt[(size_t)s * nq + t] >= 0 && tk_cnt[(size_t)s * nq + t] <= kb);
         total += tk_cnt[(size_t)s * nq + t];
         ovf |= tk_ovf[(size_t)s * nq + t];
     }
@@ -1146,6 +1156,7 @@ __global__ void hmk_member_check(const HmkCheckArgs a) {
         int32_t cl = h.z;
         bool ok = true;
         int32_t qrow[HMK_MAXL1];
+        HMK_CHECK(c >= 0 && c < a.S.K && q >= 0 && q < a.S.n && qi >= 0);
         if (FAST) hmk_qrow12(a.packed[q], qrow);
         for (int32_t m = a.S.next[a.S.c_founder[c]]; m >= 0; m = a.S.next[m]) {
             const int32_t s = FAST ? hmk_score12x3(qrow, a.packed[m], sM, a.S.P) : hmk_scalar_score(a.S, sc, m, q);
@@ -1617,6 +1628,7 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
                     const int r = __popc(cm & lt);
                     const int32_t c = ncl + r;
                     const int row = tn + r;
+                    HMK_CHECK(c < S.K && row < HMK_MAXBATCH && q >= 0 && q < S.n && bid > q && bid < S.n && S.slot[q] < 0);
                     for (int w = 0; w < nw; w++) t_mask[row * nw + w] = 0;
                     t_mask[row * nw + (bi >> 5)] = 1u << (bi & 31);
                     uint32_t h = hmk_hash((uint32_t)c);
@@ -1813,6 +1825,8 @@ __global__ void __launch_bounds__(HMK_RESOLVE_THREADS) hmk_p1_resolve_kernel(con
             if (lane == (b >> 5)) t_mask[row * nw + lane] |= 1u << (b & 31);
             if (create && lane == (b >> 5)) s_fmask[lane] |= 1u << (b & 31);
             if (lane == 0) {
+                HMK_CHECK(row >= 0 && row < HMK_MAXBATCH && c >= 0 && c < S.K && q >= 0 && q < S.n && S.slot[q] < 0);
+                HMK_CHECK(join || (bid > q && bid < S.n));
                 t_nmem[row] += 1;
                 if (join) {                                               // insertAll({q})   (:97,104)
                     S.next[t_tail[row]] = q; S.next[q] = -1;
@@ -2015,6 +2029,7 @@ __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_
                 bool act = i < ptot;
                 HmkDynEntry m;
                 m.w = 0; m.qi = 0; m.ab = 0;
+                HMK_CHECK(!act || (poff >= 0 && poff + i < P.cstart[P.ncl]));
                 if (act) m = P.dyn[poff + i];
                 const bool behind = act && i >= pnd && m.qi >= qi;      // tentative joiners at or behind q do not count
                 act = act && !behind;
@@ -2054,6 +2069,7 @@ __device__ __forceinline__ void hmk_p2_decide_query(const HmkP2& P, const int32_
             if (c < 0) continue;
             if (atomicMin(P.dirty + c, qi) == HMK_P2_CLEAN) {       // first change of this cluster in this iteration
                 const int pos = atomicAdd(P.ctl + 4 + par, 1);
+                HMK_CHECK(pos >= 0 && pos < P.ncl);
                 if (pos < HMK_P2_CHG) P.chg[(size_t)par * HMK_P2_CHG + pos] = c;
             }
         }
@@ -2140,10 +2156,15 @@ __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
                         const int32_t id = P.singles[qi];
                         HmkDynEntry en;
                         en.w = P.packed ? P.packed[id] : 0ull; en.qi = qi; en.ab = P.S.ab[id];
+                        HMK_CHECK(ci[1] + n + __popc(jm) <= P.cstart[c + 1] - P.cstart[c]);     // final + tentative <= candidates
                         out[n + __popc(jm & ((1u << lane) - 1u))] = en;
                     }
                     n += __popc(jm);
-                    if (inw && qi > dpos && atomicMax(P.stamp + qi, gen) < gen) work[atomicAdd(P.ctl + par, 1)] = qi;
+                    if (inw && qi > dpos && atomicMax(P.stamp + qi, gen) < gen) {
+                        const int wpos = atomicAdd(P.ctl + par, 1);
+                        HMK_CHECK(wpos >= 0 && wpos < P.wcap);
+                        work[wpos] = qi;
+                    }
                     if (!__all_sync(FULL, inw)) break;
                 }
                 __syncwarp();
@@ -2163,6 +2184,7 @@ __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
                 wi = __shfl_sync(FULL, wi, 0);
                 if (wi >= nwork) break;
                 const int qi = t == 0 ? P.qa + wi : work[wi];
+                HMK_CHECK(qi >= P.qa && qi < P.qb && nwork <= P.wcap);
                 if (t == 0 && P.qstart[qi] == P.qstart[qi + 1]) continue;       // no candidate: stays unassigned
                 hmk_p2_decide_query<FAST>(P, sM, qi, par, npairs);
             }
@@ -2180,6 +2202,7 @@ __global__ void __launch_bounds__(256) hmk_p2_window(const HmkP2 P) {
         const int32_t nd = ci[1];
         int32_t cnt = P.S.c_count[c], size = P.S.c_size[c];
         const HmkDynEntry* tl = P.dyn + ci[0] + nd;
+        HMK_CHECK(nd + n <= P.cstart[c + 1] - P.cstart[c]);
         for (int i = 0; i < n; i++) {
             const int32_t q = P.singles[tl[i].qi];
             P.S.rank[q] = cnt++;
@@ -2267,6 +2290,7 @@ __global__ void hmk_bucket_by_length(const int32_t* __restrict__ ids, int n, con
     const int len = off[id + 1] - off[id];
     if (len > HMK_MAXLEN) return;
     const int k = atomicAdd(count + len, 1);
+    HMK_CHECK(len >= 0 && k >= 0 && k < stride);
     out[(size_t)len * stride + k] = id;
 }
 
@@ -2515,6 +2539,7 @@ __global__ void __launch_bounds__(HMK_CL_THREADS) hmk_clinkage_chain(const HmkCl
                 if (r_id[w] >= 0) hmk_consider(g, r_score[w], r_size[w], r_id[w], w);
             const int32_t best = g.slot >= 0 ? g.fid : -1, bscore = g.slot >= 0 ? g.score : HMK_JMIN;
             s_best = best;
+            HMK_CHECK(sp >= 1 && sp <= n && nr < n && ts >= 0 && ts < n);
             if (bscore < C.T) {                                           // :85-91
                 sp--;
                 C.ready[nr++] = top;
@@ -2540,6 +2565,7 @@ __global__ void __launch_bounds__(HMK_CL_THREADS) hmk_clinkage_chain(const HmkCl
             }
             if (tid == 0) {
                 cur_id++;
+                HMK_CHECK(cur_id < 2 * n + 3 && bs >= 0 && bs < n && bs != ts);
                 sp -= 2;
                 set_remove(top);
                 set_remove(s_best);
@@ -2578,6 +2604,7 @@ __global__ void __launch_bounds__(HMK_CL_THREADS) hmk_clinkage_chain(const HmkCl
             tail[b] = id;
             if (++rsize > (int)(rcap * 0.75f)) {
                 const int ncap = rcap * 2;
+                HMK_CHECK(ncap <= C.rcap_max);
                 for (int b2 = 0; b2 < ncap; b2++) { head2[b2] = -1; tail2[b2] = -1; }
                 for (int b2 = 0; b2 < rcap; b2++)
                     for (int32_t k = head[b2], nx; k >= 0; k = nx) {

@@ -416,3 +416,18 @@ def test_cpp_host_files_from_the_oracle_clustering(tmp_path, blosum62, order):
     assert (out / "initial_clusters_sequences_original_order.tsv").read_text() == W.cluster_sequences_tsv_ordered(ct, labels, [tup(s) for s in seqs])
     assert (out / "initial_clusters.tsv").read_text() == W.clusters_tsv(ct, labels)
     assert (out / "input_statistics.tsv").read_text() == W.input_statistics([tup(s) for s in seqs], labels)
+
+
+def test_checked_build_compiles(tmp_path):
+    """-DHMK_CHECKED turns the HMK_CHECK lines of the kernels into device asserts (scripts/gpu_checked_fuzz.py runs the fuzz
+    tier under that build on a GPU box); here: the instrumented variant still compiles for sm_100a and really carries
+    the assertions, and the kernels hold a meaningful number of them"""
+    import subprocess
+    out = str(tmp_path / "libhammock_b200_checked.so")
+    hb_build.build(force=True, defines=["HMK_CHECKED"], out=out)
+    sass = subprocess.run(["cuobjdump", "-sass", out], capture_output=True, text=True).stdout
+    assert "__assertfail" in sass or "assert" in subprocess.run(["cuobjdump", "-elf", out], capture_output=True, text=True).stdout
+    src = open(os.path.join(ROOT, "hammock_b200", "csrc", "hmk_kernels.cuh")).read()
+    assert len(re.findall(r"\bHMK_CHECK\(", src)) >= 20
+    L = ctypes.CDLL(out)
+    assert L.hmk_abi_version() == 2
