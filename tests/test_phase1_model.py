@@ -97,23 +97,30 @@ class Model:
         self.steps = 0
         self.status, self.npe_step = CONTINUE, -1
         self.stats = {"windows": 0, "window_steps": 0, "sequential": 0, "restarts": 0, "prepared": 0}
+        # phase-2 hit reuse (Engine::phase2, hmk_member_check mode 2): every qualifying hit of every partner search, tagged
+        # with the batch that produced it, and per sequence the batch in which it was RESOLVED as a query
+        self.batch_id = 0
+        self.xhits = []
+        self.qbatch = [-1] * self.n
 
     # ---- stage_partner_search: what does not depend on the clustering state (or tolerates a stale one)
     def select(self, slot_seen, first, want):
         ids = [i for i in range(first, self.n) if slot_seen[i] < 0][:want]
         return ids
 
-    def partner_lists(self, qid, slot_seen):
+    def partner_lists(self, qid, slot_seen, tag):
         S, ab, T, kb = self.S, self.ab, self.T, self.kb
         lists = []
         for q in qid:
             hits = sorted((-S[i][q], -ab[i], i) for i in range(q + 1, self.n) if slot_seen[i] < 0 and S[i][q] >= T)
+            self.xhits += [(q, h[2], -h[0], tag) for h in hits]          # before the top-k cut
             lists.append({"id": [h[2] for h in hits[:kb]], "score": [-h[0] for h in hits[:kb]], "ovf": len(hits) > kb})
         return lists
 
     def stage(self, qid, slot_seen):
         S, T = self.S, self.T
-        lists = self.partner_lists(qid, slot_seen)
+        self.batch_id += 1
+        lists = self.partner_lists(qid, slot_seen, self.batch_id)
         nq = len(qid)
         ib = [[S[qid[b2]][qid[b]] for b2 in range(nq)] for b in range(nq)]
         pd = [[[S[p][qid[b]] for p in lists[b2]["id"]] for b2 in range(nq)] for b in range(nq)]
@@ -122,7 +129,7 @@ class Model:
             thr = lists[b]["score"][-1] if lists[b]["id"] else JMAX
             ibm.append({b2 for b2 in range(b) if ib[b][b2] >= T})
             ibm2.append({b2 for b2 in ibm[b] if ib[b][b2] >= thr})
-        return {"qid": qid, "lists": lists, "ib": ib, "pd": pd, "ibm": ibm, "ibm2": ibm2}
+        return {"qid": qid, "lists": lists, "ib": ib, "pd": pd, "ibm": ibm, "ibm2": ibm2, "batch_id": self.batch_id}
 
     # ---- cluster search at the start of a batch's resolution: founder filter + member check + prepare_candidates
     def static_candidates(self, qid):
@@ -242,6 +249,7 @@ class Model:
                     if kind[l] != 0:
                         self.steps += 1
                         self.cur = qid[bi] + 1
+                        self.qbatch[qid[bi]] = bt["batch_id"]
                 b += Pn
                 penalty = 0 if Pn >= min(4, self.win) else 4
                 if Pn == W:
@@ -327,6 +335,7 @@ class Model:
             self.steps += 1
             self.unproc -= 1
             self.cur = q + 1
+            self.qbatch[q] = bt["batch_id"]
             b += 1
         if status == CONTINUE and (len(self.clusters) >= K or self.unproc <= 0):
             status = DONE
@@ -382,6 +391,42 @@ class Model:
                 "clusters": [(c["fid"], c["size"], list(c["members"])) for c in self.clusters]}
 
 
+    # ---- phase 2's candidate pairs (singleton q, cluster c, min score over the phase-1 members) ...
+    def pairs_from_kept_hits(self):
+        """... from the partner-search hits of phase 1: a hit counts if its batch is the one that resolved its query and it
+        links a founder with a sequence that is still a singleton; then the member check (hmk_member_check, mode 2).
+        (The second role assignment -- the QUERY of the hit is the singleton -- is kept as in the kernel but can never
+        fire: a resolved query that is still a singleton was an orphan, i.e. had no live hit at all.)"""
+        S, T = self.S, self.T
+        out = []
+        for x, y, sc, tag in self.xhits:
+            if self.qbatch[x] != tag:
+                continue
+            sx, sy = self.slot[x], self.slot[y]
+            if sx >= 0 and sy < 0 and self.clusters[sx]["fid"] == x:
+                c, q = sx, y
+            elif sy >= 0 and sx < 0 and self.clusters[sy]["fid"] == y:
+                c, q = sy, x
+            else:
+                continue
+            cl = min([sc] + [S[m][q] for m in self.clusters[c]["members"][1:]])
+            if cl >= T:
+                out.append((q, c, cl))
+        return out
+
+    def pairs_direct(self):
+        """... by the separate founder pass: every cluster against every remaining singleton"""
+        S, T = self.S, self.T
+        out = []
+        for c, cl_ in enumerate(self.clusters):
+            for q in range(self.n):
+                if self.slot[q] < 0:
+                    cl = min(S[m][q] for m in cl_["members"])
+                    if cl >= T:
+                        out.append((q, c, cl))
+        return out
+
+
 def _instance(rng, n, family, tie_heavy, asym):
     """pair scores with family structure: sequences of one family score high against each other"""
     T = 20
@@ -407,6 +452,7 @@ def test_phase1_scheme_reaches_the_sequential_state(cfg, tie_heavy):
     batch, kb, win, gate, depth = cfg
     rng = np.random.default_rng(99 + 7 * batch + kb + (1000 if tie_heavy else 0))
     seen = {"windows": 0, "window_steps": 0, "sequential": 0, "restarts": 0, "prepared": 0}
+    npairs = 0
     for trial in range(14):
         n = int(rng.integers(2, 140))
         S, ab, T = _instance(rng, n, int(rng.choice([2, 5, 12])), tie_heavy, asym=bool(trial % 2))
@@ -415,11 +461,16 @@ def test_phase1_scheme_reaches_the_sequential_state(cfg, tie_heavy):
         m = Model(S, ab, T, K, batch, kb, win, gate, depth, rng)
         got = m.run()
         assert got == want, (cfg, tie_heavy, trial, n, K)
+        if not trial % 2 and got["status"] == 0:       # symmetric scores: phase 2 can start from the kept phase-1 hits
+            kept = m.pairs_from_kept_hits()
+            assert len(kept) == len(set(kept)) and sorted(kept) == sorted(m.pairs_direct()), (cfg, tie_heavy, trial)
+            npairs += len(kept)
         for k in seen:
             seen[k] += m.stats[k]
     if win > 0:
         assert seen["windows"] > 0 and seen["window_steps"] > 0        # the speculative path really ran ...
     assert seen["sequential"] > 0                                      # ... and so did the sequential one
+    assert npairs > 0                                    # ... and the kept hits produced candidate pairs
     if depth > 0 and batch <= 16:
         assert seen["prepared"] > 0                                    # batches prepared from a stale state were used
 
@@ -475,3 +526,26 @@ def test_phase1_window_sees_the_pairs_of_earlier_lanes():
     m = Model(S, ab, T, n, 8, 4, 4, 0, 0, np.random.default_rng(0))
     m.run()
     assert m.stats["windows"] > 0
+
+
+def test_phase2_pairs_from_kept_hits_survive_restarts_and_discarded_batches():
+    """The kept phase-1 hits are only usable because of the batch tag: a batch that restarts (or a prepared batch that is
+    thrown away) leaves hits of queries that are searched AGAIN later -- without the tag the same candidate pair would be
+    listed twice.  One-entry lists on family-rich data restart often; K well below n leaves many singletons for phase 2."""
+    rng = np.random.default_rng(11)
+    restarts = pairs = dropped = 0
+    for trial in range(30):
+        n = int(rng.integers(40, 140))
+        S, ab, T = _instance(rng, n, int(rng.choice([12, 25])), bool(trial % 3 == 0), False)
+        K = max(2, n // int(rng.choice([4, 6, 10])))
+        m = Model(S, ab, T, K, int(rng.choice([8, 16, 32])), 1, int(rng.choice([0, 4])), 0, int(rng.choice([0, 1, 2])), rng)
+        got = m.run()
+        assert got == sequential(S, ab, T, K)
+        if got["status"] != 0:
+            continue
+        kept = m.pairs_from_kept_hits()
+        assert len(kept) == len(set(kept)) and sorted(kept) == sorted(m.pairs_direct()), trial
+        restarts += m.stats["restarts"]
+        pairs += len(kept)
+        dropped += sum(1 for x, y, sc, tag in m.xhits if m.qbatch[x] >= 0 and m.qbatch[x] != tag)
+    assert restarts > 0 and pairs > 0 and dropped > 0
