@@ -87,6 +87,65 @@ HMK_HD uint64_t hmk_key_make(int32_t score, uint32_t tierank) {
 HMK_HD int32_t hmk_key_score(uint64_t key) { return (int32_t)((uint32_t)(key >> 32) ^ 0x80000000u); }
 HMK_HD uint32_t hmk_key_rank(uint64_t key) { return ~(uint32_t)key; }
 
+// ---------------------------------------------------------------- packed sequences (<= 12 residues per 64-bit word)
+// 5 bits per residue, position j in bits 5j..5j+4; one-word sequences carry their length in bits 60..63.
+// Host + device so that the CPU tests can run them against the oracle (tests/cpp/common_shim.cpp).
+#define HMK_MAXL1 12           // residues per 64-bit packed word
+#if defined(__CUDACC__)
+#define HMK_UNROLL _Pragma("unroll")
+#else
+#define HMK_UNROLL
+#endif
+
+// S(seq1 = member, seq2 = query) from two packed words that carry their lengths (<= 12 residues each): the reference's
+// roles (ShiftedScorer.java:51-57: the shorter sequence slides, equal lengths make seq2 the shorter one) and orientation
+// M[shorter][longer] (:71,75,110), Java-int arithmetic.
+HMK_HD int32_t hmk_packed_pair_score(uint64_t w1, uint64_t w2, const int32_t* sM, int X, int P) {
+    const int len1 = (int)(w1 >> 60), len2 = (int)(w2 >> 60);
+    uint64_t ws, wl;
+    int ls, ll;
+    if (len1 >= len2) { ws = w2; ls = len2; wl = w1; ll = len1; }
+    else              { ws = w1; ls = len1; wl = w2; ll = len2; }
+    const int d = ll - ls;
+    int32_t best = HMK_JMIN;
+    for (int k = -X; k <= X + d; k++) {
+        const int j0 = k > 0 ? k : 0, j1 = ls + k < ll ? ls + k : ll;      // longer index j pairs with shorter index j - k
+        int32_t v = 0;
+        for (int j = j0; j < j1; j++) {
+            const uint32_t rs = (uint32_t)(ws >> (5 * (j - k))) & 31u, rl = (uint32_t)(wl >> (5 * j)) & 31u;
+            v = hmk_wadd(v, sM[rs * HMK_NRES + rl]);
+        }
+        v = hmk_wadd(v, hmk_wmul(d, P));
+        if (k < 0) v = hmk_wadd(v, hmk_wmul(-2 * k, P));
+        if (k > d) v = hmk_wadd(v, hmk_wmul(2 * (k - d), P));
+        if (v > best) best = v;
+    }
+    return best;
+}
+
+// S(member, query) with both sequences given as packed words: uniform length 12, max shift 3, matrix in shared memory.
+// qrow[j] = 24 * (query residue j).  77 x (address add + LDS + accumulate); when a warp scores 32 members against ONE
+// query, the loads of a step hit one matrix row (conflict free).
+HMK_HD int32_t hmk_score12x3(const int32_t (&qrow)[HMK_MAXL1], uint64_t wm, const int32_t* sM, int32_t P) {
+    int32_t rm[HMK_MAXL1];
+HMK_UNROLL
+    for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
+    int32_t best = HMK_JMIN;
+HMK_UNROLL
+    for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
+        int32_t v = 2 * (k < 0 ? -k : k) * P;
+HMK_UNROLL
+        for (int j = 0; j < HMK_MAXL1; j++)
+            if (j - k >= 0 && j - k < HMK_MAXL1) v += sM[qrow[j - k] + rm[j]];
+        best = v > best ? v : best;
+    }
+    return best;
+}
+HMK_HD void hmk_qrow12(uint64_t wq, int32_t (&qrow)[HMK_MAXL1]) {
+HMK_UNROLL
+    for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
+}
+
 // status codes of the engine / C ABI (include/hammock_b200.h)
 enum {
     HMK_OK = 0,

@@ -21,7 +21,6 @@
 #include "hmk_common.h"
 #include "hmk_resolve.h"
 
-#define HMK_MAXL1 12           // residues per 64-bit packed word
 #define HMK_MAXLEN 36          // longest sequence the packed kernels take (three words)
 #define HMK_NWMAX 10           // most 32-bit words per profile entry (long kernel)
 #define HMK_LONG_THREADS 512
@@ -1024,58 +1023,9 @@ __device__ __forceinline__ void hmk_load_matrix_smem(int32_t* sM, const int32_t*
     __syncthreads();
 }
 
-// S(seq1 = member, seq2 = query) from two packed words that carry their lengths (<= 12 residues each): the reference's
-// roles (ShiftedScorer.java:51-57: the shorter sequence slides, equal lengths make seq2 the shorter one) and orientation
-// M[shorter][longer] (:71,75,110), Java-int arithmetic.
-__device__ __forceinline__ int32_t hmk_packed_pair_score(uint64_t w1, uint64_t w2, const int32_t* sM, int X, int P) {
-    const int len1 = (int)(w1 >> 60), len2 = (int)(w2 >> 60);
-    uint64_t ws, wl;
-    int ls, ll;
-    if (len1 >= len2) { ws = w2; ls = len2; wl = w1; ll = len1; }
-    else              { ws = w1; ls = len1; wl = w2; ll = len2; }
-    const int d = ll - ls;
-    int32_t best = HMK_JMIN;
-    for (int k = -X; k <= X + d; k++) {
-        const int j0 = k > 0 ? k : 0, j1 = ls + k < ll ? ls + k : ll;      // longer index j pairs with shorter index j - k
-        int32_t v = 0;
-        for (int j = j0; j < j1; j++) {
-            const uint32_t rs = (uint32_t)(ws >> (5 * (j - k))) & 31u, rl = (uint32_t)(wl >> (5 * j)) & 31u;
-            v = hmk_wadd(v, sM[rs * HMK_NRES + rl]);
-        }
-        v = hmk_wadd(v, hmk_wmul(d, P));
-        if (k < 0) v = hmk_wadd(v, hmk_wmul(-2 * k, P));
-        if (k > d) v = hmk_wadd(v, hmk_wmul(2 * (k - d), P));
-        if (v > best) best = v;
-    }
-    return best;
-}
-
 __device__ __forceinline__ int32_t hmk_scalar_score(const HmkState& S, const HmkScalar& sc, int32_t member, int32_t query) {
     if (!sc.packed) return hmk_state_score(S, member, query);
     return hmk_packed_pair_score(sc.packed[member], sc.packed[query], sc.sM, S.X, S.P);
-}
-
-// S(member, query) with both sequences given as packed words: uniform length 12, max shift 3, matrix in shared memory.
-// qrow[j] = 24 * (query residue j).  77 x (address add + LDS + accumulate); when a warp scores 32 members against ONE
-// query, the loads of a step hit one matrix row (conflict free).
-__device__ __forceinline__ int32_t hmk_score12x3(const int32_t (&qrow)[HMK_MAXL1], uint64_t wm, const int32_t* sM, int32_t P) {
-    int32_t rm[HMK_MAXL1];
-#pragma unroll
-    for (int j = 0; j < HMK_MAXL1; j++) rm[j] = (int32_t)((uint32_t)(wm >> (5 * j)) & 31u);
-    int32_t best = HMK_JMIN;
-#pragma unroll
-    for (int k = -3; k <= 3; k++) {       // equal lengths: shorter = query (second argument), ShiftedScorer.java:51-57
-        int32_t v = 2 * (k < 0 ? -k : k) * P;
-#pragma unroll
-        for (int j = 0; j < HMK_MAXL1; j++)
-            if (j - k >= 0 && j - k < HMK_MAXL1) v += sM[qrow[j - k] + rm[j]];
-        best = v > best ? v : best;
-    }
-    return best;
-}
-__device__ __forceinline__ void hmk_qrow12(uint64_t wq, int32_t (&qrow)[HMK_MAXL1]) {
-#pragma unroll
-    for (int j = 0; j < HMK_MAXL1; j++) qrow[j] = (int32_t)((uint32_t)(wq >> (5 * j)) & 31u) * HMK_NRES;
 }
 
 // Dense table of pair scores for sequences of mixed lengths <= 12 straight from the packed words (which carry their

@@ -431,3 +431,132 @@ def test_checked_build_compiles(tmp_path):
     assert len(re.findall(r"\bHMK_CHECK\(", src)) >= 20
     L = ctypes.CDLL(out)
     assert L.hmk_abi_version() == 2
+
+
+# ---------------------------------------------------------------- the product's host/device primitives, compiled for the CPU
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    """hmk_common.h / hmk_resolve.h (the scalar scorer the generic kernels run, the partner key, the arg-max order) built with
+    g++ behind C linkage: tests/cpp/common_shim.cpp"""
+    import subprocess
+    out = str(tmp_path_factory.mktemp("shim") / "libshim.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O1", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "cpp", "common_shim.cpp")])
+    L = ctypes.CDLL(out)
+    u8p, i32p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int32)
+    L.shim_pair_score.restype = ctypes.c_int32
+    L.shim_pair_score.argtypes = [u8p, ctypes.c_int, u8p, ctypes.c_int, i32p, ctypes.c_int, ctypes.c_int]
+    L.shim_pair_score_strided.restype = ctypes.c_int32
+    L.shim_pair_score_strided.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int, i32p, ctypes.c_int, ctypes.c_int]
+    L.shim_pair_cells.restype = ctypes.c_int64
+    L.shim_key_make.restype = ctypes.c_uint64
+    L.shim_key_make.argtypes = [ctypes.c_int32, ctypes.c_uint32]
+    L.shim_key_score.restype = ctypes.c_int32
+    L.shim_key_score.argtypes = [ctypes.c_uint64]
+    L.shim_key_rank.restype = ctypes.c_uint32
+    L.shim_key_rank.argtypes = [ctypes.c_uint64]
+    L.shim_wadd.restype = L.shim_wmul.restype = ctypes.c_int32
+    L.shim_wadd.argtypes = L.shim_wmul.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    L.shim_best_cluster.restype = ctypes.c_int32
+    L.shim_best_cluster.argtypes = [ctypes.c_int, i32p, i32p, i32p]
+    L.shim_packed_pair_score.restype = L.shim_score12x3.restype = ctypes.c_int32
+    L.shim_packed_pair_score.argtypes = [ctypes.c_uint64, ctypes.c_uint64, i32p, ctypes.c_int, ctypes.c_int]
+    L.shim_score12x3.argtypes = [ctypes.c_uint64, ctypes.c_uint64, i32p, ctypes.c_int]
+    return L
+
+
+def _pack_word(codes):
+    """hmk_pack_sequences for a sequence of <= 12 residues: 5 bits per residue, length in bits 60..63"""
+    w = 0
+    for j, r in enumerate(codes):
+        w |= int(r) << (5 * j)
+    return w | (len(codes) << 60)
+
+
+def test_device_packed_scorers_against_the_oracle(shim, blosum62, golden_dir):
+    """hmk_packed_pair_score (mixed lengths <= 12, any max shift / penalty) and the unrolled hmk_score12x3 (12-mers, max
+    shift 3) == ShiftedScorer.sequenceScore(member, query) as the oracle restates it, Java-int wrapping included"""
+    z = np.load(os.path.join(golden_dir, "matrices.npz"))
+    big = (blosum62.astype(np.int64) * 90000000).astype(np.int32)
+    asym = blosum62.copy()
+    asym[np.triu_indices(24, 1)] -= 3
+    mats = [blosum62, z["pam250"], asym, big]
+    rng = np.random.default_rng(10)
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    for it in range(3000):
+        l1, l2 = int(rng.integers(1, 13)), int(rng.integers(1, 13))
+        X = int(rng.integers(0, min(l1, l2)))
+        P = int(rng.choice([0, 0, -1, -4, 3, -2000000000]))
+        M = np.ascontiguousarray(mats[it % len(mats)], dtype=np.int32)
+        member = rng.integers(0, 24, l1).astype(np.uint8)
+        query = rng.integers(0, 24, l2).astype(np.uint8)
+        want, _ = O.score_with_shift(member, query, M, X, P)
+        assert shim.shim_packed_pair_score(_pack_word(member), _pack_word(query), M.ctypes.data_as(i32p), X, P) == want, (l1, l2, X, P)
+    for it in range(2000):
+        P = int(rng.choice([0, 0, -1, -4, 3]))
+        M = np.ascontiguousarray(mats[it % len(mats)], dtype=np.int32)
+        member = rng.integers(0, 24, 12).astype(np.uint8)
+        query = rng.integers(0, 24, 12).astype(np.uint8)
+        want, _ = O.score_with_shift(member, query, M, 3, P)
+        assert shim.shim_score12x3(_pack_word(query), _pack_word(member), M.ctypes.data_as(i32p), P) == want, (it, P)
+
+
+def test_device_scalar_scorer_against_the_oracle(shim, blosum62, golden_dir):
+    """hmk_pair_score(_strided) == ShiftedScorer.sequenceScore as the oracle restates it: every pair of lengths 1..36 the
+    packed kernels do NOT take falls back to exactly this function on the device"""
+    z = np.load(os.path.join(golden_dir, "matrices.npz"))
+    big = (blosum62.astype(np.int64) * 90000000).astype(np.int32)       # sums wrap like Java ints
+    mats = [blosum62, z["pam250"], z["blosum100"], big]
+    rng = np.random.default_rng(8)
+    u8p, i32p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int32)
+    n = 0
+    for it in range(4000):
+        l1, l2 = int(rng.integers(1, 37)), int(rng.integers(1, 37))
+        X = int(rng.integers(0, min(l1, l2)))
+        P = int(rng.choice([0, 0, -1, -4, 3, -2000000000]))
+        M = np.ascontiguousarray(mats[it % len(mats)], dtype=np.int32)
+        a = rng.integers(0, 24, l1).astype(np.uint8)
+        b = rng.integers(0, 24, l2).astype(np.uint8)
+        want, _ = O.score_with_shift(a, b, M, X, P)
+        got = shim.shim_pair_score(a.ctypes.data_as(u8p), l1, b.ctypes.data_as(u8p), l2, M.ctypes.data_as(i32p), X, P)
+        assert got == want, (l1, l2, X, P, it % len(mats))
+        # position-major copies with strides, as the generic kernel stages them in shared memory
+        s1, s2 = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        a2 = np.zeros(l1 * s1, np.uint8); a2[::s1] = a
+        b2 = np.zeros(l2 * s2, np.uint8); b2[::s2] = b
+        got = shim.shim_pair_score_strided(a2.ctypes.data_as(u8p), s1, l1, b2.ctypes.data_as(u8p), s2, l2, M.ctypes.data_as(i32p), X, P)
+        assert got == want
+        assert shim.shim_pair_cells(l1, l2, X) == O.pair_cells(l1, l2, X)
+        n += 1
+    assert n == 4000
+    # the reference's argument roles: equal lengths make the SECOND sequence the sliding one (ShiftedScorer.java:51-57)
+    asym = blosum62.copy()
+    asym[0, 1] += 7
+    a, b = np.array([0, 1, 2, 3], np.uint8), np.array([1, 0, 3, 2], np.uint8)
+    M = np.ascontiguousarray(asym, dtype=np.int32)
+    for x, y in ((a, b), (b, a)):
+        assert shim.shim_pair_score(x.ctypes.data_as(u8p), 4, y.ctypes.data_as(u8p), 4, M.ctypes.data_as(i32p), 1, 0) == O.score_with_shift(x, y, M, 1, 0)[0]
+
+
+def test_device_partner_key_and_cluster_order(shim):
+    """bigger hmk_key_make == preferred partner (score desc, then rank under (abundance desc, id asc) asc); hmk_consider ==
+    NearestClusterRunner's order (score desc, size desc, id asc; ClinkageSequenceClusterer.java:258-293), whatever the
+    order the candidates arrive in"""
+    rng = np.random.default_rng(9)
+    scores = [-(2 ** 31), -(2 ** 31) + 1, -5, -1, 0, 1, 19, 20, 2 ** 31 - 1]
+    ranks = [0, 1, 2, 1000, 2 ** 31, 2 ** 32 - 1]
+    keys = [(s, r, shim.shim_key_make(s, r)) for s in scores for r in ranks]
+    for s, r, k in keys:
+        assert shim.shim_key_score(k) == s and shim.shim_key_rank(k) == r
+    by_key = [(s, r) for s, r, k in sorted(keys, key=lambda t: -t[2])]
+    assert by_key == sorted([(s, r) for s, r, _ in keys], key=lambda t: (-t[0], t[1]))
+    assert shim.shim_wadd(2 ** 31 - 1, 1) == -(2 ** 31) and shim.shim_wmul(65536, 65536) == 0 and shim.shim_wmul(-3, 5) == -15
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    for it in range(300):
+        n = int(rng.integers(1, 12))
+        sc = rng.integers(18, 22, n).astype(np.int32)
+        sz = rng.integers(1, 4, n).astype(np.int32)
+        fid = rng.permutation(50)[:n].astype(np.int32)
+        want = min(range(n), key=lambda i: (-int(sc[i]), -int(sz[i]), int(fid[i])))
+        assert shim.shim_best_cluster(n, sc.ctypes.data_as(i32p), sz.ctypes.data_as(i32p), fid.ctypes.data_as(i32p)) == want
+    assert shim.shim_best_cluster(0, None, None, None) == -1
