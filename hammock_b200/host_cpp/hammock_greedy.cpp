@@ -2,6 +2,8 @@
 // top of libhammock_b200: fasta/tab input -> ordering + automatic parameters -> GPU greedy clustering
 // -> initial_clusters*.tsv in the reference's format, so that the unchanged Java `cluster` mode
 // (`java -jar Hammock.jar cluster -i <outdir>/initial_clusters_sequences.tsv`) can take over.
+// `hammock_greedy clinkage ...` is the `clinkage` mode (Hammock.java:236-252, 449-489): the exact complete-linkage
+// clusterer on the sequences in INPUT order (no sorting, no cluster limit), same result files.
 // Flags keep the reference's names (Hammock.java:824-970).  Multiple alignments are NOT built here
 // (that is the Clustal-Omega stage, outside this path): the alignment column is "NA" for multi-member
 // clusters, which `cluster` mode accepts.
@@ -13,7 +15,7 @@
 using namespace hammock;
 
 static void usage() {
-    std::cerr << "usage: hammock_greedy -i <input.fa> -d <outdir> [-f fasta|tab] [-m <matrix.txt>] [-g <threshold>] [-x <max_shift>]\n"
+    std::cerr << "usage: hammock_greedy [greedy|clinkage] -i <input.fa> -d <outdir> [-f fasta|tab] [-m <matrix.txt>] [-g <threshold>] [-x <max_shift>]\n"
                  "                      [-p <gap_penalty>] [--initial_clusters_limit <n>] [-R size|alphabetic|random|input|<label>]\n"
                  "                      [-S <seed>] [-l label1,label2,...] [--device <n>] [--dump-prepared]\n";
 }
@@ -21,6 +23,7 @@ static void usage() {
 int main(int argc, char** argv) {
     std::string input, outdir, format = "fasta", matrixPath, order = "size";
     bool haveT = false, haveX = false, haveK = false, dump = false, haveLabels = false, timeHost = false, hostOnly = false;
+    bool clinkage = false;
     int32_t threshold = 0, maxShift = 0, shiftPenalty = 0, limit = 0;   // shiftPenalty default 0 (Hammock.java:82)
     int64_t seed = 42;                                                   // Hammock.java:67
     int device = 0;
@@ -33,11 +36,14 @@ int main(int argc, char** argv) {
                 return argv[++i];
             };
             if (a == "greedy") continue;
+            else if (a == "clinkage" && i == 1) clinkage = true;
             else if (a == "-i" || a == "--input") input = next();
             else if (a == "-d" || a == "--outputDirectory") outdir = next();
             else if (a == "-f" || a == "--file_format") format = next();
             else if (a == "-m" || a == "--matrix") matrixPath = next();
-            else if (a == "-g" || a == "--greedy_threshold" || a == "--alignment_threshold") { threshold = decode_int(next()); haveT = true; }
+            else if (a == "-g" || a == "--greedy_threshold" || a == "--alignment_threshold" || a == "--clinkage_threshold") {
+                threshold = decode_int(next()); haveT = true;
+            }
             else if (a == "-x" || a == "--max_shift") { maxShift = decode_int(next()); haveX = true; }
             else if (a == "-p" || a == "--gap_penalty") shiftPenalty = decode_int(next());
             else if (a == "--initial_clusters_limit") { limit = decode_int(next()); haveK = true; }
@@ -82,11 +88,12 @@ int main(int argc, char** argv) {
         // prepareSequenceClustering (Hammock.java:795-817)
         if (!haveLabels) labels = getSortedLabels(sequences);
         if (!haveX) maxShift = getMaxShift(sequences); else maxShift = checkMaxShift(sequences, maxShift);
-        if (!haveT) threshold = setGreedyThreshold(sequences);            // Hammock.java:394-397
+        if (!haveT) threshold = clinkage ? setClinkageThreshold(sequences) : setGreedyThreshold(sequences);   // Hammock.java:394-397, 452-455
         if (!haveK) limit = initialClustersLimit(sequences);              // :398-401
         lap("labels + automatic parameters");
         std::vector<int> cameFrom;                                        // input position of every sorted sequence
-        sortSequences(sequences, order, labels, seed, &cameFrom);         // :407 (the reference copies the list instead, :800)
+        // greedy: :407 (the reference copies the list instead, :800); clinkage clusters the list as loaded (:449-462)
+        sortSequences(sequences, clinkage ? "input" : order, labels, seed, &cameFrom);
         lap("sortSequences");
         if (hostOnly) return 0;
 
@@ -98,11 +105,14 @@ int main(int argc, char** argv) {
             return 0;
         }
 
-        GpuGreedySequenceClusterer clusterer{loadScoringMatrix(matrixPath), shiftPenalty, maxShift, threshold, limit, device};
-        std::cerr << "Greedy clustering... (" << sequences.size() << " unique sequences, threshold " << threshold << ", max shift "
-                  << maxShift << ", clusters limit " << limit << ")\n";
+        const std::vector<int32_t> matrix = loadScoringMatrix(matrixPath);
+        std::cerr << (clinkage ? "Clinkage" : "Greedy") << " clustering... (" << sequences.size() << " unique sequences, threshold " << threshold
+                  << ", max shift " << maxShift;
+        if (!clinkage) std::cerr << ", clusters limit " << limit;
+        std::cerr << ")\n";
         auto t0 = std::chrono::steady_clock::now();
-        std::vector<Cluster> clusters = clusterer.cluster(sequences);
+        std::vector<Cluster> clusters = clinkage ? GpuClinkageSequenceClusterer{matrix, shiftPenalty, maxShift, threshold, device}.cluster(sequences)
+                                                 : GpuGreedySequenceClusterer{matrix, shiftPenalty, maxShift, threshold, limit, device}.cluster(sequences);
         auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
         std::cerr << "Ready. Clustering time: " << ms << "\nResulting clusers: " << clusters.size() << "\n";   // Hammock.java:411-412
 
@@ -115,7 +125,8 @@ int main(int argc, char** argv) {
             saveClusterSequencesToCsv(clusters, sequences, d + "initial_clusters_sequences.tsv", labels);
             saveClusterSequencesToCsvOrdered(clusters, sequences, inputOrder, d + "initial_clusters_sequences_original_order.tsv", labels);
             SaveClustersToCsv(clusters, sequences, d + "initial_clusters.tsv", labels);
-            std::cerr << "Greedy clustering results in: " << d << "initial_clusters.tsv\nand: " << d << "initial_clusters_sequences.tsv\n";
+            std::cerr << (clinkage ? "Clinkage" : "Greedy") << " clustering results in: " << d << "initial_clusters.tsv\nand: " << d
+                      << "initial_clusters_sequences.tsv\n";
         }
         hmk_release_cached();
         return 0;

@@ -36,6 +36,7 @@ struct NullPointerException : HammockException {   // LimitedGreedySequenceClust
         : HammockException("NullPointerException in greedy phase 1, step " + std::to_string(s)), step(s) {}
 };
 struct CudaException : HammockException { using HammockException::HammockException; };
+struct UnsupportedInput : HammockException { using HammockException::HammockException; };   // HMK_STATUS_UNSUPPORTED (clinkage entry)
 
 static const char* const ALPHABET = "ARNDCQEGHILKMFPSTWYVBZX*";   // UniqueSequence.java:23-26
 
@@ -444,6 +445,7 @@ inline double getMeanSequenceLength(const std::vector<UniqueSequence>& s) {   //
     return (double)sum / (double)s.size();
 }
 inline int32_t setGreedyThreshold(const std::vector<UniqueSequence>& s) { return java_round(getMeanSequenceLength(s) * 1.7); }   // :1409-1413
+inline int32_t setClinkageThreshold(const std::vector<UniqueSequence>& s) { return java_round(getMeanSequenceLength(s) * 1.7); } // :1415-1419
 inline int32_t checkMaxShift(const std::vector<UniqueSequence>& s, int32_t maxShift) {   // :1421-1427
     int32_t mn = INT32_MAX;
     for (auto& q : s) mn = std::min<int32_t>(mn, (int32_t)q.length());
@@ -454,11 +456,17 @@ inline int32_t initialClustersLimit(const std::vector<UniqueSequence>& s) { retu
 
 // ---------------------------------------------------------------- the clusterer (SequenceClusterer seam)
 // List<Cluster> from the arrays of the C ABI: members by rank, clusters in result order
+// (ids: greedy 0 .. n-1 = the founder's index; clinkage 1 .. 2n+1 = Cluster ids in creation order)
 inline std::vector<Cluster> rebuildClusters(int32_t n, const int32_t* cid, const int32_t* rank, const int32_t* order, int32_t nResult,
                                             const int32_t* abundance) {
-    std::vector<int> start(n + 2, 0);
+    int32_t maxId = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (cid[i] < 0) throw HammockException("negative cluster id");
+        maxId = std::max(maxId, cid[i]);
+    }
+    std::vector<int> start((size_t)maxId + 2, 0);
     for (int32_t i = 0; i < n; i++) start[cid[i] + 1]++;
-    for (int32_t i = 0; i <= n; i++) start[i + 1] += start[i];
+    for (int32_t i = 0; i <= maxId; i++) start[i + 1] += start[i];
     std::vector<int> byRank(n);
     for (int32_t i = 0; i < n; i++) byRank[start[cid[i]] + rank[i]] = i;
     std::vector<Cluster> result;
@@ -475,6 +483,23 @@ inline std::vector<Cluster> rebuildClusters(int32_t n, const int32_t* cid, const
 
 // == new LimitedGreedySequenceClusterer(new ShiftedScorer(matrix, shiftPenalty, maxShift), threshold,
 //    maxClusters).cluster(sequences)   (Hammock.java:402-409)
+// the arrays of hmk_greedy_in for a sequence list in the caller's order
+struct PackedSequences {
+    std::vector<uint8_t> res;
+    std::vector<int32_t> off, ab;
+    explicit PackedSequences(const std::vector<UniqueSequence>& seqs) : off(seqs.size() + 1, 0), ab(seqs.size()) {
+        size_t total = 0;
+        for (auto& q : seqs) total += q.length();
+        res.reserve(total + 1);
+        for (size_t i = 0; i < seqs.size(); i++) {
+            for (size_t k = 0; k < seqs[i].length(); k++) res.push_back(seqs[i].code(k));
+            off[i + 1] = (int32_t)res.size();
+            ab[i] = seqs[i].size();
+        }
+        if (res.empty()) res.push_back(0);
+    }
+};
+
 struct GpuGreedySequenceClusterer {
     std::vector<int32_t> matrix;
     int32_t shiftPenalty, maxShift, threshold, maxClusters;
@@ -482,17 +507,10 @@ struct GpuGreedySequenceClusterer {
 
     std::vector<Cluster> cluster(const std::vector<UniqueSequence>& seqs) const {
         const int32_t n = (int32_t)seqs.size();
-        std::vector<int32_t> off(n + 1, 0), ab(n), cid(std::max(n, 1)), rank(std::max(n, 1)), order(std::max(n, 1));
-        std::vector<uint8_t> res;
-        size_t total = 0;
-        for (auto& q : seqs) total += q.length();
-        res.reserve(total + 1);
-        for (int32_t i = 0; i < n; i++) {
-            for (size_t k = 0; k < seqs[i].length(); k++) res.push_back(seqs[i].code(k));
-            off[i + 1] = (int32_t)res.size();
-            ab[i] = seqs[i].size();
-        }
-        if (res.empty()) res.push_back(0);
+        std::vector<int32_t> cid(std::max(n, 1)), rank(std::max(n, 1)), order(std::max(n, 1));
+        const PackedSequences packed(seqs);
+        const std::vector<uint8_t>& res = packed.res;
+        const std::vector<int32_t>&off = packed.off, &ab = packed.ab;
         hmk_greedy_in in{n, res.data(), off.data(), ab.data(), matrix.data(), threshold, maxShift, shiftPenalty, maxClusters};
         hmk_greedy_out out{cid.data(), rank.data(), order.data(), 0, 0, -1};
         char err[512] = {0};
@@ -502,6 +520,29 @@ struct GpuGreedySequenceClusterer {
         if (rc == HMK_STATUS_BAD_RESIDUE) throw FileFormatException(err);
         if (rc != HMK_STATUS_OK) throw CudaException(std::string("hammock_b200: ") + err);
         return rebuildClusters(n, cid.data(), rank.data(), order.data(), out.n_result, ab.data());
+    }
+};
+
+// == new ClinkageSequenceClusterer(new ShiftedScorer(matrix, shiftPenalty, maxShift), threshold).cluster(sequences)
+//    (Hammock.java:457-462): sequences in the caller's order (runClinkageClustering does not sort)
+struct GpuClinkageSequenceClusterer {
+    std::vector<int32_t> matrix;
+    int32_t shiftPenalty, maxShift, threshold;
+    int device = 0;
+
+    std::vector<Cluster> cluster(const std::vector<UniqueSequence>& seqs) const {
+        const int32_t n = (int32_t)seqs.size();
+        std::vector<int32_t> cid(std::max(n, 1)), rank(std::max(n, 1)), order(std::max(n, 1));
+        const PackedSequences packed(seqs);
+        hmk_greedy_in in{n, packed.res.data(), packed.off.data(), packed.ab.data(), matrix.data(), threshold, maxShift, shiftPenalty, 0};
+        hmk_greedy_out out{cid.data(), rank.data(), order.data(), 0, 0, -1};
+        char err[512] = {0};
+        int rc = hmk_clinkage_cluster(&in, &out, device, err, sizeof err);
+        if (rc == HMK_STATUS_SHIFT_TOO_BIG) throw DataException(err);
+        if (rc == HMK_STATUS_BAD_RESIDUE) throw FileFormatException(err);
+        if (rc == HMK_STATUS_UNSUPPORTED) throw UnsupportedInput(err);
+        if (rc != HMK_STATUS_OK) throw CudaException(std::string("hammock_b200: ") + err);
+        return rebuildClusters(n, cid.data(), rank.data(), order.data(), out.n_result, packed.ab.data());
     }
 };
 

@@ -36,6 +36,16 @@ int main(int argc, char** argv) {
         for (auto& v : rank) f >> v;
         for (auto& v : order) f >> v;
         for (int32_t i = 0; i < n; i++) ab[i] = sequences[i].size();
+        {   // the arrays the clusterers hand to the C ABI
+            const PackedSequences packed(sequences);
+            std::ofstream pf(std::string(argv[5]) + "packed.txt");
+            for (auto v : packed.off) pf << v << ' ';
+            pf << '\n';
+            for (auto v : packed.ab) pf << v << ' ';
+            pf << '\n';
+            for (auto v : packed.res) pf << (int)v << ' ';
+            pf << '\n';
+        }
         lap("read the clustering (test input)");
         std::vector<Cluster> clusters = rebuildClusters(n, cid.data(), rank.data(), order.data(), nResult, ab.data());
         std::vector<int> inputOrder(sequences.size());

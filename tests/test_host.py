@@ -211,7 +211,8 @@ ACDEFGHIKLMN
 def _dump(tmp_path, args):
     import subprocess
     exe = hb_build.build_host()
-    out = subprocess.run([exe, "greedy"] + args + ["--dump-prepared"], capture_output=True, text=True, check=True).stdout.splitlines()
+    mode = [] if args and args[0] == "clinkage" else ["greedy"]
+    out = subprocess.run([exe] + mode + args + ["--dump-prepared"], capture_output=True, text=True, check=True).stdout.splitlines()
     head = {l.split("\t")[0]: l.split("\t")[1:] for l in out[:4]}
     return head, [tuple(l.split("\t")) for l in out[4:]]
 
@@ -409,6 +410,8 @@ def test_cpp_host_files_from_the_oracle_clustering(tmp_path, blosum62, order):
     r = subprocess.run([exe, str(fa), order, "11", str(tmp_path / "result.txt"), str(out) + "/"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert r.stdout.splitlines() == [f"{s.get_sequence_string()}\t{s.size()}" for s in ordered]
+    packed = [[int(v) for v in line.split()] for line in (out / "packed.txt").read_text().splitlines()]
+    assert packed[0] == offs.tolist() and packed[1] == ab.tolist() and packed[2] == res.tolist()      # what goes into hmk_greedy_in
     clusters = hb.rebuild_clusters(ordered, hb.GreedyResult(R.cluster_id, R.member_rank, R.result_order, R.n_multi, {}))
     tup = lambda s: (s.get_sequence_string(), dict(s.labels_map))
     ct = [(c.get_id(), [tup(s) for s in c.get_sequences()]) for c in clusters]
@@ -560,3 +563,50 @@ def test_device_partner_key_and_cluster_order(shim):
         want = min(range(n), key=lambda i: (-int(sc[i]), -int(sz[i]), int(fid[i])))
         assert shim.shim_best_cluster(n, sc.ctypes.data_as(i32p), sz.ctypes.data_as(i32p), fid.ctypes.data_as(i32p)) == want
     assert shim.shim_best_cluster(0, None, None, None) == -1
+
+
+def test_cpp_host_files_from_the_oracle_clinkage_clustering(tmp_path, blosum62):
+    """the `clinkage` mode of the C++ driver around the oracle's exact complete-linkage clustering: input order (no sort),
+    Cluster ids 1 .. 2n+1, list order of the emulated HashSet -- files against the oracle's writers"""
+    import subprocess
+    from oracle import pyref_writers as W
+    exe = _writers_harness(tmp_path)
+    d = synth.generate(400, 9, 12, seed=5)
+    strs = synth.to_strings(d["residues"], d["offsets"])
+    rng = np.random.default_rng(6)
+    labs = ["x", "yy"]
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for k, i in enumerate(rng.permutation(len(strs))):
+            f.write(f">r{k}|{int(rng.integers(1, 30))}|{labs[k % 2]}\n{strs[i]}\n")
+    seqs = hb.load_unique_sequences_from_fasta(str(fa))
+    labels = hb.get_sorted_labels(seqs)
+    res, offs, ab = hb.pack_sequences(seqs)
+    T, X = hb.set_clinkage_threshold(seqs), hb.get_max_shift(seqs)
+    R = O.clinkage_cluster(res, offs, ab, blosum62, T, X, 0)
+    assert R.status == 0 and int(R.cluster_id.max()) > len(seqs)          # merged clusters carry ids beyond n
+    with open(tmp_path / "result.txt", "w") as f:
+        f.write(f"{len(seqs)} {len(R.result_order)}\n")
+        for a in (R.cluster_id, R.member_rank, R.result_order):
+            f.write(" ".join(str(int(v)) for v in a) + "\n")
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([exe, str(fa), "input", "0", str(tmp_path / "result.txt"), str(out) + "/"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n_multi = int((np.bincount(R.cluster_id) > 1).sum())
+    clusters = hb.rebuild_clusters(seqs, hb.GreedyResult(R.cluster_id, R.member_rank, R.result_order, n_multi, {}))
+    tup = lambda s: (s.get_sequence_string(), dict(s.labels_map))
+    ct = [(c.get_id(), [tup(s) for s in c.get_sequences()]) for c in clusters]
+    assert (out / "initial_clusters_sequences.tsv").read_text() == W.cluster_sequences_tsv(ct, labels)
+    assert (out / "initial_clusters_sequences_original_order.tsv").read_text() == W.cluster_sequences_tsv_ordered(ct, labels, [tup(s) for s in seqs])
+    assert (out / "initial_clusters.tsv").read_text() == W.clusters_tsv(ct, labels)
+
+
+def test_cpp_driver_clinkage_mode_prepares_like_the_reference(tmp_path):
+    """hammock_greedy clinkage: sequences stay in input order, threshold = setClinkageThreshold (Hammock.java:449-455, 1415-1419)"""
+    p = tmp_path / "in.fa"
+    p.write_text(MULTI)
+    head, rows = _dump(tmp_path, ["clinkage", "-i", str(p), "-R", "size"])
+    seqs = hb.load_unique_sequences_from_fasta(str(p))
+    assert int(head["threshold"][0]) == hb.set_clinkage_threshold(seqs) and int(head["max_shift"][0]) == hb.get_max_shift(seqs)
+    assert rows == [(s.get_sequence_string(), str(s.size())) for s in seqs]
