@@ -131,7 +131,8 @@ def test_musi_clinkage_golden_gpu(golden_dir, blosum62):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [(2, 12, 12, 1), (3, 12, 12, 2), (40, 12, 12, 3), (700, 7, 12, 4), (1500, 12, 12, 5), (900, 9, 9, 6),
-                                  (600, 16, 16, 7), (400, 7, 30, 8), (3000, 12, 12, 9)])
+                                  (600, 16, 16, 7), (400, 7, 30, 8), (3000, 12, 12, 9),
+                                  (12, 12, 12, 10), (13, 12, 12, 11), (25, 9, 12, 12), (49, 12, 12, 13)])   # HashMap growth points
 def test_clinkage_gpu_vs_oracle(golden_dir, blosum62, case):
     n, lo, hi, seed = case
     z = np.load(os.path.join(golden_dir, "matrices.npz"))
@@ -164,3 +165,93 @@ def test_clinkage_gpu_status_codes(blosum62):
     assert _gpu(empty, blosum62, 20, 3, 0)[0] == _lib.STATUS_BAD_ARG
     bad = {"residues": np.array([1, 2, 24, 3], np.uint8), "offsets": np.array([0, 2, 4], np.int32), "abundance": np.array([1, 1], np.int32)}
     assert _gpu(bad, blosum62, 20, 1, 0)[0] == _lib.STATUS_BAD_RESIDUE
+
+
+# ------------------------------------------------------------------------------------------------ CPU model of the chain kernel
+def _chain_kernel_model(pair, ab, T):
+    """The LOGIC of hmk_clinkage_chain (hmk_kernels.cuh), not its CUDA -- where it differs in structure from both oracles:
+    a thresholded score matrix whose rows are merged by element-wise minimum INTO THE SLOT OF THE STACK TOP, the active set
+    as bins of a table that has its FINAL capacity from the start (the claim: HashMap's order-preserving resize makes that
+    equivalent to growing it), removal by unlinking, and the ready set rebuilt with real resizes at the end."""
+    n = len(ab)
+    BELOW = -(2 ** 31) + 1
+    D = [[(int(pair[a][b]) if pair[a][b] >= T else BELOW) for b in range(n)] for a in range(n)]
+    hsh = lambda cid: ((553 + cid) & 0xFFFFFFFF) ^ (((553 + cid) & 0xFFFFFFFF) >> 16)
+    acap = 16
+    while n > int(acap * 0.75):
+        acap *= 2
+    bins = [[] for _ in range(acap)]
+    id_of = [i + 1 for i in range(n)]
+    slot_of = {i + 1: i for i in range(n)}
+    size_of = [int(a) for a in ab]
+    members = [[i] for i in range(n)]
+    for cid in range(1, n + 1):
+        bins[hsh(cid) & (acap - 1)].append(cid)
+    nactive, cur_id, stack, ready = n, n + 1, [], []
+    while True:
+        if not stack:
+            if nactive <= 1:
+                break
+            stack.append(next(b for b in bins if b)[0])
+        top = stack[-1]
+        ts = slot_of[top]
+        best = None                                    # (score, size, id) under score desc, size desc, id asc
+        for k in range(n):
+            if id_of[k] < 0 or k == ts:
+                continue
+            cand = (D[ts][k], size_of[k], id_of[k])
+            if best is None or (-cand[0], -cand[1], cand[2]) < (-best[0], -best[1], best[2]):
+                best = cand
+        bscore = best[0] if best else -(2 ** 31)
+        if bscore < T:
+            stack.pop()
+            ready.append(top)
+            bins[hsh(top) & (acap - 1)].remove(top)
+            nactive -= 1
+            id_of[ts] = -1
+        elif len(stack) > 1 and stack[-2] == best[2]:
+            bs = slot_of[best[2]]
+            for k in range(n):
+                m = min(D[ts][k], D[bs][k])
+                D[ts][k] = m
+                D[k][ts] = m
+            cur_id += 1
+            stack.pop(); stack.pop()
+            for cid in (top, best[2]):
+                bins[hsh(cid) & (acap - 1)].remove(cid)
+            members[ts] = members[ts] + members[bs]
+            size_of[ts] = (size_of[ts] + size_of[bs] + 2 ** 31) % 2 ** 32 - 2 ** 31
+            id_of[ts], id_of[bs] = cur_id, -1
+            slot_of[cur_id] = ts
+            bins[hsh(cur_id) & (acap - 1)].append(cur_id)
+            nactive -= 1
+        else:
+            stack.append(best[2])
+    ready.append(next(b for b in bins if b)[0])
+    rs = PC.JavaHashSet()                              # the ready set grows like a real HashSet (the kernel does the same)
+    for cid in ready:
+        rs.add(cid)
+    order = list(rs)
+    cluster_id, member_rank = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    for cid in order:
+        for r, m in enumerate(members[slot_of[cid]]):
+            cluster_id[m], member_rank[m] = cid, r
+    return cluster_id, member_rank, np.array(order, np.int32)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 11, 12, 13, 14, 24, 25, 26, 48, 49, 50, 96, 97, 130])
+def test_chain_kernel_scheme_model(blosum62, n):
+    """sizes around the HashMap growth points (12, 24, 48, 96 entries): the final-capacity table of the kernel against the
+    second restatement, which grows a real node table"""
+    from oracle.pyref import PyRef
+    for seed in range(3):
+        d, seqs, T, X = _input_order_case(n, 9, 12, 100 * n + seed)
+        ref = PyRef(seqs, d["abundance"], blosum62, T, X, 0, 0)
+        pair = np.empty((n, n), dtype=np.int64)
+        for q in range(n):
+            pair[:, q] = ref.scores(np.arange(n), q)
+        for T2 in (T, T - 7):
+            want = PC.clinkage_cluster(seqs, d["abundance"], blosum62, T2, X, 0)
+            got = _chain_kernel_model(pair, d["abundance"], T2)
+            for g, w in zip(got, want):
+                assert (g == w).all(), (n, seed, T2)
