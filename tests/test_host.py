@@ -610,3 +610,60 @@ def test_cpp_driver_clinkage_mode_prepares_like_the_reference(tmp_path):
     seqs = hb.load_unique_sequences_from_fasta(str(p))
     assert int(head["threshold"][0]) == hb.set_clinkage_threshold(seqs) and int(head["max_shift"][0]) == hb.get_max_shift(seqs)
     assert rows == [(s.get_sequence_string(), str(s.size())) for s in seqs]
+
+
+def _driver(args):
+    import subprocess
+    exe = hb_build.build_host()
+    return subprocess.run([exe, "greedy"] + args + ["--dump-prepared"], capture_output=True, text=True)
+
+
+def test_cpp_loader_error_paths_match_the_python_host(tmp_path):
+    """the rewritten C++ loader fails where the reference does (FileIOManager.java:159-216, UniqueSequence.java:51-54):
+    same cases as the Python host and the oracle loader, exit code 1 and the reference's message"""
+    p = tmp_path / "in.fa"
+    cases = {">x|0|l\nACD\n": "count lower than 1", "ACD\n": "Incorrect fasta format", ">x|1\nACDJ\n": "not a valid letter",
+             ">x|abc\nACD\n": "NumberFormatException", ">x|1\n": None, "": "Incorrect fasta format", ">x|99999999999|l\nACD\n": "NumberFormatException",
+             ">x|-3|l\nACD\n": "count lower than 1"}
+    for text, msg in cases.items():
+        p.write_text(text)
+        r = _driver(["-i", str(p)])
+        try:
+            seqs = hb.load_unique_sequences_from_fasta(str(p))
+            py_ok = True
+        except hb.FileFormatException:
+            py_ok = False
+        if msg is None:            # a header without a sequence line: one empty sequence in both hosts (then "Shift too big" territory)
+            assert py_ok == (r.returncode == 0), (text, r.stderr)
+            continue
+        assert not py_ok and r.returncode == 1 and msg in r.stderr, (text, r.returncode, r.stderr)
+
+
+def test_cpp_loader_odd_headers_tab_format_and_label_filter(tmp_path):
+    text = (">a|3|lab1||\nWVTAPRSLPVLP\n"            # trailing empty fields are dropped by String.split
+            ">b|0x10||x\nGSWVVDISNVED  \n"          # hex count, EMPTY label (a fourth field keeps the third)
+            ">c| 7 |lab1\n  wvtaprslpvlp\n"         # count is trimmed; lower case is a different map key, same sequence
+            ">d|010|lab2\nGSWVVDISNVED\n"           # Integer.decode: leading zero = octal 8
+            ">e|+5|lab2\nACDEFGHIKLMN\r\n")
+    p = tmp_path / "in.fa"
+    p.write_text(text)
+    seqs = hb.load_unique_sequences_from_fasta(str(p))
+    assert [(s.get_sequence_string(), s.labels_map) for s in seqs] == [
+        ("WVTAPRSLPVLP", {"lab1": 3}), ("GSWVVDISNVED", {"": 16, "lab2": 8}), ("WVTAPRSLPVLP", {"lab1": 7}), ("ACDEFGHIKLMN", {"lab2": 5})]
+    r = _driver(["-i", str(p), "-R", "input"])
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.splitlines()
+    assert out[3].split("\t")[1:] == hb.get_sorted_labels(seqs)
+    assert [tuple(l.split("\t")) for l in out[4:]] == [(s.get_sequence_string(), str(s.size())) for s in seqs]
+    # -l: only sequences carrying one of the labels, with only those labels (Hammock.java:1661-1675)
+    r = _driver(["-i", str(p), "-R", "input", "-l", "lab2"])
+    assert [tuple(l.split("\t")) for l in r.stdout.splitlines()[4:]] == [("GSWVVDISNVED", "8"), ("ACDEFGHIKLMN", "5")]
+    # tab format (FileIOManager.java:227-255): zero counts are dropped, no de-duplication
+    t = tmp_path / "in.tsv"
+    t.write_text("sequence\tl1\tl2\nWVTAPRSLPVLP\t3\t0\nGSWVVDISNVED\t0x2\t5\nwvtaprslpvlp\t0\t1\n")
+    seqs = hb.load_unique_sequences_from_table(str(t))
+    r = _driver(["-i", str(t), "-f", "tab", "-R", "size"])
+    assert r.returncode == 0, r.stderr
+    ordered = hb.sort_sequences(seqs, "size", hb.get_sorted_labels(seqs))
+    assert [tuple(l.split("\t")) for l in r.stdout.splitlines()[4:]] == [(s.get_sequence_string(), str(s.size())) for s in ordered]
+    assert r.stdout.splitlines()[3].split("\t")[1:] == hb.get_sorted_labels(seqs)
