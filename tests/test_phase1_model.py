@@ -84,8 +84,11 @@ def sequential(S, ab, T, K):
 
 # ------------------------------------------------------------------------------------------------ the engine's scheme
 class Model:
-    def __init__(self, S, ab, T, K, batch, kb, win, gate, depth, rng):
+    def __init__(self, S, ab, T, K, batch, kb, win, gate, depth, rng, join_lanes=False):
         self.S, self.ab, self.T, self.K = S, ab, T, K
+        # join_lanes: NOT in the kernel -- the extension DESIGN.md section 10 proposes (window lanes that join their best
+        # pre-batch cluster), kept here so that its trust conditions stay checked against the sequential loop
+        self.join_lanes = join_lanes
         self.n = len(ab)
         # a window never reaches the LAST unprocessed sequence (whose empty sub-list is the null-object case): every lane
         # consumes at most two sequences, so more than 2 x lanes must be left (the kernel: 32 lanes, gate 96)
@@ -96,7 +99,7 @@ class Model:
         self.cur, self.unproc = 0, self.n
         self.steps = 0
         self.status, self.npe_step = CONTINUE, -1
-        self.stats = {"windows": 0, "window_steps": 0, "sequential": 0, "restarts": 0, "prepared": 0}
+        self.stats = {"windows": 0, "window_steps": 0, "sequential": 0, "restarts": 0, "prepared": 0, "window_joins": 0}
         # phase-2 hit reuse (Engine::phase2, hmk_member_check mode 2): every qualifying hit of every partner search, tagged
         # with the batch that produced it, and per sequence the batch in which it was RESOLVED as a query
         self.batch_id = 0
@@ -197,6 +200,11 @@ class Model:
             if penalty == 0 and ncl > 0 and ncl < K and self.unproc > self.gate and self.win > 0:
                 W = min(self.win, nq - b)
                 kind, bid, bscore, bpick = [3] * W, [-1] * W, [JMIN] * W, [0] * W
+                jt = [-1] * W                      # join lanes (kind 4): the cluster they join
+
+                def can_join(bi):                  # its static best is still THE best pre-batch cluster, untouched
+                    sb_ = s_best[bi]
+                    return self.join_lanes and sb_ is not None and bi not in dirty and sb_[3] not in touched
                 for l in range(W):
                     bi = b + l
                     q = qid[bi]
@@ -211,22 +219,32 @@ class Model:
                         bpick[l], bid[l], bscore[l] = pick, lists[bi]["id"][pick], lists[bi]["score"][pick]
                         if not (sb is not None and sb[0] >= bscore[l]):
                             kind[l] = 1
+                        elif can_join(bi):         # a_score >= b_score whichever listed partner is still alive
+                            kind[l], jt[l] = 4, sb[3]
                     elif sb is None:
                         kind[l] = 2
+                    elif can_join(bi):             # no partner at all (and the list was complete)
+                        kind[l], jt[l] = 4, sb[3]
                 cm0 = [k == 1 for k in kind]
                 for l in range(W):                 # clusters born in this batch, incl. by earlier lanes of the window
-                    if kind[l] not in (1, 2):
+                    if kind[l] not in (1, 2, 4):
                         continue
                     bi = b + l
                     founders = fmask | {b + j for j in range(l) if cm0[j]}
                     hm = ibm2[bi] if kind[l] == 1 else ibm[bi]
-                    need = max(bscore[l], T) if kind[l] == 1 else T
+                    need = max(bscore[l], T) if kind[l] == 1 else (s_best[bi][0] if kind[l] == 4 else T)
                     for b2 in founders & hm:
                         pk = bpick[b2 - b] if b2 >= b else f_pick[b2]
                         if min(ib[bi][b2], pd[bi][b2][pk]) >= need:
                             kind[l] = 3
                             break
                 bad = [k == 3 for k in kind]
+                jt0 = list(jt)
+                for l in range(W):                 # a join lane needs its cluster as it was: no earlier lane may join it,
+                    if kind[l] == 4:               # nor grow a cluster that ties with it on the score (size decides ties)
+                        ties = {cc[0] for cc in static[b + l][0] if cc[1] == s_best[b + l][0]}
+                        if any(jt0[j] in ties for j in range(l)):
+                            bad[l] = True
                 for l in range(W):
                     q = qid[b + l]
                     taken = any(kind[j] == 1 and bid[j] == q for j in range(l))
@@ -246,6 +264,19 @@ class Model:
                     elif kind[l] == 2:
                         self.orphans.append(qid[bi])
                         self.unproc -= 1
+                    elif kind[l] == 4:
+                        ci = jt[l]
+                        assert ci not in touched
+                        touched[ci] = {"fb": -1, "mask": {bi}}
+                        for b3 in range(bi + 1, nq):
+                            if any(cc[0] == ci for cc in static[b3][0]):
+                                dirty.add(b3)
+                        c = self.clusters[ci]
+                        c["members"].append(qid[bi])
+                        c["size"] = _wadd(c["size"], ab[qid[bi]])
+                        self.slot[qid[bi]] = ci
+                        self.unproc -= 1
+                        self.stats["window_joins"] += 1
                     if kind[l] != 0:
                         self.steps += 1
                         self.cur = qid[bi] + 1
@@ -549,3 +580,26 @@ def test_phase2_pairs_from_kept_hits_survive_restarts_and_discarded_batches():
         pairs += len(kept)
         dropped += sum(1 for x, y, sc, tag in m.xhits if m.qbatch[x] >= 0 and m.qbatch[x] != tag)
     assert restarts > 0 and pairs > 0 and dropped > 0
+
+
+@pytest.mark.parametrize("tie_heavy", [False, True])
+def test_phase1_window_join_lanes_extension(tie_heavy):
+    """NOT built: the next step for the resolver proposed in DESIGN.md section 10.  A window lane may also JOIN when its
+    staged best pre-batch cluster is still the true arg-max (none of its candidates touched in this batch), no earlier
+    lane joins that cluster or grows one that ties with it, no cluster born in this batch can reach its score, and the
+    partner -- whichever is still alive -- scores no higher.  Exactness of these conditions, same instances as above."""
+    rng = np.random.default_rng(4242 + tie_heavy)
+    joins = 0
+    for trial in range(60):
+        n = int(rng.integers(20, 160))
+        # big families and no early stop: most queries join a cluster that already exists
+        S, ab, T = _instance(rng, n, int(rng.choice([12, 30, 60])), tie_heavy, asym=bool(trial % 2))
+        if trial % 3 == 0:                     # ... and families that agree internally: long runs of joins to one cluster
+            S = [[v + 12 if v >= T - 3 else v for v in row] for row in S]
+        K = int(rng.choice([max(2, n // 8), n, n]))
+        want = sequential(S, ab, T, K)
+        m = Model(S, ab, T, K, int(rng.choice([8, 16, 64])), int(rng.choice([1, 3, 8])), int(rng.choice([4, 8, 32])), 0,
+                  int(rng.choice([0, 1, 2])), rng, join_lanes=True)
+        assert m.run() == want, (tie_heavy, trial)
+        joins += m.stats["window_joins"]
+    assert joins > 30
