@@ -667,3 +667,57 @@ def test_cpp_loader_odd_headers_tab_format_and_label_filter(tmp_path):
     ordered = hb.sort_sequences(seqs, "size", hb.get_sorted_labels(seqs))
     assert [tuple(l.split("\t")) for l in r.stdout.splitlines()[4:]] == [(s.get_sequence_string(), str(s.size())) for s in ordered]
     assert r.stdout.splitlines()[3].split("\t")[1:] == hb.get_sorted_labels(seqs)
+
+
+def test_struct_layouts_agree_between_header_ctypes_and_java(tmp_path):
+    """the three structs of include/hammock_b200.h as the C compiler lays them out == the ctypes mirrors in _lib.py ==
+    the byte offsets the Java (FFM) bindings write to"""
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "hammock_b200.h")).read()
+    structs = {}
+    for body, name in re.findall(r"typedef struct \{(.*?)\}\s*(hmk_\w+);", hdr, flags=re.S):
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = [re.sub(r"[\s\*]", "", x).split("[")[0] for x in decl.split(",")]
+            names[0] = re.split(r"[\s\*]+", decl.split(",")[0].strip())[-1]
+            fields += names
+        structs[name] = fields
+    assert set(structs) >= {"hmk_greedy_in", "hmk_greedy_out", "hmk_stats"}
+    src = '#include <stddef.h>\n#include <stdio.h>\n#include "hammock_b200.h"\nint main(void) {\n'
+    for name, fields in structs.items():
+        src += f'  printf("{name} size %zu\\n", sizeof({name}));\n'
+        for f in fields:
+            src += f'  printf("{name} {f} %zu\\n", offsetof({name}, {f}));\n'
+    src += "  return 0;\n}\n"
+    (tmp_path / "o.c").write_text(src)
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "o"), str(tmp_path / "o.c")])
+    off = {}
+    for line in subprocess.run([str(tmp_path / "o")], capture_output=True, text=True, check=True).stdout.splitlines():
+        s, f, v = line.split()
+        off[(s, f)] = int(v)
+    for cname, T in (("hmk_greedy_in", _lib.GreedyIn), ("hmk_greedy_out", _lib.GreedyOut), ("hmk_stats", _lib.Stats)):
+        assert [f for f, _ in T._fields_] == structs[cname], cname
+        assert ctypes.sizeof(T) == off[(cname, "size")], cname
+        for f, _ in T._fields_:
+            assert getattr(T, f).offset == off[(cname, f)], (cname, f)
+    # Java: in.set(<layout>, <offset>, <java name>) / out.set(...) / out.get(JAVA_INT, <offset>)
+    jmap = {"n": "n", "residues": "residues", "offsets": "offsets", "abundance": "abundance", "matrix": "matrix", "threshold": "threshold",
+            "maxShift": "max_shift", "shiftPenalty": "shift_penalty", "maxClusters": "max_clusters", "0": "max_clusters",
+            "clusterId": "cluster_id", "memberRank": "member_rank", "resultOrder": "result_order"}
+    jdir = os.path.join(ROOT, "java", "cz", "krejciadam", "hammock")
+    checked = 0
+    for fn in os.listdir(jdir):
+        txt = open(os.path.join(jdir, fn)).read()
+        for var, o, val in re.findall(r"\b(in|out)\.set\(\w+, (\d+), (\w+)\)", txt):
+            sname = "hmk_greedy_in" if var == "in" else "hmk_greedy_out"
+            assert off[(sname, jmap[val])] == int(o), (fn, var, o, val)
+            checked += 1
+        assert re.search(r"nResult = out\.get\(JAVA_INT, %d\)" % off[("hmk_greedy_out", "n_result")], txt), fn
+        m = re.search(r'step " \+ out\.get\(JAVA_INT, (\d+)\)', txt)
+        if m:
+            assert int(m.group(1)) == off[("hmk_greedy_out", "error_step")]
+    assert checked >= 24
