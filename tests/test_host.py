@@ -721,3 +721,22 @@ def test_struct_layouts_agree_between_header_ctypes_and_java(tmp_path):
         if m:
             assert int(m.group(1)) == off[("hmk_greedy_out", "error_step")]
     assert checked >= 24
+
+
+def test_reference_arm_of_the_bench_runs_on_the_cpu():
+    """`bench.py --impl reference` (the arm the driver runs first, on host cores only) prints one JSON line with the keys of
+    the contract -- here on a small debug-sized set so that it takes seconds"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--n", "20000"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "greedy_cluster_unique_seqs_per_sec" and d["unit"] == "seq/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["extrapolated"] is True and "workload" in d["config"]
