@@ -1,6 +1,4 @@
-cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 30 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c31_smoke.log 2>&1
-echo "smoke rc=$?" >> gpurun_out/c31_smoke.log
-timeout 25 python -m pytest tests/test_clinkage.py -m gpu -q -p no:cacheprovider -k "musi or status" > gpurun_out/c31_pytest.log 2>&1
-tail -2 gpurun_out/c31_smoke.log; tail -2 gpurun_out/c31_pytest.log
+timeout 21 python -m pytest -q -x -p no:cacheprovider "tests/test_gpu_parity.py::test_cpp_host_driver_end_to_end" "tests/test_clinkage.py::test_clinkage_gpu_vs_oracle[case9]" "tests/test_clinkage.py::test_clinkage_gpu_vs_oracle[case10]" "tests/test_clinkage.py::test_clinkage_gpu_vs_oracle[case11]" "tests/test_clinkage.py::test_clinkage_gpu_vs_oracle[case12]" > gpurun_out/c32.log 2>&1
+echo "exit $?" >> gpurun_out/c32.log
+tail -5 gpurun_out/c32.log
