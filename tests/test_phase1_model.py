@@ -84,8 +84,9 @@ def sequential(S, ab, T, K):
 
 # ------------------------------------------------------------------------------------------------ the engine's scheme
 class Model:
-    def __init__(self, S, ab, T, K, batch, kb, win, gate, depth, rng, join_lanes=False):
+    def __init__(self, S, ab, T, K, batch, kb, win, gate, depth, rng, join_lanes=False, ranks=1):
         self.S, self.ab, self.T, self.K = S, ab, T, K
+        self.ranks = ranks                         # GPUs: each scores a stripe of the later sequences (section 6)
         # join_lanes: NOT in the kernel -- the extension DESIGN.md section 10 proposes (window lanes that join their best
         # pre-batch cluster), kept here so that its trust conditions stay checked against the sequential loop
         self.join_lanes = join_lanes
@@ -111,19 +112,30 @@ class Model:
         ids = [i for i in range(first, self.n) if slot_seen[i] < 0][:want]
         return ids
 
-    def partner_lists(self, qid, slot_seen, tag):
-        S, ab, T, kb = self.S, self.ab, self.T, self.kb
+    def partner_lists(self, qid, snapshots, tag):
+        """per rank: the best kb hits of ITS stripe of the later sequences, against ITS (possibly stale) view of who is
+        still a singleton; then the exchange: every rank merges all lists -> one list per query, identical everywhere"""
+        S, ab, T, kb, R = self.S, self.ab, self.T, self.kb, len(snapshots)
+        lo0 = qid[0] + 1
+        bounds = [lo0 + (self.n - lo0) * r // R for r in range(R + 1)]          # contiguous stripes of [first query + 1, n)
         lists = []
         for q in qid:
-            hits = sorted((-S[i][q], -ab[i], i) for i in range(q + 1, self.n) if slot_seen[i] < 0 and S[i][q] >= T)
-            self.xhits += [(q, h[2], -h[0], tag) for h in hits]          # before the top-k cut
-            lists.append({"id": [h[2] for h in hits[:kb]], "score": [-h[0] for h in hits[:kb]], "ovf": len(hits) > kb})
+            merged, ovf = [], False
+            for r in range(R):
+                hits = sorted((-S[i][q], -ab[i], i) for i in range(max(q + 1, bounds[r]), bounds[r + 1])
+                              if snapshots[r][i] < 0 and S[i][q] >= T)
+                self.xhits += [(q, h[2], -h[0], tag) for h in hits]      # before the top-k cut
+                merged += hits[:kb]
+                ovf = ovf or len(hits) > kb
+            merged.sort()
+            ovf = ovf or len(merged) > kb                                # hmk_topk_merge: "more existed than the list holds"
+            lists.append({"id": [h[2] for h in merged[:kb]], "score": [-h[0] for h in merged[:kb]], "ovf": ovf})
         return lists
 
-    def stage(self, qid, slot_seen):
+    def stage(self, qid, snapshots):
         S, T = self.S, self.T
         self.batch_id += 1
-        lists = self.partner_lists(qid, slot_seen, self.batch_id)
+        lists = self.partner_lists(qid, snapshots, self.batch_id)
         nq = len(qid)
         ib = [[S[qid[b2]][qid[b]] for b2 in range(nq)] for b in range(nq)]
         pd = [[[S[p][qid[b]] for p in lists[b2]["id"]] for b2 in range(nq)] for b in range(nq)]
@@ -375,52 +387,67 @@ class Model:
 
     # ---- Engine::phase1: the ring of prepared batches
     def run(self):
-        ring = []                                  # prepared batches behind the current one
+        """The look-ahead is issued right behind the resolver of the current batch and runs on the side stream: rank 0's
+        query selection and every rank's partner search see SOME state between that moment and the start of the prepared
+        batch's own resolution -- possibly one resolution later, and a different one on every rank (the ranks' resolvers
+        are replicas, but nothing keeps them in step).  Modelled with a global tick per resolver step / window and a random
+        tick per event, in order per rank (one side stream each); rank 0's selection is what every rank uses."""
+        R = self.ranks
+        ring = []                                  # prepared batches behind the current one, in issue order
+        self.tick = 0
+
+        def advance(force=None):
+            for nb in ring if force is None else [force]:
+                if nb["sel"] is None and (nb is force or self.tick >= nb["sel_at"]):
+                    nb["sel"] = list(self.slot)
+                for r in range(R):
+                    if nb["seen"][r] is None and (nb is force or self.tick >= nb["search_at"][r]):
+                        nb["seen"][r] = list(self.slot)
+
+        def hook(b):
+            self.tick += 1
+            advance()
+
         while len(self.clusters) < self.K and self.unproc > 0:
             if ring:
                 cb = ring.pop(0)
+                advance(force=cb)                  # the main stream waits for the batch's `ready` event
+                qid = self.select(cb["sel"], cb["after"]["qid"][-1] + 1, self.B)
+                assert len(qid) == self.B          # the margin of Engine::phase1 guarantees a full batch
+                cb.update(self.stage(qid, cb["seen"]))
+                self.stats["prepared"] += 1
             else:
                 qid = self.select(self.slot, self.cur, min(self.B, self.unproc))
-                cb = self.stage(qid, self.slot)
+                cb = self.stage(qid, [self.slot] * R)
             nq = len(cb["qid"])
-            unproc_at_issue = self.unproc
-            # the look-ahead is issued right behind the resolver: the side stream sees SOME state of this resolution --
-            # here: the select and the partner search of every prepared batch each at a random step of it
-            plan, prev, s2 = [], cb, 0
+            prev = cb
             for d in range(1, self.depth + 1):
                 if len(ring) >= d:
                     prev = ring[d - 1]
                     continue
-                if len(prev["qid"]) != self.B or unproc_at_issue < nq + (2 + d) * self.B:
+                if (prev["nq"] if "nq" in prev else len(prev["qid"])) != self.B or self.unproc < nq + (2 + d) * self.B:
                     break
-                s1 = int(self.rng.integers(s2, nq + 1))        # one side stream: batch d + 1 is staged behind batch d
-                s2 = int(self.rng.integers(s1, nq + 1))
-                nb = {"pending": True, "after": prev, "s1": s1, "s2": s2, "qid": [0] * self.B}
-                plan.append(nb)
+                horizon = self.tick + 1 + int(self.rng.integers(0, 2 * self.B))
+                last = ring[-1] if ring else None
+                sel_at = int(self.rng.integers(self.tick, horizon + 1))
+                if last is not None:
+                    sel_at = max(sel_at, last["sel_at"])
+                search_at = []
+                for r in range(R):
+                    t = int(self.rng.integers(self.tick, horizon + 1))
+                    if last is not None:
+                        t = max(t, last["search_at"][r])
+                    search_at.append(t)
+                nb = {"after": prev, "nq": self.B, "qid": None, "sel": None, "seen": [None] * R, "sel_at": sel_at, "search_at": search_at}
                 ring.append(nb)
                 prev = nb
-            done_sel, done_search = set(), set()
-
-            def hook(b, final=False):
-                for nb in plan:
-                    if id(nb) not in done_sel and (final or b >= nb["s1"]):
-                        last = nb["after"]["qid"][-1]
-                        nb["qid"] = self.select(self.slot, last + 1, self.B)
-                        assert len(nb["qid"]) == self.B
-                        done_sel.add(id(nb))
-                    if id(nb) not in done_search and (final or b >= nb["s2"]):
-                        nb.update(self.stage(nb["qid"], list(self.slot)))
-                        done_search.add(id(nb))
-                        self.stats["prepared"] += 1
             st = self.resolve(cb, hook)
-            hook(nq, final=True)
             if st != CONTINUE:
                 ring = []
             if st in (NPE, DONE):
                 break
         return {"status": NPE if self.status == NPE else 0, "npe_step": self.npe_step, "steps": self.steps, "orphans": self.orphans,
                 "clusters": [(c["fid"], c["size"], list(c["members"])) for c in self.clusters]}
-
 
     # ---- phase 2's candidate pairs (singleton q, cluster c, min score over the phase-1 members) ...
     def pairs_from_kept_hits(self):
@@ -603,3 +630,28 @@ def test_phase1_window_join_lanes_extension(tie_heavy):
         assert m.run() == want, (tie_heavy, trial)
         joins += m.stats["window_joins"]
     assert joins > 30
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+def test_phase1_scheme_on_several_ranks(ranks):
+    """every rank scores its stripe of the later sequences against ITS OWN stale view of the singletons
+    (the ranks' resolvers are replicas but not in step), keeps its best kb hits per query, and all ranks merge all lists.
+    With rank 0's query selection shared, the merged lists lead the replicated resolver to the sequential result -- and the
+    union of the ranks' kept hits gives phase 2 the candidate pairs of the founder pass."""
+    rng = np.random.default_rng(77 + ranks)
+    prepared = pairs = 0
+    for trial in range(24):
+        n = int(rng.integers(30, 150))
+        S, ab, T = _instance(rng, n, int(rng.choice([5, 12, 30])), bool(trial % 3 == 0), asym=bool(trial % 2))
+        K = int(rng.choice([3, max(1, n // 8), n]))
+        want = sequential(S, ab, T, K)
+        m = Model(S, ab, T, K, int(rng.choice([4, 8, 16])), int(rng.choice([1, 2, 8])), int(rng.choice([0, 4, 32])), 0,
+                  int(rng.choice([1, 2])), rng, ranks=ranks)
+        got = m.run()
+        assert got == want, (ranks, trial)
+        prepared += m.stats["prepared"]
+        if not trial % 2 and got["status"] == 0:
+            kept = m.pairs_from_kept_hits()
+            assert len(kept) == len(set(kept)) and sorted(kept) == sorted(m.pairs_direct()), (ranks, trial)
+            pairs += len(kept)
+    assert prepared > 0 and pairs > 0
